@@ -1,0 +1,253 @@
+"""ctypes binding of libconvexadam_b200.so (include/convexadam_b200.h) over torch tensors.
+
+PyTorch is plumbing here: device memory, the current stream, host<->device copies.  All arithmetic on the hot
+path happens inside the library's sm_100a kernels.  There is NO fallback: if the library is missing, was not
+built for CUDA, or a tensor is not on a CUDA device, the call raises.
+"""
+import ctypes as C
+import os
+from functools import lru_cache
+
+import torch
+import torch.nn.functional as F
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libconvexadam_b200.so")
+
+_vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+_SIGS = {
+    "ca_abi_version": (C.c_int, []),
+    "ca_last_error": (C.c_char_p, []),
+    "ca_is_cuda_build": (C.c_int, []),
+    "ca_mindssc_workspace_bytes": (_sz, [_i, _i, _i]),
+    "ca_mindssc_pooled": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "ca_avgpool3d": (_i, [_vp, _i64, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ca_onehot_pooled": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp, _vp]),
+    "ca_correlate_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "ca_correlate": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "ca_coupled_convex_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "ca_coupled_convex": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "ca_inverse_consistency_workspace_bytes": (_sz, [_i, _i, _i]),
+    "ca_inverse_consistency": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ca_field_affine": (_i, [_vp, _vp, _i64, _i, C.POINTER(_f), C.POINTER(_f), _f, _vp]),
+    "ca_trilinear": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _f, _vp]),
+    "ca_adam_workspace_bytes": (_sz, [_i, _i, _i]),
+    "ca_adam_run": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ca_pack_field": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+}
+EXPORTS = tuple(_SIGS)
+ABI_VERSION = 1
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+@lru_cache(maxsize=64)
+def identity_axes_cpu(h, w, d):
+    """1-D axes (x over d, y over w, z over h) of F.affine_grid(eye, (1,1,h,w,d), align_corners=False), computed
+    by torch on the host exactly as the reference does (utils.py:121, MIND.py:160)."""
+    g = F.affine_grid(torch.eye(3, 4).unsqueeze(0), (1, 1, h, w, d), align_corners=False)[0]
+    return g[0, 0, :, 0].contiguous(), g[0, :, 0, 1].contiguous(), g[:, 0, 0, 2].contiguous()
+
+
+@lru_cache(maxsize=16)
+def disp_mesh_cpu(disp_hw):
+    """disp_mesh_t of MIND.py:127 as a (3, L) fp32 CPU tensor."""
+    S = 2 * disp_hw + 1
+    m = F.affine_grid(disp_hw * torch.eye(3, 4).unsqueeze(0), (1, 1, S, S, S), align_corners=True)
+    return m.permute(0, 4, 1, 2, 3).reshape(3, -1).contiguous()
+
+
+class Lib:
+    """One loaded build of the C ABI.  `expect_cuda=True` (the product) refuses the CPU-emulation test build."""
+
+    def __init__(self, path=LIB_PATH, expect_cuda=True):
+        if not os.path.exists(path):
+            raise NativeError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              f"(nvcc, sm_100a). convexadam_b200 has no CPU fallback.")
+        self.path = path
+        self.dll = C.CDLL(path)
+        for name, (res, args) in _SIGS.items():
+            try:
+                fn = getattr(self.dll, name)
+            except AttributeError as e:
+                raise NativeError(f"{path} does not export {name}") from e
+            fn.restype = res
+            fn.argtypes = args
+        if self.dll.ca_abi_version() != ABI_VERSION:
+            raise NativeError(f"ABI mismatch: library {self.dll.ca_abi_version()} != binding {ABI_VERSION}")
+        self.is_cuda = bool(self.dll.ca_is_cuda_build())
+        if expect_cuda and not self.is_cuda:
+            raise NativeError(f"{path} is not a CUDA build")
+        self._consts = {}
+
+    # -- helpers -----------------------------------------------------------------------------------------
+    def _chk(self, rc):
+        if rc != 0:
+            raise NativeError(f"libconvexadam_b200 error {rc}: {self.dll.ca_last_error().decode()}")
+
+    def _t(self, t, dtype=torch.float32):
+        if not isinstance(t, torch.Tensor):
+            raise TypeError("expected a torch.Tensor")
+        if self.is_cuda and not t.is_cuda:
+            raise NativeError("convexadam_b200 kernels need CUDA tensors (there is no CPU path)")
+        if not self.is_cuda and t.is_cuda:
+            raise NativeError("the CPU-emulation test build got a CUDA tensor")
+        if t.dtype != dtype:
+            raise TypeError(f"expected {dtype}, got {t.dtype}")
+        return t.contiguous()
+
+    def _stream(self, ref):
+        return C.c_void_p(torch.cuda.current_stream(ref.device).cuda_stream) if self.is_cuda else C.c_void_p(0)
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+    def _ws(self, nbytes, ref):
+        return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=ref.device)
+
+    def const(self, key, maker, device):
+        k = (key, str(device))
+        if k not in self._consts:
+            self._consts[k] = tuple(x.to(device) for x in maker())
+        return self._consts[k]
+
+    def identity_axes(self, h, w, d, device):
+        return self.const(("axes", h, w, d), lambda: identity_axes_cpu(h, w, d), device)
+
+    def disp_mesh(self, disp_hw, device):
+        return self.const(("mesh", disp_hw), lambda: (disp_mesh_cpu(disp_hw),), device)[0]
+
+    # -- stages ------------------------------------------------------------------------------------------
+    def mindssc_pooled(self, img, radius, dilation, gs_a, gs_b=0):
+        img = self._t(img)
+        H, W, D = img.shape
+        out_a = torch.empty((12, H // gs_a, W // gs_a, D // gs_a), dtype=torch.float32, device=img.device)
+        out_b = torch.empty((12, H // gs_b, W // gs_b, D // gs_b), dtype=torch.float32, device=img.device) if gs_b else None
+        nb = self.dll.ca_mindssc_workspace_bytes(H, W, D)
+        ws = self._ws(nb, img)
+        self._chk(self.dll.ca_mindssc_pooled(self._p(img), H, W, D, radius, dilation, gs_a, self._p(out_a), gs_b,
+                                            self._p(out_b), self._p(ws), nb, self._stream(img)))
+        return out_a, out_b
+
+    def avgpool3d(self, x, k, stride, pad=0):
+        x = self._t(x)
+        T, H, W = x.shape[-3:]
+        nc = 1
+        for s in x.shape[:-3]:
+            nc *= s
+        o = [(s + 2 * pad - k) // stride + 1 for s in (T, H, W)]
+        out = torch.empty(tuple(x.shape[:-3]) + tuple(o), dtype=torch.float32, device=x.device)
+        self._chk(self.dll.ca_avgpool3d(self._p(x), nc, T, H, W, k, stride, pad, self._p(out), self._stream(x)))
+        return out
+
+    def onehot_pooled(self, labels, lut, weight, gs):
+        labels = self._t(labels)
+        lut = self._t(lut, torch.int32)
+        weight = self._t(weight)
+        H, W, D = labels.shape
+        Cn = weight.numel()
+        out = torch.empty((Cn, H // gs, W // gs, D // gs), dtype=torch.float32, device=labels.device)
+        self._chk(self.dll.ca_onehot_pooled(self._p(labels), H, W, D, self._p(lut), lut.numel(), self._p(weight), Cn, gs,
+                                           self._p(out), self._stream(labels)))
+        return out
+
+    def correlate(self, fix, mov, disp_hw, want_argmin=True, workspace_bytes=None, out=None):
+        fix = self._t(fix)
+        mov = self._t(mov)
+        if fix.shape != mov.shape or fix.dim() != 4:
+            raise ValueError("correlate: fix/mov must both be (C,h,w,d)")
+        Cn, h, w, d = fix.shape
+        L = (2 * disp_hw + 1) ** 3
+        ssd = out if out is not None else torch.empty((L, h, w, d), dtype=torch.float32, device=fix.device)
+        am = torch.empty((h, w, d), dtype=torch.int64, device=fix.device) if want_argmin else None
+        nb = workspace_bytes or self.dll.ca_correlate_workspace_bytes(Cn, h, w, d, disp_hw)
+        ws = self._ws(nb, fix)
+        self._chk(self.dll.ca_correlate(self._p(fix), self._p(mov), Cn, h, w, d, disp_hw, self._p(ssd), self._p(am),
+                                       self._p(ws), nb, self._stream(fix)))
+        return ssd, am
+
+    def coupled_convex(self, ssd, argmin, mesh, disp_hw, want_sel=False):
+        ssd = self._t(ssd)
+        argmin = self._t(argmin, torch.int64)
+        mesh = self._t(mesh.reshape(3, -1))
+        L, h, w, d = ssd.shape
+        if L != (2 * disp_hw + 1) ** 3 or mesh.shape[1] != L:
+            raise ValueError("coupled_convex: label count mismatch")
+        soft = torch.empty((3, h, w, d), dtype=torch.float32, device=ssd.device)
+        sel = torch.empty((6, h, w, d), dtype=torch.int64, device=ssd.device) if want_sel else None
+        nb = self.dll.ca_coupled_convex_workspace_bytes(h, w, d, disp_hw)
+        ws = self._ws(nb, ssd)
+        self._chk(self.dll.ca_coupled_convex(self._p(ssd), self._p(argmin), self._p(mesh), h, w, d, disp_hw, self._p(soft),
+                                            self._p(sel), self._p(ws), nb, self._stream(ssd)))
+        return (soft, sel) if want_sel else soft
+
+    def inverse_consistency(self, f1, f2, iters):
+        f1 = self._t(f1)
+        f2 = self._t(f2)
+        _, h, w, d = f1.shape
+        gx, gy, gz = self.identity_axes(h, w, d, f1.device)
+        o1 = torch.empty_like(f1)
+        o2 = torch.empty_like(f2)
+        nb = self.dll.ca_inverse_consistency_workspace_bytes(h, w, d)
+        ws = self._ws(nb, f1)
+        self._chk(self.dll.ca_inverse_consistency(self._p(f1), self._p(f2), h, w, d, iters, self._p(gx), self._p(gy),
+                                                 self._p(gz), self._p(o1), self._p(o2), self._p(ws), nb, self._stream(f1)))
+        return o1, o2
+
+    def field_affine(self, x, flip=False, div=(1.0, 1.0, 1.0), mul1=(1.0, 1.0, 1.0), mul2=1.0):
+        x = self._t(x)
+        out = torch.empty_like(x)
+        n = x.numel() // 3
+        self._chk(self.dll.ca_field_affine(self._p(x), self._p(out), n, int(flip), (_f * 3)(*div), (_f * 3)(*mul1), mul2,
+                                          self._stream(x)))
+        return out
+
+    def trilinear(self, x, size, post_mul=1.0):
+        x = self._t(x)
+        Cn, ih, iw, idd = x.shape
+        out = torch.empty((Cn,) + tuple(size), dtype=torch.float32, device=x.device)
+        self._chk(self.dll.ca_trilinear(self._p(x), Cn, ih, iw, idd, self._p(out), size[0], size[1], size[2], post_mul,
+                                       self._stream(x)))
+        return out
+
+    def adam_run(self, fix, mov, lambda_weight, p, m, v, first_step, niter, want_grad=False):
+        fix = self._t(fix)
+        mov = self._t(mov)
+        for s in (p, m, v):
+            if not s.is_contiguous() or s.dtype != torch.float32:
+                raise TypeError("adam_run: p, m, v must be contiguous float32 (updated in place)")
+            self._t(s)
+        Cn, ha, wa, da = fix.shape
+        gx, gy, gz = self.identity_axes(ha, wa, da, fix.device)
+        u = torch.empty_like(p)
+        g = torch.empty_like(p) if want_grad else None
+        nb = self.dll.ca_adam_workspace_bytes(ha, wa, da)
+        ws = self._ws(nb, fix)
+        self._chk(self.dll.ca_adam_run(self._p(fix), self._p(mov), Cn, ha, wa, da, lambda_weight, self._p(p), self._p(m),
+                                      self._p(v), first_step, niter, self._p(gx), self._p(gy), self._p(gz), self._p(u),
+                                      self._p(g), self._p(ws), nb, self._stream(fix)))
+        return (u, g) if want_grad else u
+
+    def pack_field(self, field, round_half=False, out=None):
+        field = self._t(field)
+        _, H, W, D = field.shape
+        if out is None:
+            out = torch.empty((H, W, D, 3), dtype=torch.float64, device=field.device)
+        self._chk(self.dll.ca_pack_field(self._p(field), H, W, D, int(round_half), self._p(out), self._stream(field)))
+        return out
+
+
+_LIB = None
+
+
+def get_lib() -> Lib:
+    """The product library: in-tree CUDA build only.  Raises loudly when it (or a GPU) is missing."""
+    global _LIB
+    if _LIB is None:
+        if not torch.cuda.is_available():
+            raise NativeError("convexadam_b200 requires a CUDA device (B200, sm_100a); there is no CPU fallback")
+        _LIB = Lib(LIB_PATH, expect_cuda=True)
+    return _LIB

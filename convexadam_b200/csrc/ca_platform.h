@@ -1,0 +1,69 @@
+// Platform glue for the convexadam_b200 kernels.
+//
+// Product build: nvcc, sm_100a (see __graft_entry__.build()).  The CA_EMU branch exists only so that
+// tests/emu/ can compile the *same kernel sources* with g++ and run them block-by-block on the CPU
+// (fibers = CUDA threads) to debug indexing without a GPU.  The product library is never built with
+// CA_EMU and the Python package refuses to load anything but the CUDA build.
+#pragma once
+
+#ifdef CA_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#define CA_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define CA_DYN_SMEM(T, name)                                        \
+    extern __shared__ __align__(16) unsigned char ca_dyn_smem_raw[]; \
+    T* name = reinterpret_cast<T*>(ca_dyn_smem_raw)
+#endif
+
+#include "../../include/convexadam_b200.h"
+
+// ---- error plumbing (no exceptions across the C ABI) -------------------------------------------------
+void ca_set_error(const char* fmt, ...);
+#define CA_CHECK_ARG(cond, ...)          \
+    do {                                 \
+        if (!(cond)) {                   \
+            ca_set_error(__VA_ARGS__);   \
+            return CA_ERR_BAD_ARGUMENT;  \
+        }                                \
+    } while (0)
+#define CA_CHECK_LAUNCH(what)                                                       \
+    do {                                                                            \
+        cudaError_t e__ = cudaGetLastError();                                       \
+        if (e__ != cudaSuccess) {                                                   \
+            ca_set_error("%s: launch failed: %s", what, cudaGetErrorString(e__));   \
+            return CA_ERR_LAUNCH;                                                   \
+        }                                                                           \
+    } while (0)
+
+// ---- small device helpers ---------------------------------------------------------------------------
+static __host__ __device__ __forceinline__ int ca_min(int a, int b) { return a < b ? a : b; }
+static __host__ __device__ __forceinline__ int ca_max(int a, int b) { return a > b ? a : b; }
+static __host__ __device__ __forceinline__ int ca_clamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+static __host__ __device__ __forceinline__ int64_t ca_divup(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static __host__ __device__ __forceinline__ int ca_roundup4(int a) { return (a + 3) & ~3; }
+
+// x / 27 etc. with IEEE round-to-nearest, never contracted with neighbours (torch: `sum / divide_factor`).
+static __device__ __forceinline__ float ca_div(float a, float b) { return __fdiv_rn(a, b); }
+
+// streaming (read-once) 128-bit load: do not pollute L1
+static __device__ __forceinline__ float4 ca_ld_stream4(const float4* p) {
+#if defined(__CUDA_ARCH__)
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+#else
+    return *p;
+#endif
+}
+static __device__ __forceinline__ float ca_ld_stream1(const float* p) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+#else
+    return *p;
+#endif
+}

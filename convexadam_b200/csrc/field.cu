@@ -1,0 +1,226 @@
+// Coarse-grid field glue kept on the device (no host round trips, unlike the reference's MIND.py:156):
+// inverse consistency, trilinear resize, per-channel affine/flip, output packing.
+//
+//   k_ic_step      inverse_consistency            reference src/convexAdam/convex_adam_utils.py:114-129
+//   k_trilinear    F.interpolate(trilinear)       convex_adam_MIND.py:141,153,182   (ATen UpSample.h:289-305)
+//   k_field_affine (x/scale).flip(1), *scale*gs   convex_adam_MIND.py:134,139,141
+//   k_pack_field   .to(dtype) + np.stack(...,3)   convex_adam_MIND.py:198-202
+// All are elementwise / gather kernels over <= a few million voxels: one thread per output voxel, D fastest.
+#include "ca_platform.h"
+
+#ifndef CA_EMU
+#include <cuda_fp16.h>
+#endif
+
+// ---- shared trilinear sampling helpers (torch grid_sampler_3d, bilinear, zeros padding, align_corners=False) ----
+struct Corner8 {
+    int x0, y0, z0;
+    float w[8];   // tnw, tne, tsw, tse, bnw, bne, bsw, bse  (x fastest)
+};
+
+static __device__ __forceinline__ float ca_unnormalize(float c, int size) {
+    // GridSampler.h:27-36: ((coord + 1) * size - 1) / 2, every op rounded
+    return ca_div(__fsub_rn(__fmul_rn(__fadd_rn(c, 1.f), (float)size), 1.f), 2.f);
+}
+
+static __device__ __forceinline__ void ca_corners(float ix, float iy, float iz, Corner8& k) {
+    const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+    const float x1 = __fadd_rn(fx, 1.f), y1 = __fadd_rn(fy, 1.f), z1 = __fadd_rn(fz, 1.f);
+    // clamp before the int conversion: wildly out-of-range coordinates must stay "out of bounds", not overflow
+    k.x0 = (int)fminf(fmaxf(fx, -2.f), 1.0e9f);
+    k.y0 = (int)fminf(fmaxf(fy, -2.f), 1.0e9f);
+    k.z0 = (int)fminf(fmaxf(fz, -2.f), 1.0e9f);
+    const float ax = __fsub_rn(x1, ix), bx = __fsub_rn(ix, fx);
+    const float ay = __fsub_rn(y1, iy), by = __fsub_rn(iy, fy);
+    const float az = __fsub_rn(z1, iz), bz = __fsub_rn(iz, fz);
+    k.w[0] = __fmul_rn(__fmul_rn(ax, ay), az);
+    k.w[1] = __fmul_rn(__fmul_rn(bx, ay), az);
+    k.w[2] = __fmul_rn(__fmul_rn(ax, by), az);
+    k.w[3] = __fmul_rn(__fmul_rn(bx, by), az);
+    k.w[4] = __fmul_rn(__fmul_rn(ax, ay), bz);
+    k.w[5] = __fmul_rn(__fmul_rn(bx, ay), bz);
+    k.w[6] = __fmul_rn(__fmul_rn(ax, by), bz);
+    k.w[7] = __fmul_rn(__fmul_rn(bx, by), bz);
+}
+
+// ---- inverse consistency: one fixed-point iteration for both fields -------------------------------------------
+__global__ void __launch_bounds__(256) k_ic_step(const float* __restrict__ a, const float* __restrict__ b, int h, int w,
+                                                 int d, const float* __restrict__ gx, const float* __restrict__ gy,
+                                                 const float* __restrict__ gz, float* __restrict__ oa,
+                                                 float* __restrict__ ob) {
+    const int64_t n = (int64_t)h * w * d;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+        const int z = (int)(o % d), y = (int)((o / d) % w), x = (int)(o / ((int64_t)d * w));
+        const float bgx = gx[z], bgy = gy[y], bgz = gz[x];
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const float* self = pass ? b : a;
+            const float* other = pass ? a : b;
+            float* dst = pass ? ob : oa;
+            const float sx = self[o], sy = self[n + o], sz = self[2 * n + o];
+            const float ix = ca_unnormalize(__fadd_rn(bgx, sx), d), iy = ca_unnormalize(__fadd_rn(bgy, sy), w),
+                        iz = ca_unnormalize(__fadd_rn(bgz, sz), h);
+            Corner8 k;
+            ca_corners(ix, iy, iz, k);
+            float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int xx = k.x0 + (t & 1), yy = k.y0 + ((t >> 1) & 1), zz = k.z0 + ((t >> 2) & 1);
+                if (xx >= 0 && xx < d && yy >= 0 && yy < w && zz >= 0 && zz < h) {
+                    const int64_t q = ((int64_t)zz * w + yy) * d + xx;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(__ldg(other + c * n + q), k.w[t]));
+                }
+            }
+            dst[o] = __fmul_rn(0.5f, __fsub_rn(sx, acc[0]));
+            dst[n + o] = __fmul_rn(0.5f, __fsub_rn(sy, acc[1]));
+            dst[2 * n + o] = __fmul_rn(0.5f, __fsub_rn(sz, acc[2]));
+        }
+    }
+}
+
+static inline unsigned field_grid(int64_t n) {
+    int64_t b = ca_divup(n, 256);
+    if (b > 148 * 16) b = 148 * 16;
+    return (unsigned)(b < 1 ? 1 : b);
+}
+
+extern "C" size_t ca_inverse_consistency_workspace_bytes(int h, int w, int d) { return (size_t)h * w * d * 3 * 4 * 2 + 256; }
+
+extern "C" int ca_inverse_consistency(const float* f1, const float* f2, int h, int w, int d, int iters, const float* gx,
+                                      const float* gy, const float* gz, float* o1, float* o2, void* workspace,
+                                      size_t workspace_bytes, ca_stream_t stream) {
+    CA_CHECK_ARG(f1 && f2 && gx && gy && gz && o1 && o2 && workspace, "inverse_consistency: null pointer");
+    CA_CHECK_ARG(h > 0 && w > 0 && d > 0 && iters >= 0, "inverse_consistency: bad dims");
+    if (workspace_bytes < ca_inverse_consistency_workspace_bytes(h, w, d)) {
+        ca_set_error("inverse_consistency: workspace too small");
+        return CA_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n3 = (int64_t)h * w * d * 3;
+    float* wa = (float*)workspace;
+    float* wb = wa + n3;
+    if (iters == 0) {
+        cudaMemcpyAsync(o1, f1, n3 * 4, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(o2, f2, n3 * 4, cudaMemcpyDeviceToDevice, st);
+        return CA_OK;
+    }
+    const float* sa = f1;
+    const float* sb = f2;
+    for (int it = 0; it < iters; ++it) {
+        const bool to_out = ((iters - it) & 1) == 1;
+        float* da = to_out ? o1 : wa;
+        float* db = to_out ? o2 : wb;
+        CA_LAUNCH(k_ic_step, dim3(field_grid(n3 / 3)), dim3(256), 0, st, sa, sb, h, w, d, gx, gy, gz, da, db);
+        CA_CHECK_LAUNCH("inverse_consistency");
+        sa = da;
+        sb = db;
+    }
+    return CA_OK;
+}
+
+// ---- per-channel affine + optional channel flip --------------------------------------------------------------
+struct Affine3 { float div[3], mul1[3], mul2; int flip; };
+
+__global__ void __launch_bounds__(256) k_field_affine(const float* __restrict__ in, float* __restrict__ out, int64_t n,
+                                                      Affine3 p) {
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < 3 * n; o += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(o / n);
+        const int sc = p.flip ? 2 - c : c;
+        float v = in[sc * n + (o - c * n)];
+        v = ca_div(v, p.div[sc]);
+        v = __fmul_rn(v, p.mul1[sc]);
+        v = __fmul_rn(v, p.mul2);
+        out[o] = v;
+    }
+}
+
+extern "C" int ca_field_affine(const float* in, float* out, int64_t n_per_channel, int flip, const float div[3],
+                               const float mul1[3], float mul2, ca_stream_t stream) {
+    CA_CHECK_ARG(in && out && div && mul1 && n_per_channel > 0, "field_affine: bad argument");
+    CA_CHECK_ARG(in != out || !flip, "field_affine: in-place flip is not supported");
+    Affine3 p;
+    for (int i = 0; i < 3; ++i) { p.div[i] = div[i]; p.mul1[i] = mul1[i]; }
+    p.mul2 = mul2;
+    p.flip = flip;
+    CA_LAUNCH(k_field_affine, dim3(field_grid(3 * n_per_channel)), dim3(256), 0, (cudaStream_t)stream, in, out, n_per_channel, p);
+    CA_CHECK_LAUNCH("field_affine");
+    return CA_OK;
+}
+
+// ---- trilinear resize, align_corners=False ----------------------------------------------------------------------
+static __device__ __forceinline__ void ca_src_index(int o, int isz, int osz, float scale, int& i0, int& i1, float& l0, float& l1) {
+    if (isz == osz) { i0 = o; i1 = o; l0 = 1.f; l1 = 0.f; return; }
+    float s = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)o, 0.5f)), 0.5f);
+    s = s < 0.f ? 0.f : s;
+    i0 = (int)s;
+    i1 = i0 + ((i0 < isz - 1) ? 1 : 0);
+    l1 = __fsub_rn(s, (float)i0);
+    l0 = __fsub_rn(1.f, l1);
+}
+
+__global__ void __launch_bounds__(256) k_trilinear(const float* __restrict__ in, int C, int ih, int iw, int id, int oh,
+                                                   int ow, int od, float sh, float sw, float sd, float post_mul,
+                                                   float* __restrict__ out) {
+    const int64_t on = (int64_t)oh * ow * od, inn = (int64_t)ih * iw * id;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < on; o += (int64_t)gridDim.x * blockDim.x) {
+        const int z = (int)(o % od), y = (int)((o / od) % ow), x = (int)(o / ((int64_t)od * ow));
+        int x0, x1, y0, y1, z0, z1;
+        float a0, a1, b0, b1, c0, c1;
+        ca_src_index(x, ih, oh, sh, x0, x1, a0, a1);
+        ca_src_index(y, iw, ow, sw, y0, y1, b0, b1);
+        ca_src_index(z, id, od, sd, z0, z1, c0, c1);
+        for (int c = 0; c < C; ++c) {
+            const float* p = in + c * inn;
+#define CA_AT(X, Y, Z) __ldg(p + ((int64_t)(X) * iw + (Y)) * id + (Z))
+            const float v00 = __fadd_rn(__fmul_rn(c0, CA_AT(x0, y0, z0)), __fmul_rn(c1, CA_AT(x0, y0, z1)));
+            const float v01 = __fadd_rn(__fmul_rn(c0, CA_AT(x0, y1, z0)), __fmul_rn(c1, CA_AT(x0, y1, z1)));
+            const float v10 = __fadd_rn(__fmul_rn(c0, CA_AT(x1, y0, z0)), __fmul_rn(c1, CA_AT(x1, y0, z1)));
+            const float v11 = __fadd_rn(__fmul_rn(c0, CA_AT(x1, y1, z0)), __fmul_rn(c1, CA_AT(x1, y1, z1)));
+#undef CA_AT
+            const float v0 = __fadd_rn(__fmul_rn(b0, v00), __fmul_rn(b1, v01));
+            const float v1 = __fadd_rn(__fmul_rn(b0, v10), __fmul_rn(b1, v11));
+            const float v = __fadd_rn(__fmul_rn(a0, v0), __fmul_rn(a1, v1));
+            out[c * on + o] = __fmul_rn(v, post_mul);
+        }
+    }
+}
+
+extern "C" int ca_trilinear(const float* in, int C, int ih, int iw, int id, float* out, int oh, int ow, int od,
+                            float post_mul, ca_stream_t stream) {
+    CA_CHECK_ARG(in && out, "trilinear: null pointer");
+    CA_CHECK_ARG(C > 0 && ih > 0 && iw > 0 && id > 0 && oh > 0 && ow > 0 && od > 0, "trilinear: bad dims");
+    const float sh = (float)ih / (float)oh, sw = (float)iw / (float)ow, sd = (float)id / (float)od;
+    CA_LAUNCH(k_trilinear, dim3(field_grid((int64_t)oh * ow * od)), dim3(256), 0, (cudaStream_t)stream, in, C, ih, iw, id, oh,
+              ow, od, sh, sw, sd, post_mul, out);
+    CA_CHECK_LAUNCH("trilinear");
+    return CA_OK;
+}
+
+// ---- output packing: (3,H,W,D) f32 -> (H,W,D,3) f64, optionally rounded through half ----------------------------
+static __device__ __forceinline__ float ca_round_half(float v) {
+#ifdef CA_EMU
+    return emu_round_half(v);
+#else
+    return __half2float(__float2half_rn(v));
+#endif
+}
+
+__global__ void __launch_bounds__(256) k_pack_field(const float* __restrict__ f, int64_t n, int round_half,
+                                                    double* __restrict__ out) {
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < 3 * n; o += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = o / 3;
+        const int c = (int)(o - 3 * v);
+        float x = __ldg(f + c * n + v);
+        if (round_half) x = ca_round_half(x);
+        out[o] = (double)x;
+    }
+}
+
+extern "C" int ca_pack_field(const float* field, int H, int W, int D, int round_half, double* out, ca_stream_t stream) {
+    CA_CHECK_ARG(field && out && H > 0 && W > 0 && D > 0, "pack_field: bad argument");
+    const int64_t n = (int64_t)H * W * D;
+    CA_LAUNCH(k_pack_field, dim3(field_grid(3 * n)), dim3(256), 0, (cudaStream_t)stream, field, n, round_half, out);
+    CA_CHECK_LAUNCH("pack_field");
+    return CA_OK;
+}

@@ -1,0 +1,211 @@
+"""Kernel-vs-oracle checks shared by the CPU-emulation tests (tests/test_kernels_emu.py, small sizes, debugging aid)
+and the real GPU parity tests (tests/test_kernels_gpu.py, `-m gpu`).  Every check calls the C ABI through
+convexadam_b200._native.Lib and compares with oracle/ca_oracle.py on the same seeded inputs."""
+import numpy as np
+import torch
+
+from oracle import ca_oracle as orc
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_bits_equal(a, b, what):
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    bad = _bits(a) != _bits(b)
+    if bad.any():
+        idx = np.argwhere(bad)[0]
+        raise AssertionError(f"{what}: {int(bad.sum())}/{bad.size} elements differ bitwise; first at {tuple(idx)}: "
+                             f"{a[tuple(idx)]!r} vs {b[tuple(idx)]!r}; max|diff| {np.abs(a - b).max():.3e}")
+
+
+def T(a, device, dtype=torch.float32):
+    return torch.from_numpy(np.array(a, copy=True, order="C")).to(dtype).to(device)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def rng(seed):
+    return np.random.RandomState(seed)
+
+
+def check_avgpool(lib, device):
+    x = rng(0).randn(3, 13, 11, 17).astype(np.float32)
+    for (k, s, p) in [(3, 1, 1), (2, 2, 0), (6, 6, 0), (5, 1, 2), (4, 1, 2), (3, 3, 0)]:
+        assert_bits_equal(N(lib.avgpool3d(T(x, device), k, s, p)), orc.avgpool3d(x, k, s, p), f"avgpool k{k}s{s}p{p}")
+
+
+def check_mind(lib, device, shape=(22, 18, 26)):
+    img = (rng(1).randn(*shape) * 100).astype(np.float32)
+    for (r, dl) in [(1, 2), (2, 2)]:
+        ref = orc.mindssc(img, r, dl)
+        full, _ = lib.mindssc_pooled(T(img, device), r, dl, 1)
+        assert np.abs(N(full) - ref).max() <= 3e-7, f"mind r{r} d{dl}: {np.abs(N(full) - ref).max()}"
+    ref = orc.mindssc(img, 1, 2)
+    a, b = lib.mindssc_pooled(T(img, device), 1, 2, 3, 2)
+    assert np.abs(N(a) - orc.avgpool3d(ref, 3, 3)).max() <= 3e-7
+    assert np.abs(N(b) - orc.avgpool3d(ref, 2, 2)).max() <= 3e-7
+
+
+def check_correlate(lib, device, cases=((12, 6, 5, 7, 2), (16, 4, 6, 8, 1), (3, 5, 4, 9, 3), (12, 7, 6, 12, 2))):
+    for i, (C, h, w, d, hw) in enumerate(cases):
+        r = rng(10 + i)
+        fix = r.rand(C, h, w, d).astype(np.float32)
+        mov = r.rand(C, h, w, d).astype(np.float32)
+        ssd_o, am_o = orc.correlate(fix, mov, hw, tail=0)
+        ssd, am = lib.correlate(T(fix, device), T(mov, device), hw)
+        assert_bits_equal(N(ssd), ssd_o, f"correlate ssd {(C, h, w, d, hw)}")
+        assert (N(am) == am_o).all(), f"correlate argmin {(C, h, w, d, hw)}"
+        # smallest legal workspace (one (kH,kW) pair per chunk) must give the same bits
+        small = lib.dll.ca_correlate_workspace_bytes(C, h, w, d, hw)
+        ssd2, am2 = lib.correlate(T(fix, device), T(mov, device), hw, workspace_bytes=_min_corr_ws(C, h, w, d, hw))
+        assert_bits_equal(N(ssd2), ssd_o, f"correlate ssd (min workspace) {(C, h, w, d, hw)}")
+        assert (N(am2) == am_o).all()
+        assert small >= _min_corr_ws(C, h, w, d, hw)
+
+
+def _min_corr_ws(C, h, w, d, hw):
+    S = 2 * hw + 1
+    dF = (d + 3) & ~3
+    dP = dF + ((4 + 2 * hw + 3) & ~3) - 4
+    a = lambda v: (v + 255) & ~255
+    plane = h * w * dF * 4
+    return a(C * plane) + a(C * (h + 2 * hw) * (w + 2 * hw) * dP * 4) + 2 * a(S * plane) + a(h * w * d * 8)
+
+
+def check_coupled(lib, device, C=12, h=6, w=7, d=8, hw=2):
+    r = rng(20)
+    fix = r.rand(C, h, w, d).astype(np.float32)
+    mov = r.rand(C, h, w, d).astype(np.float32)
+    ssd_o, am_o = orc.correlate(fix, mov, hw, tail=0)
+    mesh = orc.disp_mesh(hw)
+    soft_o, sel_o = orc.coupled_convex(ssd_o, am_o, mesh, want_sel=True)
+    soft, sel = lib.coupled_convex(T(ssd_o, device), T(am_o, device, torch.int64), T(mesh, device), hw, want_sel=True)
+    assert (N(sel) == sel_o[1:]).all(), "coupled_convex per-pass argmin"
+    assert_bits_equal(N(soft), soft_o, "coupled_convex soft")
+    # ragged voxel count (scalar path of the streaming kernel)
+    h2, w2, d2 = 3, 5, 7
+    fix = r.rand(C, h2, w2, d2).astype(np.float32)
+    mov = r.rand(C, h2, w2, d2).astype(np.float32)
+    ssd_o, am_o = orc.correlate(fix, mov, hw, tail=0)
+    soft_o = orc.coupled_convex(ssd_o, am_o, mesh)
+    soft = lib.coupled_convex(T(ssd_o, device), T(am_o, device, torch.int64), T(mesh, device), hw)
+    assert_bits_equal(N(soft), soft_o, "coupled_convex soft (ragged)")
+
+
+def check_mesh_and_axes(lib, device):
+    for hw in (1, 2, 3, 4, 6, 8):
+        assert_bits_equal(N(lib.disp_mesh(hw, device)), orc.disp_mesh(hw), f"mesh hw={hw}")
+    for (h, w, d) in [(5, 7, 9), (16, 14, 18), (96, 80, 128)]:
+        ax = lib.identity_axes(h, w, d, device)
+        for a, b in zip(ax, orc.identity_axes(h, w, d)):
+            assert_bits_equal(N(a), b, f"identity axes {(h, w, d)}")
+
+
+def check_inverse_consistency(lib, device, shape=(8, 10, 12)):
+    r = rng(30)
+    f1 = (r.randn(3, *shape) * 0.1).astype(np.float32)
+    f2 = (r.randn(3, *shape) * 0.1).astype(np.float32)
+    for iters in (0, 1, 4, 15):
+        o1, o2 = lib.inverse_consistency(T(f1, device), T(f2, device), iters)
+        r1, r2 = orc.inverse_consistency(f1, f2, iters)
+        assert_bits_equal(N(o1), r1, f"inverse_consistency d1 iters={iters}")
+        assert_bits_equal(N(o2), r2, f"inverse_consistency d2 iters={iters}")
+    # far out-of-range displacements sample zeros and must not overflow
+    big = (r.randn(3, *shape) * 50).astype(np.float32)
+    o1, _ = lib.inverse_consistency(T(big, device), T(f2, device), 2)
+    r1, _ = orc.inverse_consistency(big, f2, 2)
+    assert_bits_equal(N(o1), r1, "inverse_consistency out-of-range")
+
+
+def check_trilinear_affine_pack(lib, device):
+    r = rng(40)
+    x = r.randn(3, 8, 7, 9).astype(np.float32)
+    for size in [(16, 14, 18), (17, 15, 19), (4, 3, 4), (8, 7, 9)]:
+        assert_bits_equal(N(lib.trilinear(T(x, device), size)), orc.trilinear(x, size), f"trilinear {size}")
+    got = N(lib.trilinear(T(x, device), (16, 14, 18), post_mul=2.0))
+    assert_bits_equal(got, orc.trilinear(x, (16, 14, 18)) * np.float32(2.0), "trilinear post_mul")
+    scale = np.array([3.5, 3.0, 4.0], np.float32)
+    got = N(lib.field_affine(T(x, device), flip=True, div=tuple(float(s) for s in scale)))
+    assert_bits_equal(got, np.ascontiguousarray((x / scale.reshape(3, 1, 1, 1))[::-1]), "field_affine div+flip")
+    got = N(lib.field_affine(T(x, device), flip=True, mul1=tuple(float(s) for s in scale), mul2=2.0))
+    want = np.ascontiguousarray((x * scale.reshape(3, 1, 1, 1) * np.float32(2.0))[::-1])
+    assert_bits_equal(got, want, "field_affine mul+flip")
+    f = (r.randn(3, 5, 6, 7) * 7).astype(np.float32)
+    p = N(lib.pack_field(T(f, device), False))
+    assert p.dtype == np.float64 and p.shape == (5, 6, 7, 3)
+    assert (p == np.stack([f[0], f[1], f[2]], 3).astype(np.float64)).all()
+    p16 = N(lib.pack_field(T(f, device), True))
+    assert (p16 == np.stack([f[0], f[1], f[2]], 3).astype(np.float16).astype(np.float64)).all()
+
+
+def check_onehot(lib, device):
+    r = rng(50)
+    H, W, D, gs = 8, 6, 10, 2
+    labels = r.randint(0, 6, size=(H, W, D)).astype(np.float32)
+    labels[labels == 3] = 5                      # label 3 absent
+    present = [0, 1, 2, 4, 5]
+    lut = np.full(6, -1, np.int32)
+    lut[present] = np.arange(len(present))
+    weight = r.rand(len(present)).astype(np.float32) * 10
+    onehot = np.stack([(labels == c).astype(np.float32) * weight[i] for i, c in enumerate(present)], 0)
+    want = orc.avgpool3d(onehot, gs, gs)
+    got = N(lib.onehot_pooled(T(labels, device), T(lut, device, torch.int32), T(weight, device), gs))
+    assert_bits_equal(got, want, "onehot_pooled")
+
+
+def check_adam(lib, device, C=12, shape=(10, 12, 14), lam=1.25, steps=(1, 2, 7)):
+    r = rng(60)
+    fix = r.rand(C, *shape).astype(np.float32)
+    mov = r.rand(C, *shape).astype(np.float32)
+    st = orc.AdamState((r.randn(3, *shape) * 1.5).astype(np.float32))
+    for k in range(max(steps)):
+        p0, m0, v0 = st.p.copy(), st.m.copy(), st.v.copy()
+        u_o, g_o = orc.adam_step(st, fix, mov, lam, want_grad=True)
+        if k + 1 not in steps:
+            continue
+        p, m, v = T(p0, device), T(m0, device), T(v0, device)
+        u, g = lib.adam_run(T(fix, device), T(mov, device), lam, p, m, v, k + 1, 1, want_grad=True)
+        assert_bits_equal(N(u), u_o, f"adam u step {k + 1}")
+        gmax = np.abs(g_o).max()
+        assert np.abs(N(g) - g_o).max() <= 5e-6 * gmax, f"adam grad step {k + 1}: {np.abs(N(g) - g_o).max() / gmax:.2e}"
+        # |dp| <= |dg| / eps (eps = 1e-8, lr = 1): the first step (v = 0) amplifies fp32 gradient noise
+        assert np.abs(N(p) - st.p).max() <= (2e-4 if k == 0 else 2e-5), f"adam p step {k + 1}: {np.abs(N(p) - st.p).max():.2e}"
+        assert np.abs(N(m) - st.m).max() <= 1e-6 * max(1.0, np.abs(st.m).max())
+    # several iterations in one call == the same iterations one call at a time
+    p0 = (r.randn(3, *shape) * 1.5).astype(np.float32)
+    pa, ma, va = T(p0, device), T(np.zeros_like(p0), device), T(np.zeros_like(p0), device)
+    ua = lib.adam_run(T(fix, device), T(mov, device), lam, pa, ma, va, 1, 4)
+    pb, mb, vb = T(p0, device), T(np.zeros_like(p0), device), T(np.zeros_like(p0), device)
+    for s in range(1, 5):
+        ub = lib.adam_run(T(fix, device), T(mov, device), lam, pb, mb, vb, s, 1)
+    assert_bits_equal(N(ua), N(ub), "adam multi-step u")
+    assert_bits_equal(N(pa), N(pb), "adam multi-step p")
+
+
+def check_golden_convex_stage(lib, device, g, disp_hw):
+    """Kernels vs the committed reference vectors: stored pooled features -> argmin / disp_soft / IC field."""
+    mesh = T(g["mesh"], device)
+    fs, ms = T(g["fix_s"], device), T(g["mov_s"], device)
+    ssd, am = lib.correlate(fs, ms, disp_hw)
+    assert (N(am) == g["argmin"]).all(), "argmin vs reference golden"
+    got = N(ssd).reshape(-1)[g["ssd_idx"]]
+    assert np.abs(got - g["ssd_val"]).max() <= 2e-6          # only the torch sum(0) tail columns may differ by an ulp
+    assert int((_bits(got) != _bits(g["ssd_val"])).sum()) <= 32
+    soft = lib.coupled_convex(ssd, am, mesh, disp_hw)
+    assert_bits_equal(N(soft), g["soft"], "disp_soft vs reference golden")
+    ssd_, am_ = lib.correlate(ms, fs, disp_hw, out=ssd)
+    assert (N(am_) == g["argmin_"]).all()
+    soft_ = lib.coupled_convex(ssd_, am_, mesh, disp_hw)
+    assert_bits_equal(N(soft_), g["soft_"], "backward disp_soft vs reference golden")
+    _, h, w, d = g["soft"].shape
+    scale = tuple(float(s) for s in (np.array([h - 1, w - 1, d - 1], np.float32) / np.float32(2)))
+    a = lib.field_affine(soft, flip=True, div=scale[::-1] if False else scale)
+    b = lib.field_affine(soft_, flip=True, div=scale)
+    ice, _ = lib.inverse_consistency(a, b, 15)
+    assert_bits_equal(N(ice), g["ice"], "inverse-consistent field vs reference golden")

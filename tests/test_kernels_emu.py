@@ -1,0 +1,32 @@
+"""Runs the product kernel SOURCES under the CUDA-on-CPU shim (tests/emu/) against the oracle.  CPU only, small
+sizes.  This is a debugging aid for indexing/ordering -- the parity tests proper are tests/test_kernels_gpu.py."""
+import pytest
+import torch
+
+from convexadam_b200._native import Lib
+from tests import kernel_checks as kc
+from tests.emu.build_emu import build
+
+DEV = torch.device("cpu")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return Lib(build(), expect_cuda=False)
+
+
+def test_product_binding_rejects_emulation_build(lib):
+    from convexadam_b200._native import NativeError
+    with pytest.raises(NativeError):
+        Lib(lib.path, expect_cuda=True)
+
+
+def test_avgpool(lib): kc.check_avgpool(lib, DEV)
+def test_mind(lib): kc.check_mind(lib, DEV, shape=(14, 12, 18))
+def test_correlate(lib): kc.check_correlate(lib, DEV, cases=((12, 4, 5, 7, 2), (16, 3, 4, 8, 1), (3, 4, 4, 5, 3)))
+def test_coupled(lib): kc.check_coupled(lib, DEV, h=4, w=5, d=8)
+def test_mesh_and_axes(lib): kc.check_mesh_and_axes(lib, DEV)
+def test_inverse_consistency(lib): kc.check_inverse_consistency(lib, DEV, shape=(6, 7, 9))
+def test_trilinear_affine_pack(lib): kc.check_trilinear_affine_pack(lib, DEV)
+def test_onehot(lib): kc.check_onehot(lib, DEV)
+def test_adam(lib): kc.check_adam(lib, DEV, shape=(6, 7, 8), steps=(1, 3))
