@@ -19,6 +19,7 @@ _SIGS = {
     "ca_abi_version": (C.c_int, []),
     "ca_last_error": (C.c_char_p, []),
     "ca_is_cuda_build": (C.c_int, []),
+    "ca_launch_count": (C.c_ulonglong, []),
     "ca_mindssc_workspace_bytes": (_sz, [_i, _i, _i]),
     "ca_mindssc_pooled": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "ca_avgpool3d": (_i, [_vp, _i64, _i, _i, _i, _i, _i, _i, _vp, _vp]),
@@ -81,6 +82,9 @@ class Lib:
         if expect_cuda and not self.is_cuda:
             raise NativeError(f"{path} is not a CUDA build")
         self._consts = {}
+
+    def launch_count(self) -> int:
+        return int(self.dll.ca_launch_count())
 
     # -- helpers -----------------------------------------------------------------------------------------
     def _chk(self, rc):

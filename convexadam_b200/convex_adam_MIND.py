@@ -1,0 +1,175 @@
+"""Drop-in for the reference's src/convexAdam/convex_adam_MIND.py: same entry points (extract_features :22,
+convex_adam_pt :64, convex_adam :205, CLI :251), same defaults, same returned layout -- (H,W,D,3) float64,
+[..., c] = displacement in voxels along array axis c -- computed by the B200 kernels of libconvexadam_b200.
+"""
+import argparse
+import os
+import time
+import warnings
+from pathlib import Path
+from typing import Optional, Union
+
+import numpy as np
+import torch
+
+from . import pipeline
+from ._native import get_lib
+from .convex_adam_utils import MINDSSC, validate_image
+
+warnings.filterwarnings("ignore")
+
+
+def _default_device():
+    return torch.device("cuda" if torch.cuda.is_available() else "cpu")
+
+
+def _require_cuda(device):
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("convexadam_b200 runs on CUDA devices only (B200, sm_100a); there is no CPU path. "
+                           "Use the reference package for CPU execution.")
+    return device
+
+
+def _fill_outside_mask(img, mask, device):
+    """use_mask branch of the reference (MIND.py:36-54): erode the mask, fill the outside with the nearest inside
+    value found on a 2x subsampled grid (scipy EDT on the host), keep the inside.  Host-side, outside the kernels
+    (out of scope for the CUDA path)."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from scipy.ndimage import distance_transform_edt as edt
+
+    H, W, D = img.shape[-3:]
+    avg3 = nn.Sequential(nn.ReplicationPad3d(1), nn.AvgPool3d(3, stride=1)).to(device)
+    m = (avg3(mask.view(1, 1, H, W, D).to(device)) > 0.9).float()
+    _, idx = edt((m[0, 0, ::2, ::2, ::2] == 0).squeeze().cpu().numpy(), return_indices=True)
+    idx = torch.from_numpy(idx).to(device)
+    sub = img[::2, ::2, ::2].to(device).reshape(-1)[idx[0] * D // 2 * W // 2 + idx[1] * D // 2 + idx[2]]
+    filled = F.interpolate(sub.unsqueeze(0).unsqueeze(0), scale_factor=2, mode="trilinear")
+    filled.view(-1)[m.view(-1) != 0] = img.to(device).reshape(-1)[m.view(-1) != 0]
+    return filled[0, 0].contiguous()
+
+
+def extract_features(img_fixed, img_moving, mind_r, mind_d, use_mask, mask_fixed, mask_moving,
+                     device=torch.device("cuda"), dtype=torch.float16):
+    """MIND-SSC features of both images, (1,12,H,W,D) each, cast to `dtype` (reference MIND.py:22-61)."""
+    device = _require_cuda(device)
+    if use_mask:
+        img_fixed = _fill_outside_mask(img_fixed, mask_fixed, device)
+        img_moving = _fill_outside_mask(img_moving, mask_moving, device)
+    ff = MINDSSC(img_fixed.reshape((1, 1) + tuple(img_fixed.shape[-3:])).to(device), mind_r, mind_d, device=device).to(dtype)
+    fm = MINDSSC(img_moving.reshape((1, 1) + tuple(img_moving.shape[-3:])).to(device), mind_r, mind_d, device=device).to(dtype)
+    return ff, fm
+
+
+def convex_adam_pt(
+    img_fixed,
+    img_moving,
+    mind_r: int = 1,
+    mind_d: int = 2,
+    lambda_weight: float = 1.25,
+    grid_sp: int = 6,
+    disp_hw: int = 4,
+    selected_niter: int = 80,
+    selected_smooth: int = 0,
+    grid_sp_adam: int = 2,
+    ic: bool = True,
+    use_mask: bool = False,
+    path_fixed_mask: Optional[Union[Path, str]] = None,
+    path_moving_mask: Optional[Union[Path, str]] = None,
+    dtype: torch.dtype = torch.float16,
+    verbose: bool = False,
+    device: torch.device = None,
+) -> np.ndarray:
+    """Coupled convex optimisation with adam instance optimisation (reference MIND.py:64-202).
+
+    dtype: float32 computes and returns fp32 values (the reference's CPU policy, parity-pinned against it);
+    float16 (the reference's GPU default) currently keeps the cost volume in fp32 and rounds the returned field
+    through half exactly where the reference does (MIND.py:198-200)."""
+    device = _require_cuda(device if device is not None else _default_device())
+    lib = get_lib()
+    img_fixed = validate_image(img_fixed).float()
+    img_moving = validate_image(img_moving).float()
+    if dtype not in (torch.float16, torch.float32):
+        raise ValueError("dtype must be torch.float16 or torch.float32")
+    if img_fixed.dim() != 3 or img_fixed.shape != img_moving.shape:
+        raise ValueError("img_fixed and img_moving must be 3-D volumes of the same shape")
+    prm = pipeline.Params(mind_r, mind_d, lambda_weight, grid_sp, disp_hw, selected_niter, selected_smooth, grid_sp_adam, ic)
+
+    t0 = time.time()
+    with torch.cuda.device(device):
+        fixed_dev = img_fixed.to(device, non_blocking=True).contiguous()
+        moving_dev = img_moving.to(device, non_blocking=True).contiguous()
+        if use_mask:
+            import nibabel as nib
+            mask_fixed = torch.from_numpy(nib.load(path_fixed_mask).get_fdata()).float()
+            mask_moving = torch.from_numpy(nib.load(path_moving_mask).get_fdata()).float()
+            fixed_dev = _fill_outside_mask(fixed_dev, mask_fixed, device)
+            moving_dev = _fill_outside_mask(moving_dev, mask_moving, device)
+        disp = pipeline.register_mind(fixed_dev, moving_dev, prm, lib)
+        packed = lib.pack_field(disp, round_half=(dtype == torch.float16))
+        host = torch.empty(packed.shape, dtype=torch.float64, pin_memory=True)
+        host.copy_(packed, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    if verbose:
+        print(f"case time: {time.time() - t0}")
+    return host.numpy()
+
+
+def convex_adam(
+    path_img_fixed,
+    path_img_moving,
+    mind_r: int = 1,
+    mind_d: int = 2,
+    lambda_weight: float = 1.25,
+    grid_sp: int = 6,
+    disp_hw: int = 4,
+    selected_niter: int = 80,
+    selected_smooth: int = 0,
+    grid_sp_adam: int = 2,
+    ic: bool = True,
+    use_mask: bool = False,
+    path_fixed_mask=None,
+    path_moving_mask=None,
+    result_path="./",
+    verbose: bool = False,
+) -> None:
+    """File-in / disp.nii.gz-out wrapper (reference MIND.py:205-248).  Needs nibabel."""
+    import nibabel as nib
+
+    img_fixed = torch.from_numpy(nib.load(path_img_fixed).get_fdata()).float()
+    img_moving = torch.from_numpy(nib.load(path_img_moving).get_fdata()).float()
+    displacements = convex_adam_pt(img_fixed=img_fixed, img_moving=img_moving, mind_r=mind_r, mind_d=mind_d,
+                                   lambda_weight=lambda_weight, grid_sp=grid_sp, disp_hw=disp_hw,
+                                   selected_niter=selected_niter, selected_smooth=selected_smooth,
+                                   grid_sp_adam=grid_sp_adam, ic=ic, use_mask=use_mask, path_fixed_mask=path_fixed_mask,
+                                   path_moving_mask=path_moving_mask, verbose=verbose)
+    affine = nib.load(path_img_fixed).affine
+    nib.save(nib.Nifti1Image(displacements, affine), os.path.join(result_path, "disp.nii.gz"))
+
+
+def _main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("-f", "--path_img_fixed", type=str, required=True)
+    parser.add_argument("-m", "--path_img_moving", type=str, required=True)
+    parser.add_argument("--mind_r", type=int, default=1)
+    parser.add_argument("--mind_d", type=int, default=2)
+    parser.add_argument("--lambda_weight", type=float, default=1.25)
+    parser.add_argument("--grid_sp", type=int, default=6)
+    parser.add_argument("--disp_hw", type=int, default=4)
+    parser.add_argument("--selected_niter", type=int, default=80)
+    parser.add_argument("--selected_smooth", type=int, default=0)
+    parser.add_argument("--grid_sp_adam", type=int, default=2)
+    parser.add_argument("--ic", choices=("True", "False"), default="True")
+    parser.add_argument("--use_mask", choices=("True", "False"), default="False")
+    parser.add_argument("--path_mask_fixed", type=str, default=None)
+    parser.add_argument("--path_mask_moving", type=str, default=None)
+    parser.add_argument("--result_path", type=str, default="./")
+    a = parser.parse_args()
+    convex_adam(a.path_img_fixed, a.path_img_moving, a.mind_r, a.mind_d, a.lambda_weight, a.grid_sp, a.disp_hw,
+                a.selected_niter, a.selected_smooth, a.grid_sp_adam, a.ic == "True", a.use_mask == "True",
+                a.path_mask_fixed, a.path_mask_moving, a.result_path)
+
+
+if __name__ == "__main__":
+    _main()

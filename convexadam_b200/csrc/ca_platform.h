@@ -12,13 +12,16 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
-#define CA_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define CA_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    (ca_note_launch(), kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__))
 #define CA_DYN_SMEM(T, name)                                        \
     extern __shared__ __align__(16) unsigned char ca_dyn_smem_raw[]; \
     T* name = reinterpret_cast<T*>(ca_dyn_smem_raw)
 #endif
 
 #include "../../include/convexadam_b200.h"
+
+void ca_note_launch();   // counts kernel launches (ca_launch_count) -- the bench reports it
 
 // ---- error plumbing (no exceptions across the C ABI) -------------------------------------------------
 void ca_set_error(const char* fmt, ...);

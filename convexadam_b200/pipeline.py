@@ -1,0 +1,113 @@
+"""Device-resident registration pipeline: the fused form of convex_adam_pt (reference
+src/convexAdam/convex_adam_MIND.py:102-193) over libconvexadam_b200's kernels.
+
+Everything between the host images and the dense field stays on the GPU, on the caller's current stream, with
+no host synchronisation (the reference syncs at utils.py:61 and round-trips the field through the CPU at
+MIND.py:156).  The cost volume (L,h,w,d) is allocated once and reused for the backward direction.
+"""
+from dataclasses import dataclass
+
+import torch
+
+from ._native import Lib, get_lib
+
+
+TIMER = None   # bench.py installs an object with .mark(name) to time stages with CUDA events on the current stream
+
+
+def _mark(name):
+    if TIMER is not None:
+        TIMER.mark(name)
+
+
+@dataclass
+class Params:
+    mind_r: int = 1
+    mind_d: int = 2
+    lambda_weight: float = 1.25
+    grid_sp: int = 6
+    disp_hw: int = 4
+    selected_niter: int = 80
+    selected_smooth: int = 0
+    grid_sp_adam: int = 2
+    ic: bool = True
+
+
+def convex_stage(lib: Lib, fix_s, mov_s, shape, prm: Params, ssd_buf=None):
+    """correlate + coupled_convex (+ inverse consistency + upsampling when prm.ic).  fix_s/mov_s: (C,h,w,d).
+    Returns disp_hr (3,H,W,D) in voxels (or the coarse (3,h,w,d) field in coarse units when ic=False -- the
+    reference's behaviour at MIND.py:143-144)."""
+    H, W, D = shape
+    C, h, w, d = fix_s.shape
+    dev = fix_s.device
+    mesh = lib.disp_mesh(prm.disp_hw, dev)
+    L = (2 * prm.disp_hw + 1) ** 3
+    if ssd_buf is None or ssd_buf.shape != (L, h, w, d):
+        ssd_buf = torch.empty((L, h, w, d), dtype=torch.float32, device=dev)
+    ssd, am = lib.correlate(fix_s, mov_s, prm.disp_hw, out=ssd_buf)
+    _mark("correlate")
+    soft = lib.coupled_convex(ssd, am, mesh, prm.disp_hw)
+    _mark("coupled_convex")
+    if not prm.ic:
+        return soft
+    ssd, am = lib.correlate(mov_s, fix_s, prm.disp_hw, out=ssd_buf)
+    _mark("correlate")
+    soft_ = lib.coupled_convex(ssd, am, mesh, prm.disp_hw)
+    _mark("coupled_convex")
+    # scale = tensor([h-1, w-1, d-1]) / 2 (MIND.py:134); (disp/scale).flip(1) (:139)
+    scale = tuple(float(torch.tensor(float(s - 1)) / 2) for s in (h, w, d))
+    a = lib.field_affine(soft, flip=True, div=scale)
+    b = lib.field_affine(soft_, flip=True, div=scale)
+    ice, _ = lib.inverse_consistency(a, b, 15)
+    # disp_ice.flip(1) * scale * grid_sp, upsampled (:141); mul1 is indexed by the SOURCE channel
+    up = lib.field_affine(ice, flip=True, mul1=scale[::-1], mul2=float(prm.grid_sp))
+    out = lib.trilinear(up, (H, W, D))
+    _mark("inverse_consistency+upsample")
+    return out
+
+
+def adam_stage(lib: Lib, disp_hr, fix_a, mov_a, shape, prm: Params):
+    """Adam instance optimisation (MIND.py:147-191).  disp_hr: (3,*,*,*) start field; fix_a/mov_a: (C,ha,wa,da)."""
+    H, W, D = shape
+    if prm.selected_niter < 1:
+        # the reference reads `disp_sample` after a loop that never ran (MIND.py:181) and dies with a NameError
+        raise ValueError("selected_niter must be >= 1 when lambda_weight > 0")
+    ha, wa, da = fix_a.shape[1:]
+    gsa = float(prm.grid_sp_adam)
+    p = lib.field_affine(lib.trilinear(disp_hr, (ha, wa, da)), div=(gsa, gsa, gsa))      # :153,156
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    u = lib.adam_run(fix_a, mov_a, float(prm.lambda_weight), p, m, v, 1, int(prm.selected_niter))
+    out = lib.trilinear(lib.field_affine(u, mul2=gsa), (H, W, D))                           # :181-182
+    if prm.selected_smooth > 0:
+        if prm.selected_smooth % 2 == 0:
+            print("selected_smooth should be an odd number, adding 1")   # and then, like the reference, not adding it (:185-189)
+        k = int(prm.selected_smooth)
+        for _ in range(3):
+            out = lib.avgpool3d(out, k, 1, k // 2)
+    _mark("adam")
+    return out
+
+
+def register_features(lib: Lib, fix_s, mov_s, fix_a, mov_a, shape, prm: Params, ssd_buf=None):
+    disp = convex_stage(lib, fix_s, mov_s, shape, prm, ssd_buf)
+    if prm.lambda_weight > 0:
+        disp = adam_stage(lib, disp, fix_a, mov_a, shape, prm)
+    return disp
+
+
+def register_mind(fixed_dev, moving_dev, prm: Params, lib: Lib = None, ssd_buf=None):
+    """fixed_dev, moving_dev: (H,W,D) float32 CUDA tensors.  Returns the dense field (3,H',W',D') float32 on the
+    device (voxel units, channel c = displacement along array axis c)."""
+    lib = lib or get_lib()
+    H, W, D = fixed_dev.shape
+    _mark("start")
+    same = prm.grid_sp == prm.grid_sp_adam
+    need_adam = prm.lambda_weight > 0
+    gs_b = 0 if (same or not need_adam) else prm.grid_sp_adam
+    fix_s, fix_a = lib.mindssc_pooled(fixed_dev, prm.mind_r, prm.mind_d, prm.grid_sp, gs_b)
+    mov_s, mov_a = lib.mindssc_pooled(moving_dev, prm.mind_r, prm.mind_d, prm.grid_sp, gs_b)
+    if same:
+        fix_a, mov_a = fix_s, mov_s
+    _mark("mind")
+    return register_features(lib, fix_s, mov_s, fix_a, mov_a, (H, W, D), prm, ssd_buf)

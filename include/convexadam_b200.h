@@ -41,46 +41,54 @@ extern "C" {
 
 typedef void* ca_stream_t; /* cudaStream_t */
 
-int ca_abi_version(void);
-const char* ca_last_error(void);
+#if defined(__GNUC__)
+#define CA_API __attribute__((visibility("default")))
+#else
+#define CA_API
+#endif
+
+CA_API int ca_abi_version(void);
+CA_API const char* ca_last_error(void);
 /* 1 when the library was compiled for the GPU (sm_100a); the test-only CPU emulation build returns 0. */
-int ca_is_cuda_build(void);
+CA_API int ca_is_cuda_build(void);
+/* Number of kernels this library has launched in this process so far (bench.py reports the per-step count). */
+CA_API unsigned long long ca_launch_count(void);
 
 /* ---- MIND-SSC descriptor fused with block-mean pooling (utils.py:24-68 + MIND.py:118-119) -------------------
  * img (H,W,D) f32.  Up to two pooled outputs (pool factor gs_a / gs_b, 0 = absent; 1 = full resolution, i.e. the
  * plain MINDSSC operator).  out_x: planar (12, H/gs, W/gs, D/gs) f32.  Channel order = the reference's (after the
  * permutation at utils.py:66).  Two passes over the image because of the global mean at utils.py:61; the host
  * sync of the reference (.item()) is replaced by a device scalar. */
-size_t ca_mindssc_workspace_bytes(int H, int W, int D);
-int ca_mindssc_pooled(const float* img, int H, int W, int D, int radius, int dilation, int gs_a, float* out_a,
+CA_API size_t ca_mindssc_workspace_bytes(int H, int W, int D);
+CA_API int ca_mindssc_pooled(const float* img, int H, int W, int D, int radius, int dilation, int gs_a, float* out_a,
                       int gs_b, float* out_b, void* workspace, size_t workspace_bytes, ca_stream_t stream);
 
 /* ---- F.avg_pool3d(x, k, stride, padding), count_include_pad=True (torch defaults) -------------------------
  * in (nc, T, H, W) -> out (nc, oT, oH, oW), o = (i + 2*pad - k)/stride + 1.  Exact torch-CPU summation order. */
-int ca_avgpool3d(const float* in, int64_t nc, int T, int H, int W, int k, int stride, int pad, float* out,
+CA_API int ca_avgpool3d(const float* in, int64_t nc, int T, int H, int W, int k, int stride, int pad, float* out,
                  ca_stream_t stream);
 
 /* ---- nnUNet features (nnUNet.py:19-38) fused with avg_pool3d(gs) ------------------------------------------
  * labels (H,W,D) f32 holding integer class ids; lut (n_lut) int32 maps class id -> channel (or -1 = absent);
  * weight (C) f32 is the value a voxel of that class contributes (the reference's 10*weight, already rounded the
  * way the caller's dtype policy wants).  out planar (C, H/gs, W/gs, D/gs). */
-int ca_onehot_pooled(const float* labels, int H, int W, int D, const int32_t* lut, int n_lut, const float* weight,
+CA_API int ca_onehot_pooled(const float* labels, int H, int W, int D, const int32_t* lut, int n_lut, const float* weight,
                      int C, int gs, float* out, ca_stream_t stream);
 
 /* ---- correlate (utils.py:72-89) -----------------------------------------------------------------------------
  * fix, mov: planar (C,h,w,d) f32 coarse features.  ssd: (L,h,w,d) f32, L = (2*disp_hw+1)^3, label
  * l = kD*S*S + kW*S + kH (reference layout).  argmin: (h,w,d) int64, first minimum; may be NULL.
  * Bit-exact restatement of the torch-CPU arithmetic (sequential channel sum, two zero-padded 27-tap sums, /27). */
-size_t ca_correlate_workspace_bytes(int C, int h, int w, int d, int disp_hw);
-int ca_correlate(const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, float* ssd,
+CA_API size_t ca_correlate_workspace_bytes(int C, int h, int w, int d, int disp_hw);
+CA_API int ca_correlate(const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, float* ssd,
                  int64_t* argmin, void* workspace, size_t workspace_bytes, ca_stream_t stream);
 
 /* ---- coupled_convex (utils.py:93-109) -----------------------------------------------------------------------
  * ssd (L,h,w,d); argmin (h,w,d) int64; mesh (3,L) f32 = disp_mesh_t of MIND.py:127 (pass the values torch's
  * affine_grid produces -- they are not integral).  disp_soft: (3,h,w,d) f32 out, coarse-voxel units.
  * sel_out: optional (6,h,w,d) int64, the argmin of each of the six passes (for parity tests). */
-size_t ca_coupled_convex_workspace_bytes(int h, int w, int d, int disp_hw);
-int ca_coupled_convex(const float* ssd, const int64_t* argmin, const float* mesh, int h, int w, int d, int disp_hw,
+CA_API size_t ca_coupled_convex_workspace_bytes(int h, int w, int d, int disp_hw);
+CA_API int ca_coupled_convex(const float* ssd, const int64_t* argmin, const float* mesh, int h, int w, int d, int disp_hw,
                       float* disp_soft, int64_t* sel_out, void* workspace, size_t workspace_bytes,
                       ca_stream_t stream);
 
@@ -88,20 +96,20 @@ int ca_coupled_convex(const float* ssd, const int64_t* argmin, const float* mesh
  * f1, f2: (3,h,w,d) f32, normalised units, channel 0 = x (last array axis) as in the reference call at
  * MIND.py:139.  gx (d), gy (w), gz (h): the identity-grid axes of F.affine_grid(eye, (1,1,h,w,d)).
  * o1, o2: results after `iters` fixed-point iterations.  workspace: 2 * 3*h*w*d floats. */
-size_t ca_inverse_consistency_workspace_bytes(int h, int w, int d);
-int ca_inverse_consistency(const float* f1, const float* f2, int h, int w, int d, int iters, const float* gx,
+CA_API size_t ca_inverse_consistency_workspace_bytes(int h, int w, int d);
+CA_API int ca_inverse_consistency(const float* f1, const float* f2, int h, int w, int d, int iters, const float* gx,
                            const float* gy, const float* gz, float* o1, float* o2, void* workspace,
                            size_t workspace_bytes, ca_stream_t stream);
 
 /* ---- per-channel affine on a 3-channel field, optional channel flip (MIND.py:134,139,141) ---------------------
  * out[c] = (in[flip ? 2-c : c] / div[c']) * mul1[c'] * mul2   with c' = the source channel, applied in that order,
  * each op rounded (div/mul by 1 are exact no-ops). */
-int ca_field_affine(const float* in, float* out, int64_t n_per_channel, int flip, const float div[3],
+CA_API int ca_field_affine(const float* in, float* out, int64_t n_per_channel, int flip, const float div[3],
                     const float mul1[3], float mul2, ca_stream_t stream);
 
 /* ---- F.interpolate(mode='trilinear', align_corners=False) (MIND.py:141,153,182) ------------------------------
  * in (C,ih,iw,id) -> out (C,oh,ow,od);  out = interp(in) * post_mul  (post_mul = 1 for the plain operator). */
-int ca_trilinear(const float* in, int C, int ih, int iw, int id, float* out, int oh, int ow, int od, float post_mul,
+CA_API int ca_trilinear(const float* in, int C, int ih, int iw, int id, float* out, int oh, int ow, int od, float post_mul,
                  ca_stream_t stream);
 
 /* ---- Adam instance optimisation (MIND.py:147-181) ---------------------------------------------------------------
@@ -111,15 +119,15 @@ int ca_trilinear(const float* in, int C, int ih, int iw, int id, float* out, int
  * u_out (3,ha,wa,da): B^3(p) of the LAST forward, i.e. what the reference returns (the final update is applied
  * to p but does not show in u_out, MIND.py:181).  g_out: optional, dL/dp of the last iteration.
  * g0x (da), g0y (wa), g0z (ha): identity-grid axes of affine_grid (MIND.py:160). lr=1, betas=(0.9,0.999), eps=1e-8. */
-size_t ca_adam_workspace_bytes(int ha, int wa, int da);
-int ca_adam_run(const float* fix, const float* mov, int C, int ha, int wa, int da, float lambda_weight, float* p,
+CA_API size_t ca_adam_workspace_bytes(int ha, int wa, int da);
+CA_API int ca_adam_run(const float* fix, const float* mov, int C, int ha, int wa, int da, float lambda_weight, float* p,
                 float* m, float* v, int first_step, int niter, const float* g0x, const float* g0y, const float* g0z,
                 float* u_out, float* g_out, void* workspace, size_t workspace_bytes, ca_stream_t stream);
 
 /* ---- output packing (MIND.py:198-202) --------------------------------------------------------------------------
  * field (3,H,W,D) f32 -> out (H,W,D,3) f64; round_half != 0 rounds every value through IEEE half first
  * (the reference's `.to(dtype)` when dtype=float16). */
-int ca_pack_field(const float* field, int H, int W, int D, int round_half, double* out, ca_stream_t stream);
+CA_API int ca_pack_field(const float* field, int H, int W, int D, int round_half, double* out, ca_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -57,7 +57,9 @@ int lane_id();
 int warp_alive_mask_has(int lane);
 }  // namespace emu
 
-#define CA_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
+void ca_note_launch();
+#define CA_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    (ca_note_launch(), emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); }))
 #define CA_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emu::dyn_smem())
 
 static inline void __syncthreads() { emu::sync_block(); }

@@ -1,0 +1,147 @@
+"""GPU parity tests proper: every kernel of libconvexadam_b200 (through the C ABI) against the CPU oracle on the
+same seeded inputs, against the reference's committed golden vectors, and -- at the BASELINE full size --
+through size-independent properties.  Run with `-m gpu` on the B200 box."""
+import numpy as np
+import pytest
+import torch
+
+from tests import kernel_checks as kc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from convexadam_b200._native import get_lib
+    return get_lib()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def test_avgpool(lib, dev): kc.check_avgpool(lib, dev)
+def test_mind(lib, dev): kc.check_mind(lib, dev, shape=(40, 34, 46))
+def test_mesh_and_axes(lib, dev): kc.check_mesh_and_axes(lib, dev)
+def test_inverse_consistency(lib, dev): kc.check_inverse_consistency(lib, dev, shape=(20, 18, 22))
+def test_trilinear_affine_pack(lib, dev): kc.check_trilinear_affine_pack(lib, dev)
+def test_onehot(lib, dev): kc.check_onehot(lib, dev)
+def test_adam(lib, dev): kc.check_adam(lib, dev, shape=(20, 18, 22), steps=(1, 2, 7))
+def test_adam_16ch(lib, dev): kc.check_adam(lib, dev, C=16, shape=(12, 14, 16), steps=(1, 4))
+
+
+def test_correlate(lib, dev):
+    kc.check_correlate(lib, dev, cases=((12, 10, 9, 14, 3), (16, 6, 7, 8, 1), (3, 5, 6, 9, 4), (12, 12, 10, 16, 2),
+                                        (12, 6, 5, 7, 5), (12, 8, 6, 12, 6), (4, 4, 4, 4, 7), (12, 5, 5, 8, 8)))
+
+
+def test_coupled(lib, dev):
+    kc.check_coupled(lib, dev, h=12, w=10, d=16, hw=3)
+    kc.check_coupled(lib, dev, h=6, w=7, d=9, hw=6)
+
+
+def test_correlate_rejects_bad_arguments(lib, dev):
+    from convexadam_b200._native import NativeError
+    f = torch.zeros(12, 4, 4, 4, device=dev)
+    with pytest.raises(NativeError):
+        lib.correlate(f, f, 9)          # disp_hw outside 1..8
+    with pytest.raises(ValueError):
+        lib.correlate(f, f[:, :2], 2)
+    with pytest.raises(NativeError):
+        lib.correlate(f.cpu(), f.cpu(), 2)   # no CPU path
+
+
+@pytest.mark.parametrize("name,hw", [("pair_gs2_hw3", 3), ("pair_defaults", 4)])
+def test_golden_convex_stage(lib, dev, golden, name, hw):
+    kc.check_golden_convex_stage(lib, dev, golden(name), hw)
+
+
+# ---- BASELINE.json config 2 sizes: size-independent properties ------------------------------------------------
+FULL = dict(C=12, h=96, w=80, d=128, hw=6)
+
+
+@pytest.fixture(scope="module")
+def full_volume(lib, dev):
+    from oracle import ca_oracle as orc
+    g = torch.Generator().manual_seed(5)
+    C, h, w, d, hw = FULL["C"], FULL["h"], FULL["w"], FULL["d"], FULL["hw"]
+    low = torch.rand(2, C, h // 4 + 2, w // 4 + 2, d // 4 + 2, generator=g)
+    smooth = torch.nn.functional.interpolate(low, size=(h, w, d), mode="trilinear", align_corners=True)
+    feats = (0.7 * smooth + 0.3 * torch.rand(2, C, h, w, d, generator=g)).float().contiguous()
+    fix, mov = feats[0], feats[1]
+    ssd, am = lib.correlate(fix.to(dev), mov.to(dev), hw)
+    torch.cuda.synchronize()
+    return fix, mov, ssd, am, orc
+
+
+def test_full_size_correlate_point_samples(full_volume):
+    """1500 random (voxel,label) entries of the 8.6 GB volume, bit-exact against the oracle's 5x5x5 point evaluation
+    (faces, edges and corners of the volume and of the search window included)."""
+    fix, mov, ssd, am, orc = full_volume
+    C, h, w, d, hw = FULL["C"], FULL["h"], FULL["w"], FULL["d"], FULL["hw"]
+    L = (2 * hw + 1) ** 3
+    rs = np.random.RandomState(0)
+    pts = [(rs.randint(L), rs.randint(h), rs.randint(w), rs.randint(d)) for _ in range(1400)]
+    pts += [(l, x, y, z) for l in (0, L - 1, L // 2) for x in (0, h - 1) for y in (0, w - 1) for z in (0, 1, d - 2, d - 1)]
+    idx = torch.tensor(pts, device=ssd.device)
+    got = ssd[idx[:, 0], idx[:, 1], idx[:, 2], idx[:, 3]].cpu().numpy()
+    fn, mn = fix.numpy(), mov.numpy()
+    for (l, x, y, z), gv in zip(pts, got):
+        want = np.float32(orc.correlate_point(fn, mn, hw, l, x, y, z))
+        assert np.float32(gv).view(np.uint32) == want.view(np.uint32), f"ssd[{l},{x},{y},{z}] = {gv!r} vs oracle {want!r}"
+
+
+def test_full_size_argmin_is_first_minimum(full_volume):
+    fix, mov, ssd, am, orc = full_volume
+    ref = torch.empty_like(am)
+    n_chunk = 8
+    hs = ssd.shape[1] // n_chunk
+    for i in range(n_chunk):                               # torch.argmin == first minimum on CUDA as well
+        ref[i * hs:(i + 1) * hs] = torch.argmin(ssd[:, i * hs:(i + 1) * hs], 0)
+    assert bool((ref == am).all())
+
+
+def test_full_size_coupled_sampled_columns(lib, full_volume):
+    """Each of the six passes at 400 random voxels: argmin of ssd + coeff*|mesh - soft|^2 recomputed on the host in
+    the reference's op order from the downloaded cost columns and the kernel's own previous disp_soft."""
+    fix, mov, ssd, am, orc = full_volume
+    hw = FULL["hw"]
+    L, h, w, d = ssd.shape
+    mesh = lib.disp_mesh(hw, ssd.device)
+    soft, sel = lib.coupled_convex(ssd, am, mesh, hw, want_sel=True)
+    rs = np.random.RandomState(1)
+    vox = np.stack([rs.randint(1, h - 1, 400), rs.randint(1, w - 1, 400), rs.randint(1, d - 1, 400)], 1)
+    vt = torch.tensor(vox, device=ssd.device)
+    cols = ssd[:, vt[:, 0], vt[:, 1], vt[:, 2]].cpu().numpy()           # (L, 400)
+    mesh_n = mesh.cpu().numpy()
+    sel_all = torch.cat([am[None], sel], 0).cpu().numpy()                # (7,h,w,d): selection entering pass j
+    coeffs = np.array([0.003, 0.01, 0.03, 0.1, 0.3, 1], np.float32)
+    for j in range(6):
+        prev = sel_all[j]
+        for k, (x, y, z) in enumerate(vox):
+            nb = prev[x - 1:x + 2, y - 1:y + 2, z - 1:z + 2].reshape(-1)
+            s = np.zeros(3, np.float32)
+            for l in nb:                                                 # ascending (dH,dW,dD) 27-tap sum, / 27
+                s = (s + mesh_n[:, l]).astype(np.float32)
+            s = (s / np.float32(27)).astype(np.float32)
+            dd = (mesh_n - s[:, None]).astype(np.float32)
+            q = (dd * dd).astype(np.float32)
+            dist = ((q[0] + q[1]).astype(np.float32) + q[2]).astype(np.float32)
+            cost = (cols[:, k] + (coeffs[j] * dist).astype(np.float32)).astype(np.float32)
+            assert int(np.argmin(cost)) == int(sel_all[j + 1][x, y, z]), f"pass {j} voxel {(x, y, z)}"
+    assert torch.isfinite(soft).all()
+
+
+def test_full_size_identity_pair(lib, dev):
+    """fixed == moving: the zero-displacement label has cost exactly 0 in the interior and wins everywhere it can."""
+    C, h, w, d, hw = 12, 48, 40, 64, 6
+    g = torch.Generator().manual_seed(9)
+    f = torch.rand(C, h, w, d, generator=g).to(dev)
+    ssd, am = lib.correlate(f, f, hw)
+    S = 2 * hw + 1
+    centre = hw * S * S + hw * S + hw
+    assert float(ssd[centre].abs().max()) == 0.0
+    assert bool((am == centre).all())
+    soft = lib.coupled_convex(ssd, am, lib.disp_mesh(hw, dev), hw)
+    assert float(soft.abs().max()) <= 1e-6

@@ -1,0 +1,113 @@
+"""End-to-end parity on the GPU through the reference-facing entry points (convex_adam_pt etc.)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+KW_A = dict(mind_r=1, mind_d=2, lambda_weight=1.25, grid_sp=2, disp_hw=3, selected_smooth=0, grid_sp_adam=2, ic=True)
+KW_B = dict(mind_r=1, mind_d=2, lambda_weight=1.25, grid_sp=6, disp_hw=4, selected_smooth=3, grid_sp_adam=2, ic=True)
+
+
+def api():
+    from convexadam_b200.convex_adam_MIND import convex_adam_pt
+    return convex_adam_pt
+
+
+@pytest.mark.parametrize("name,kw", [("pair_gs2_hw3", KW_A), ("pair_defaults", KW_B)])
+def test_golden_field_niter1(golden, name, kw):
+    # convex stage + B^3, <= 1e-5 voxel vs the reference's CPU fp32 field
+    g = golden(name)
+    got = api()(g["fixed"], g["moving"], selected_niter=1, dtype=torch.float32, **kw)
+    assert got.dtype == np.float64 and got.flags["C_CONTIGUOUS"]
+    assert np.abs(got[::2, ::2, ::2] - g["field_niter1"]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("name,kw", [("pair_gs2_hw3", KW_A), ("pair_defaults", KW_B)])
+def test_golden_field_free_running(golden, name, kw):
+    # free-running Adam inside the pre-chaos window (niter <= 15): <= 1e-3 voxel
+    g = golden(name)
+    got = api()(g["fixed"], g["moving"], selected_niter=int(g["niter"]), dtype=torch.float32, **kw)
+    err = np.abs(got[::2, ::2, ::2] - g["field"]).max()
+    assert err <= 1e-3, err
+
+
+def test_golden_adam_teacher_forced(golden):
+    # SURVEY 7.2 P2 against the reference's own (p, m, v, grad) snapshots
+    from convexadam_b200._native import get_lib
+    lib = get_lib()
+    g = golden("pair_gs2_hw3")
+    dev = torch.device("cuda:0")
+    pf, pm = torch.from_numpy(g["fix_s"]).to(dev), torch.from_numpy(g["mov_s"]).to(dev)
+    for k in (0, 5, 11):
+        p, m, v = (torch.from_numpy(g[f"adam{k}_{n}"].copy()).to(dev) for n in ("p", "m", "v"))
+        u, gr = lib.adam_run(pf, pm, 1.25, p, m, v, k + 1, 1, want_grad=True)
+        gref = g[f"adam{k}_g"]
+        assert np.abs(gr.cpu().numpy() - gref).max() <= 5e-6 * np.abs(gref).max()
+        assert np.abs(p.cpu().numpy() - g[f"adam{k}_p_next"]).max() <= (2e-4 if k == 0 else 2e-5)
+
+
+def test_fp16_output_rounding_and_types(golden):
+    g = golden("pair_gs2_hw3")
+    f32 = api()(g["fixed"], g["moving"], selected_niter=2, dtype=torch.float32, **KW_A)
+    f16 = api()(torch.from_numpy(g["fixed"]), torch.from_numpy(g["moving"]), selected_niter=2, dtype=torch.float16, **KW_A)
+    assert (f16 == f32.astype(np.float16).astype(np.float64)).all()
+
+
+def test_errors_like_the_reference():
+    with pytest.raises(ValueError):
+        api()("not an image", "neither")
+    with pytest.raises(RuntimeError):
+        api()(np.zeros((8, 8, 8)), np.zeros((8, 8, 8)), device=torch.device("cpu"))
+
+
+def test_operator_api_shapes(golden):
+    import torch.nn.functional as F
+    from convexadam_b200.convex_adam_utils import MINDSSC, correlate, coupled_convex, inverse_consistency
+    g = golden("pair_gs2_hw3")
+    dev = torch.device("cuda:0")
+    H, W, D = (int(v) for v in g["shape"])
+    feat = MINDSSC(torch.from_numpy(g["fixed"])[None, None].to(dev), 1, 2, device=dev)
+    assert feat.shape == (1, 12, H, W, D)
+    got = feat[0].reshape(-1)[torch.from_numpy(g["mind_fix_idx"]).to(dev)].cpu().numpy()
+    assert np.abs(got - g["mind_fix_val"]).max() <= 3e-7
+    fs = torch.from_numpy(g["fix_s"])[None].to(dev)
+    ms = torch.from_numpy(g["mov_s"])[None].to(dev)
+    ssd, am = correlate(fs, ms, 3, 2, (H, W, D), 12)
+    assert ssd.shape == (343, H // 2, W // 2, D // 2) and am.dtype == torch.int64
+    mesh = F.affine_grid(3 * torch.eye(3, 4).unsqueeze(0), (1, 1, 7, 7, 7), align_corners=True).permute(0, 4, 1, 2, 3).reshape(3, -1, 1).to(dev)
+    soft = coupled_convex(ssd, am, mesh, 2, (H, W, D))
+    assert soft.shape == (1, 3, H // 2, W // 2, D // 2)
+    assert (soft[0].cpu().numpy().view(np.uint32) == g["soft"].view(np.uint32)).all()
+    a, b = inverse_consistency(soft * 0.01, soft * -0.01, iter=3)
+    assert a.shape == soft.shape and b.shape == soft.shape
+
+
+def test_nnunet_path_vs_oracle():
+    from convexadam_b200.convex_adam_nnUNet import _label_tables, convex_adam_pt
+    from convexadam_b200.synth import make_label_pair
+    from oracle import ca_oracle as orc
+    lf, lm = make_label_pair((32, 32, 40), n_labels=6, seed=2)
+    got = convex_adam_pt(lf, lm, 1.25, 2, 3, 2, 0, 2, True, dtype=torch.float32)
+    pos, weight, lut = _label_tables(lf, lm)
+    w = (10 * weight).numpy()
+    ff = np.stack([(lf.numpy() == int(c)).astype(np.float32) * w[i] for i, c in enumerate(pos)], 0)
+    fm = np.stack([(lm.numpy() == int(c)).astype(np.float32) * w[i] for i, c in enumerate(pos)], 0)
+    want = orc.field_from_features(ff, fm, (32, 32, 40), 1.25, 2, 3, 2, 0, 2, True)
+    assert np.abs(got - want).max() <= 1e-4
+
+
+def test_full_size_translation_and_determinism():
+    """BASELINE config 2 shape, 10 Adam iterations: run-to-run bit identical; a circular shift of (2,-2,2) voxels is
+    recovered in the interior (property check, the oracle cannot run this size in seconds)."""
+    from convexadam_b200.synth import make_pair
+    fixed, _ = make_pair((192, 160, 256), seed=0)
+    moving = torch.roll(fixed, (2, -2, 2), (0, 1, 2))
+    kw = dict(mind_r=1, mind_d=2, lambda_weight=1.25, grid_sp=2, disp_hw=6, selected_niter=10, selected_smooth=0,
+              grid_sp_adam=2, ic=True, dtype=torch.float32)
+    a = api()(fixed, moving, **kw)
+    b = api()(fixed, moving, **kw)
+    assert a.shape == (192, 160, 256, 3) and (a == b).all()
+    core = a[32:-32, 32:-32, 32:-32].reshape(-1, 3)
+    # warped(x) = moving(x + disp): moving(x) = fixed(x - s) => disp = +s
+    assert np.abs(np.median(core, 0) - np.array([2.0, -2.0, 2.0])).max() <= 0.15, np.median(core, 0)
