@@ -32,7 +32,7 @@ _SIGS = {
     "ca_inverse_consistency": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ca_field_affine": (_i, [_vp, _vp, _i64, _i, C.POINTER(_f), C.POINTER(_f), _f, _vp]),
     "ca_trilinear": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _f, _vp]),
-    "ca_adam_workspace_bytes": (_sz, [_i, _i, _i]),
+    "ca_adam_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "ca_adam_run": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ca_pack_field": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
 }
@@ -228,7 +228,7 @@ class Lib:
         gx, gy, gz = self.identity_axes(ha, wa, da, fix.device)
         u = torch.empty_like(p)
         g = torch.empty_like(p) if want_grad else None
-        nb = self.dll.ca_adam_workspace_bytes(ha, wa, da)
+        nb = self.dll.ca_adam_workspace_bytes(Cn, ha, wa, da)
         ws = self._ws(nb, fix)
         self._chk(self.dll.ca_adam_run(self._p(fix), self._p(mov), Cn, ha, wa, da, lambda_weight, self._p(p), self._p(m),
                                       self._p(v), first_step, niter, self._p(gx), self._p(gy), self._p(gz), self._p(u),

@@ -23,77 +23,103 @@ struct AdamGeom {
     float gscale;     // 2 * 12 / (C * N)  (MIND.py:176-177: mean over channels, *12, mean over voxels)
 };
 
-__global__ void __launch_bounds__(128) k_adam_grad(const float* __restrict__ u, const float* __restrict__ fix,
-                                                   const float* __restrict__ mov, AdamGeom g,
+// planar (C,n) -> channel-last (n, CG) float4 groups, zero padded to a multiple of 4 channels: the 8-corner gather
+// of the moving features then costs 8*CG 128-bit loads per voxel instead of 8*C scalar ones.
+__global__ void __launch_bounds__(256) k_planar_to_cl(const float* __restrict__ in, int C, int CG, int64_t n,
+                                                      float4* __restrict__ out) {
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x)
+        for (int cg = 0; cg < CG; ++cg) {
+            float4 o;
+            o.x = (4 * cg + 0 < C) ? __ldg(in + (int64_t)(4 * cg + 0) * n + v) : 0.f;
+            o.y = (4 * cg + 1 < C) ? __ldg(in + (int64_t)(4 * cg + 1) * n + v) : 0.f;
+            o.z = (4 * cg + 2 < C) ? __ldg(in + (int64_t)(4 * cg + 2) * n + v) : 0.f;
+            o.w = (4 * cg + 3 < C) ? __ldg(in + (int64_t)(4 * cg + 3) * n + v) : 0.f;
+            out[v * CG + cg] = o;
+        }
+}
+
+__global__ void __launch_bounds__(128) k_adam_grad(const float* __restrict__ u, const float4* __restrict__ fixcl,
+                                                   const float4* __restrict__ movcl, int CG, AdamGeom g,
                                                    const float* __restrict__ g0x, const float* __restrict__ g0y,
                                                    const float* __restrict__ g0z, float* __restrict__ gu) {
     const int ha = g.ha, wa = g.wa, da = g.da;
-    const int64_t n = (int64_t)ha * wa * da;
-    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
-        const int z = (int)(o % da), y = (int)((o / da) % wa), x = (int)(o / ((int64_t)da * wa));
-        const float u0 = u[o], u1 = u[n + o], u2 = u[2 * n + o];
-        // grid_disp = grid0 + (u/scale).flip(1)   (MIND.py:171), then GridSampler.h:27-36
-        const float cx = __fadd_rn(g0x[z], ca_div(u2, g.sc[2]));
-        const float cy = __fadd_rn(g0y[y], ca_div(u1, g.sc[1]));
-        const float cz = __fadd_rn(g0z[x], ca_div(u0, g.sc[0]));
-        const float ix = ca_div(__fsub_rn(__fmul_rn(__fadd_rn(cx, 1.f), (float)da), 1.f), 2.f);
-        const float iy = ca_div(__fsub_rn(__fmul_rn(__fadd_rn(cy, 1.f), (float)wa), 1.f), 2.f);
-        const float iz = ca_div(__fsub_rn(__fmul_rn(__fadd_rn(cz, 1.f), (float)ha), 1.f), 2.f);
-        const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
-        const float tx = __fsub_rn(ix, fx), ty = __fsub_rn(iy, fy), tz = __fsub_rn(iz, fz);
-        const float sx = __fsub_rn(__fadd_rn(fx, 1.f), ix), sy = __fsub_rn(__fadd_rn(fy, 1.f), iy), sz = __fsub_rn(__fadd_rn(fz, 1.f), iz);
-        const int x0 = (int)fminf(fmaxf(fx, -2.f), 1.0e9f), y0 = (int)fminf(fmaxf(fy, -2.f), 1.0e9f), z0 = (int)fminf(fmaxf(fz, -2.f), 1.0e9f);
-        float wgt[8];
-        wgt[0] = __fmul_rn(__fmul_rn(sx, sy), sz); wgt[1] = __fmul_rn(__fmul_rn(tx, sy), sz);
-        wgt[2] = __fmul_rn(__fmul_rn(sx, ty), sz); wgt[3] = __fmul_rn(__fmul_rn(tx, ty), sz);
-        wgt[4] = __fmul_rn(__fmul_rn(sx, sy), tz); wgt[5] = __fmul_rn(__fmul_rn(tx, sy), tz);
-        wgt[6] = __fmul_rn(__fmul_rn(sx, ty), tz); wgt[7] = __fmul_rn(__fmul_rn(tx, ty), tz);
-        int64_t off[8];
-        bool inb[8];
+    const int n = ha * wa * da;
+    const int z = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int y = (int)blockIdx.y, x = (int)blockIdx.z;
+    if (z >= da) return;
+    const int o = (x * wa + y) * da + z;
+    const float u0 = u[o], u1 = u[n + o], u2 = u[2 * n + o];
+    // grid_disp = grid0 + (u/scale).flip(1)   (MIND.py:171), then GridSampler.h:27-36, every op rounded as torch does
+    const float cx = __fadd_rn(g0x[z], ca_div(u2, g.sc[2]));
+    const float cy = __fadd_rn(g0y[y], ca_div(u1, g.sc[1]));
+    const float cz = __fadd_rn(g0z[x], ca_div(u0, g.sc[0]));
+    const float ix = ca_div(__fsub_rn(__fmul_rn(__fadd_rn(cx, 1.f), (float)da), 1.f), 2.f);
+    const float iy = ca_div(__fsub_rn(__fmul_rn(__fadd_rn(cy, 1.f), (float)wa), 1.f), 2.f);
+    const float iz = ca_div(__fsub_rn(__fmul_rn(__fadd_rn(cz, 1.f), (float)ha), 1.f), 2.f);
+    const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+    const float tx = __fsub_rn(ix, fx), ty = __fsub_rn(iy, fy), tz = __fsub_rn(iz, fz);
+    const float sx = __fsub_rn(__fadd_rn(fx, 1.f), ix), sy = __fsub_rn(__fadd_rn(fy, 1.f), iy), sz = __fsub_rn(__fadd_rn(fz, 1.f), iz);
+    const int x0 = (int)fminf(fmaxf(fx, -2.f), 1.0e9f), y0 = (int)fminf(fmaxf(fy, -2.f), 1.0e9f), z0 = (int)fminf(fmaxf(fz, -2.f), 1.0e9f);
+    float wgt[8];
+    wgt[0] = __fmul_rn(__fmul_rn(sx, sy), sz); wgt[1] = __fmul_rn(__fmul_rn(tx, sy), sz);
+    wgt[2] = __fmul_rn(__fmul_rn(sx, ty), sz); wgt[3] = __fmul_rn(__fmul_rn(tx, ty), sz);
+    wgt[4] = __fmul_rn(__fmul_rn(sx, sy), tz); wgt[5] = __fmul_rn(__fmul_rn(tx, sy), tz);
+    wgt[6] = __fmul_rn(__fmul_rn(sx, ty), tz); wgt[7] = __fmul_rn(__fmul_rn(tx, ty), tz);
+    int off[8];
+    bool inb[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int xx = x0 + (t & 1), yy = y0 + ((t >> 1) & 1), zz = z0 + ((t >> 2) & 1);
+        inb[t] = xx >= 0 && xx < da && yy >= 0 && yy < wa && zz >= 0 && zz < ha;
+        off[t] = inb[t] ? ((zz * wa + yy) * da + xx) * CG : 0;
+    }
+    // d(w_t)/d(ix) = +-(Y_t Z_t) etc.: sum_t val_t dw_t = sum over corner pairs of (val_hi - val_lo) * (product of the other two)
+    const float yz[4] = {sy * sz, ty * sz, sy * tz, ty * tz};
+    const float xz[4] = {sx * sz, tx * sz, sx * tz, tx * tz};
+    const float xy[4] = {sx * sy, tx * sy, sx * ty, tx * ty};
+    float gix = 0.f, giy = 0.f, giz = 0.f;
+    for (int cg = 0; cg < CG; ++cg) {
+        float4 val[8];
+        float4 smp = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-            const int xx = x0 + (t & 1), yy = y0 + ((t >> 1) & 1), zz = z0 + ((t >> 2) & 1);
-            inb[t] = xx >= 0 && xx < da && yy >= 0 && yy < wa && zz >= 0 && zz < ha;
-            off[t] = inb[t] ? ((int64_t)zz * wa + yy) * da + xx : 0;
-        }
-        float gix = 0.f, giy = 0.f, giz = 0.f;
-        for (int c = 0; c < g.C; ++c) {
-            const float* mp = mov + c * n;
-            float val[8];
-            float smp = 0.f;
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                val[t] = inb[t] ? __ldg(mp + off[t]) : 0.f;
-                if (inb[t]) smp = __fadd_rn(smp, __fmul_rn(val[t], wgt[t]));
+            val[t] = inb[t] ? __ldg(movcl + off[t] + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (inb[t]) {   // sample = sum over the in-bounds corners in torch's order (tnw, tne, tsw, tse, bnw, ...)
+                smp.x = __fadd_rn(smp.x, __fmul_rn(val[t].x, wgt[t]));
+                smp.y = __fadd_rn(smp.y, __fmul_rn(val[t].y, wgt[t]));
+                smp.z = __fadd_rn(smp.z, __fmul_rn(val[t].z, wgt[t]));
+                smp.w = __fadd_rn(smp.w, __fmul_rn(val[t].w, wgt[t]));
             }
-            const float r = __fsub_rn(smp, __ldg(fix + c * n + o));
-            // d(sample)/d(ix,iy,iz) of the trilinear interpolant (zeros outside the volume)
-            const float dx = sy * sz * (val[1] - val[0]) + ty * sz * (val[3] - val[2]) + sy * tz * (val[5] - val[4]) + ty * tz * (val[7] - val[6]);
-            const float dy = sx * sz * (val[2] - val[0]) + tx * sz * (val[3] - val[1]) + sx * tz * (val[6] - val[4]) + tx * tz * (val[7] - val[5]);
-            const float dz = sx * sy * (val[4] - val[0]) + tx * sy * (val[5] - val[1]) + sx * ty * (val[6] - val[2]) + tx * ty * (val[7] - val[3]);
-            gix += r * dx; giy += r * dy; giz += r * dz;
         }
-        float grad[3];
-        grad[2] = g.gscale * gix * g.gmul[2];
-        grad[1] = g.gscale * giy * g.gmul[1];
-        grad[0] = g.gscale * giz * g.gmul[0];
-        // diffusion regulariser: d/du_c(x) of lambda * mean_k (u[x+e_k]-u[x])^2, one-sided at the faces
-        const int idx[3] = {x, y, z};
-        const int dims[3] = {ha, wa, da};
-        const int64_t strd[3] = {(int64_t)wa * da, (int64_t)da, 1};
-        const float uc[3] = {u0, u1, u2};
+        const float4 f = __ldg(fixcl + o * CG + cg);
+        const float rx = smp.x - f.x, ry = smp.y - f.y, rz = smp.z - f.z, rw = smp.w - f.w;
+        float dot[8];
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            float gr = 0.f;
+        for (int t = 0; t < 8; ++t) dot[t] = rx * val[t].x + ry * val[t].y + rz * val[t].z + rw * val[t].w;
+        gix += yz[0] * (dot[1] - dot[0]) + yz[1] * (dot[3] - dot[2]) + yz[2] * (dot[5] - dot[4]) + yz[3] * (dot[7] - dot[6]);
+        giy += xz[0] * (dot[2] - dot[0]) + xz[1] * (dot[3] - dot[1]) + xz[2] * (dot[6] - dot[4]) + xz[3] * (dot[7] - dot[5]);
+        giz += xy[0] * (dot[4] - dot[0]) + xy[1] * (dot[5] - dot[1]) + xy[2] * (dot[6] - dot[2]) + xy[3] * (dot[7] - dot[3]);
+    }
+    float grad[3];
+    grad[2] = g.gscale * gix * g.gmul[2];
+    grad[1] = g.gscale * giy * g.gmul[1];
+    grad[0] = g.gscale * giz * g.gmul[0];
+    // diffusion regulariser: d/du_c(x) of lambda * mean_k (u[x+e_k]-u[x])^2, one-sided at the faces
+    const int idx[3] = {x, y, z};
+    const int dims[3] = {ha, wa, da};
+    const int strd[3] = {wa * da, da, 1};
+    const float uc[3] = {u0, u1, u2};
 #pragma unroll
-            for (int ax = 0; ax < 3; ++ax) {
-                float lap = 0.f;
-                if (idx[ax] > 0) lap += uc[ch] - u[ch * n + o - strd[ax]];
-                if (idx[ax] < dims[ax] - 1) lap += uc[ch] - u[ch * n + o + strd[ax]];
-                gr += g.reg[ax] * lap;
-            }
-            gu[ch * n + o] = grad[ch] + gr;
+    for (int ch = 0; ch < 3; ++ch) {
+        float gr = 0.f;
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+            float lap = 0.f;
+            if (idx[ax] > 0) lap += uc[ch] - u[ch * n + o - strd[ax]];
+            if (idx[ax] < dims[ax] - 1) lap += uc[ch] - u[ch * n + o + strd[ax]];
+            gr += g.reg[ax] * lap;
         }
+        gu[ch * n + o] = grad[ch] + gr;
     }
 }
 
@@ -118,7 +144,18 @@ static inline unsigned adam_grid(int64_t n, int block) {
     return (unsigned)(b < 1 ? 1 : b);
 }
 
-extern "C" size_t ca_adam_workspace_bytes(int ha, int wa, int da) { return (size_t)ha * wa * da * 3 * 4 * 3 + 256; }
+int ca_launch_box3_planes(const float* in, int nl, int h, int w, int d, float* out, cudaStream_t st);   // correlate.cu
+
+// one B pass: F.avg_pool3d(x, 3, stride=1, padding=1) on a 3-channel field (MIND.py:166)
+static int box3_field(const float* in, int ha, int wa, int da, float* out, cudaStream_t st) {
+    if ((da & 3) == 0 && ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0) return ca_launch_box3_planes(in, 3, ha, wa, da, out, st);
+    return ca_launch_avgpool3d(in, 3, ha, wa, da, 3, 1, 1, out, st);
+}
+
+extern "C" size_t ca_adam_workspace_bytes(int C, int ha, int wa, int da) {
+    const size_t n = (size_t)ha * wa * da;
+    return n * 3 * 4 * 3 + 2 * n * (size_t)((C + 3) & ~3) * 4 + 1024;
+}
 
 extern "C" int ca_adam_run(const float* fix, const float* mov, int C, int ha, int wa, int da, float lambda_weight, float* p,
                            float* m, float* v, int first_step, int niter, const float* g0x, const float* g0y,
@@ -127,7 +164,8 @@ extern "C" int ca_adam_run(const float* fix, const float* mov, int C, int ha, in
     CA_CHECK_ARG(fix && mov && p && m && v && g0x && g0y && g0z && u_out && workspace, "adam_run: null pointer");
     CA_CHECK_ARG(C > 0 && ha > 1 && wa > 1 && da > 1, "adam_run: bad dims (each Adam-grid axis must be >= 2)");
     CA_CHECK_ARG(first_step >= 1 && niter >= 0, "adam_run: bad step range");
-    if (workspace_bytes < ca_adam_workspace_bytes(ha, wa, da)) {
+    CA_CHECK_ARG((int64_t)ha * wa * da * ((C + 3) / 4) < (1ll << 31) && wa < 65536 && ha < 65536, "adam_run: grid too large");
+    if (workspace_bytes < ca_adam_workspace_bytes(C, ha, wa, da)) {
         ca_set_error("adam_run: workspace too small");
         return CA_ERR_WORKSPACE;
     }
@@ -136,6 +174,15 @@ extern "C" int ca_adam_run(const float* fix, const float* mov, int C, int ha, in
     float* t0 = (float*)workspace;
     float* t1 = t0 + 3 * n;
     float* gu = t1 + 3 * n;
+    const int CG = (C + 3) / 4;
+    float4* fixcl = (float4*)(((uintptr_t)(gu + 3 * n) + 255) & ~(uintptr_t)255);
+    float4* movcl = fixcl + n * CG;
+    if (niter > 0) {
+        const unsigned gb = adam_grid(n, 256);
+        CA_LAUNCH(k_planar_to_cl, dim3(gb), dim3(256), 0, st, fix, C, CG, n, fixcl);
+        CA_LAUNCH(k_planar_to_cl, dim3(gb), dim3(256), 0, st, mov, C, CG, n, movcl);
+        CA_CHECK_LAUNCH("adam/planar_to_cl");
+    }
     AdamGeom g;
     g.ha = ha; g.wa = wa; g.da = da; g.C = C;
     const int dims[3] = {ha, wa, da};
@@ -150,15 +197,17 @@ extern "C" int ca_adam_run(const float* fix, const float* mov, int C, int ha, in
     for (int it = 0; it < niter; ++it) {
         const int step = first_step + it;
         int rc;
-        if ((rc = ca_launch_avgpool3d(p, 3, ha, wa, da, 3, 1, 1, t0, st)) != CA_OK) return rc;
-        if ((rc = ca_launch_avgpool3d(t0, 3, ha, wa, da, 3, 1, 1, t1, st)) != CA_OK) return rc;
-        if ((rc = ca_launch_avgpool3d(t1, 3, ha, wa, da, 3, 1, 1, u_out, st)) != CA_OK) return rc;
-        CA_LAUNCH(k_adam_grad, dim3(adam_grid(n, 128)), dim3(128), 0, st, u_out, fix, mov, g, g0x, g0y, g0z, gu);
+        if ((rc = box3_field(p, ha, wa, da, t0, st)) != CA_OK) return rc;
+        if ((rc = box3_field(t0, ha, wa, da, t1, st)) != CA_OK) return rc;
+        if ((rc = box3_field(t1, ha, wa, da, u_out, st)) != CA_OK) return rc;
+        const int bx = da >= 128 ? 128 : (da >= 64 ? 64 : 32);
+        CA_LAUNCH(k_adam_grad, dim3((unsigned)((da + bx - 1) / bx), (unsigned)wa, (unsigned)ha), dim3(bx), 0, st, u_out, fixcl, movcl, CG,
+                  g, g0x, g0y, g0z, gu);
         CA_CHECK_LAUNCH("adam_grad");
-        if ((rc = ca_launch_avgpool3d(gu, 3, ha, wa, da, 3, 1, 1, t0, st)) != CA_OK) return rc;
-        if ((rc = ca_launch_avgpool3d(t0, 3, ha, wa, da, 3, 1, 1, t1, st)) != CA_OK) return rc;
+        if ((rc = box3_field(gu, ha, wa, da, t0, st)) != CA_OK) return rc;
+        if ((rc = box3_field(t0, ha, wa, da, t1, st)) != CA_OK) return rc;
         float* gp = g_out ? g_out : t0;
-        if ((rc = ca_launch_avgpool3d(t1, 3, ha, wa, da, 3, 1, 1, gp, st)) != CA_OK) return rc;
+        if ((rc = box3_field(t1, ha, wa, da, gp, st)) != CA_OK) return rc;
         AdamScalars s;
         const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
         s.w_lerp = (float)(1.0 - b1);

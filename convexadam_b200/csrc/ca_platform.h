@@ -51,6 +51,17 @@ static __host__ __device__ __forceinline__ int ca_roundup4(int a) { return (a + 
 // x / 27 etc. with IEEE round-to-nearest, never contracted with neighbours (torch: `sum / divide_factor`).
 static __device__ __forceinline__ float ca_div(float a, float b) { return __fdiv_rn(a, b); }
 
+// x / 27 for the 3x3x3 box filters: q0 = RN(x*c), r = fma(-27, q0, x) (exact), q = fma(r, c, q0), c = RN(1/27).
+// Bit-identical to the IEEE division for EVERY finite fp32 x (exhaustively verified over all 2^31 non-negative
+// floats incl. subnormals by tests/div27_exhaustive.c; the ops are sign-symmetric) at 3 instructions instead of the
+// ~12 of __fdiv_rn -- the box filters are issue-bound, so this matters.  (-0 maps to +0: never compared.)
+static __device__ __forceinline__ float ca_div27(float x) {
+    const float c = 1.0f / 27.0f;
+    const float q0 = __fmul_rn(x, c);
+    const float r = __fmaf_rn(-27.0f, q0, x);
+    return __fmaf_rn(r, c, q0);
+}
+
 // streaming (read-once) 128-bit load: do not pollute L1
 static __device__ __forceinline__ float4 ca_ld_stream4(const float4* p) {
 #if defined(__CUDA_ARCH__)

@@ -16,6 +16,8 @@
 // reference's argmin.  Every arithmetic op is an explicit _rn intrinsic: nvcc must not contract them to FMAs.
 #include "ca_platform.h"
 
+#include <cstdlib>
+
 int ca_launch_cost_argmin(const float* ssd, int64_t n, int L, const float* mesh, const float* soft, float coeff,
                           unsigned long long* keys, cudaStream_t st);
 int ca_launch_keys_to_i64(const unsigned long long* keys, int64_t n, int64_t* out, cudaStream_t st);
@@ -36,21 +38,36 @@ __global__ void __launch_bounds__(256) k_pad_features(const float* __restrict__ 
     }
 }
 
+// ---- tile geometry shared by the raw-SSD and box kernels ---------------------------------------------------------
+// A block is (bx, by) threads: bx consecutive z-quads (4 voxels each) x by consecutive y rows; grid = (tiles, h, planes)
+// so that no thread ever needs a 64-bit div/mod (the kernels are issue-bound, index maths must be free).
+struct TileGeom {
+    int zq, nzb, bx, by;
+};
+static TileGeom make_tile(int dF, int nthreads) {
+    TileGeom t;
+    t.zq = dF >> 2;
+    t.bx = 1;
+    while (t.bx < t.zq && t.bx < 32) t.bx <<= 1;
+    t.by = nthreads / t.bx;
+    t.nzb = (t.zq + t.bx - 1) / t.bx;
+    return t;
+}
+
 // raw[(g*S + kD), x, y, z] = sum_c (f_c(x,y,z) - mpad_c(x+kH, y+kW, z+kD))^2 for the pair (kH,kW) = chunk_start+g
-template <int HW>
-__global__ void __launch_bounds__(128) k_raw_ssd(const float* __restrict__ fixp, const float* __restrict__ movp, int C,
-                                                 int h, int w, int d, int dF, int dP, int chunk_start,
-                                                 float* __restrict__ raw) {
+template <int HW, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_raw_ssd(const float* __restrict__ fixp, const float* __restrict__ movp,
+                                                       int C, int h, int w, int d, int dF, int dP, int chunk_start,
+                                                       int zq, int nzb, float* __restrict__ raw) {
     constexpr int S = 2 * HW + 1;
     constexpr int NM = (4 + 2 * HW + 3) & ~3;   // moving values touched by 4 voxels x S shifts, rounded to float4
-    const int zq = dF >> 2;
-    const int64_t nthreads = (int64_t)h * w * zq;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nthreads) return;
-    const int z0 = (int)(t % zq) * 4;
-    const int y = (int)((t / zq) % w);
-    const int x = (int)(t / ((int64_t)zq * w));
-    const int pi = chunk_start + (int)blockIdx.y;
+    const int bz = (int)blockIdx.x % nzb, byi = (int)blockIdx.x / nzb;
+    const int q = bz * (int)blockDim.x + (int)threadIdx.x;
+    const int y = byi * (int)blockDim.y + (int)threadIdx.y;
+    const int x = (int)blockIdx.y;
+    if (q >= zq || y >= w) return;
+    const int z0 = q * 4;
+    const int pi = chunk_start + (int)blockIdx.z;
     const int kH = pi % S, kW = pi / S;
     const int hp = h + 2 * HW, wp = w + 2 * HW;
 
@@ -64,14 +81,16 @@ __global__ void __launch_bounds__(128) k_raw_ssd(const float* __restrict__ fixp,
     const float* mp = movp + ((int64_t)(x + kH) * wp + (y + kW)) * dP + z0;
     const int64_t fstride = (int64_t)h * w * dF, mstride = (int64_t)hp * wp * dP;
     for (int c = 0; c < C; ++c) {
-        const float4 f4 = __ldg(reinterpret_cast<const float4*>(fp + c * fstride));
+        const float4 f4 = __ldg(reinterpret_cast<const float4*>(fp));
         const float f[4] = {f4.x, f4.y, f4.z, f4.w};
         float m[NM];
 #pragma unroll
         for (int j = 0; j < NM / 4; ++j) {
-            const float4 m4 = __ldg(reinterpret_cast<const float4*>(mp + c * mstride) + j);
+            const float4 m4 = __ldg(reinterpret_cast<const float4*>(mp) + j);
             m[4 * j + 0] = m4.x; m[4 * j + 1] = m4.y; m[4 * j + 2] = m4.z; m[4 * j + 3] = m4.w;
         }
+        fp += fstride;
+        mp += mstride;
 #pragma unroll
         for (int k = 0; k < S; ++k)
 #pragma unroll
@@ -80,8 +99,10 @@ __global__ void __launch_bounds__(128) k_raw_ssd(const float* __restrict__ fixp,
                 acc[k][i] = __fadd_rn(acc[k][i], __fmul_rn(df, df));
             }
     }
-    const int64_t plane = (int64_t)h * w * dF;
-    float* rp = raw + (int64_t)blockIdx.y * S * plane + ((int64_t)x * w + y) * dF + z0;
+    // chunk planes carry a zero halo: (h+2, w+2, dF+8), interior at (+1, +1, +4) -- the box filters then need no
+    // bounds checks (the halo is zeroed once per call and never written)
+    const int64_t plane = (int64_t)(h + 2) * (w + 2) * (dF + 8);
+    float* rp = raw + (int64_t)blockIdx.z * S * plane + ((int64_t)(x + 1) * (w + 2) + (y + 1)) * (dF + 8) + 4 + z0;
 #pragma unroll
     for (int k = 0; k < S; ++k) {
         float4 o;
@@ -93,47 +114,71 @@ __global__ void __launch_bounds__(128) k_raw_ssd(const float* __restrict__ fixp,
     }
 }
 
-// One zero-padded box3 pass over nl label planes (h,w,dF) [columns >= d are zero on input].
-// FINAL=false: out has the same (nl,h,w,dF) layout (pad columns written as zero).
-// FINAL=true : plane (g*S + kD) goes to label kD*S*S + chunk_start + g of the (L,h,w,d) volume.
-template <bool FINAL>
-__global__ void __launch_bounds__(256) k_box3_exact(const float* __restrict__ in, int nl, int h, int w, int d, int dF,
-                                                    int S, int chunk_start, float* __restrict__ out) {
-    const int zq = dF >> 2;
-    const int64_t nthreads = (int64_t)nl * h * w * zq;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nthreads) return;
-    const int z0 = (int)(t % zq) * 4;
-    const int y = (int)((t / zq) % w);
-    const int x = (int)((t / ((int64_t)zq * w)) % h);
-    const int l = (int)(t / ((int64_t)zq * w * h));
-    const float* ip = in + (int64_t)l * h * w * dF;
+// One zero-padded box3 pass over label planes, 4 outputs per thread, ascending (dH,dW,dD) sums, exact /27.
+// PADIN : input planes are (h+2, w+2, dF+8) with a zero halo (interior at +1,+1,+4; columns >= d zero): no bounds
+//         checks, 9 rows at constant offsets.  !PADIN: plain (h,w,dF) planes, taps outside the volume skipped.
+// MODE 0: output plane in the padded layout (pad columns written as zero)
+// MODE 1: plane (g*S + kD) goes to label kD*S*S + chunk_start + g of the dense (L,h,w,d) cost volume
+// MODE 2: output plane plain (h,w,dF)
+template <int MODE, bool PADIN>
+__global__ void __launch_bounds__(256) k_box3_exact(const float* __restrict__ in, int h, int w, int d, int dF, int S,
+                                                    int chunk_start, int zq, int nzb, float* __restrict__ out) {
+    const int bz = (int)blockIdx.x % nzb, byi = (int)blockIdx.x / nzb;
+    const int q = bz * (int)blockDim.x + (int)threadIdx.x;
+    const int y = byi * (int)blockDim.y + (int)threadIdx.y;
+    const int x = (int)blockIdx.y;
+    const int l = (int)blockIdx.z;
+    if (q >= zq || y >= w) return;
+    const int z0 = q * 4;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    for (int dx = -1; dx <= 1; ++dx) {
-        const int xx = x + dx;
-        if (xx < 0 || xx >= h) continue;
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int yy = y + dy;
-            if (yy < 0 || yy >= w) continue;
-            const float* row = ip + ((int64_t)xx * w + yy) * dF + z0;
-            const float4 c = *reinterpret_cast<const float4*>(row);
-            const float a = (z0 > 0) ? row[-1] : 0.f;
-            const float b = (z0 + 4 < dF) ? row[4] : 0.f;
-            s0 = __fadd_rn(__fadd_rn(__fadd_rn(s0, a), c.x), c.y);
-            s1 = __fadd_rn(__fadd_rn(__fadd_rn(s1, c.x), c.y), c.z);
-            s2 = __fadd_rn(__fadd_rn(__fadd_rn(s2, c.y), c.z), c.w);
-            s3 = __fadd_rn(__fadd_rn(__fadd_rn(s3, c.z), c.w), b);
+    if (PADIN) {
+        const int wp = w + 2, dp = dF + 8;
+        const float* ip = in + ((int64_t)l * (h + 2) * wp + (int64_t)x * wp + y) * dp + 4 + z0;   // row (x-1, y-1) of the interior
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                const float* row = ip + (dx * wp + dy) * dp;
+                const float a = row[-1];
+                const float4 c = *reinterpret_cast<const float4*>(row);
+                const float b = row[4];
+                s0 = __fadd_rn(__fadd_rn(__fadd_rn(s0, a), c.x), c.y);
+                s1 = __fadd_rn(__fadd_rn(__fadd_rn(s1, c.x), c.y), c.z);
+                s2 = __fadd_rn(__fadd_rn(__fadd_rn(s2, c.y), c.z), c.w);
+                s3 = __fadd_rn(__fadd_rn(__fadd_rn(s3, c.z), c.w), b);
+            }
+    } else {
+        const float* ip = in + (int64_t)l * h * w * dF + z0;
+        const bool has_a = z0 > 0, has_b = z0 + 4 < dF;
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = x + dx;
+            if (xx < 0 || xx >= h) continue;
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int yy = y + dy;
+                if (yy < 0 || yy >= w) continue;
+                const float* row = ip + (xx * w + yy) * dF;
+                const float4 c = *reinterpret_cast<const float4*>(row);
+                const float a = has_a ? row[-1] : 0.f;
+                const float b = has_b ? row[4] : 0.f;
+                s0 = __fadd_rn(__fadd_rn(__fadd_rn(s0, a), c.x), c.y);
+                s1 = __fadd_rn(__fadd_rn(__fadd_rn(s1, c.x), c.y), c.z);
+                s2 = __fadd_rn(__fadd_rn(__fadd_rn(s2, c.y), c.z), c.w);
+                s3 = __fadd_rn(__fadd_rn(__fadd_rn(s3, c.z), c.w), b);
+            }
         }
     }
-    s0 = ca_div(s0, 27.f); s1 = ca_div(s1, 27.f); s2 = ca_div(s2, 27.f); s3 = ca_div(s3, 27.f);
-    if (!FINAL) {
+    s0 = ca_div27(s0); s1 = ca_div27(s1); s2 = ca_div27(s2); s3 = ca_div27(s3);
+    if (MODE == 0 || MODE == 2) {
         float4 o;
         o.x = (z0 + 0 < d) ? s0 : 0.f; o.y = (z0 + 1 < d) ? s1 : 0.f; o.z = (z0 + 2 < d) ? s2 : 0.f; o.w = (z0 + 3 < d) ? s3 : 0.f;
-        *reinterpret_cast<float4*>(out + ((int64_t)l * h * w + (int64_t)x * w + y) * dF + z0) = o;
+        if (MODE == 0)
+            *reinterpret_cast<float4*>(out + ((int64_t)l * (h + 2) * (w + 2) + (int64_t)(x + 1) * (w + 2) + (y + 1)) * (dF + 8) + 4 + z0) = o;
+        else
+            *reinterpret_cast<float4*>(out + ((int64_t)l * h * w + x * w + y) * dF + z0) = o;
     } else {
-        const int g = l / S, kD = l % S;
+        const int g = l / S, kD = l - g * S;
         const int64_t label = (int64_t)kD * S * S + chunk_start + g;
-        float* op = out + (label * h * w + (int64_t)x * w + y) * d + z0;
+        float* op = out + (label * h * w + x * w + y) * d + z0;
         if ((d & 3) == 0) {
             *reinterpret_cast<float4*>(op) = make_float4(s0, s1, s2, s3);
         } else {
@@ -145,10 +190,20 @@ __global__ void __launch_bounds__(256) k_box3_exact(const float* __restrict__ in
     }
 }
 
+// box3 of `nl` planes (h,w,d) with d % 4 == 0 (no pad columns), used by the Adam stage for B^3 (adam.cu)
+int ca_launch_box3_planes(const float* in, int nl, int h, int w, int d, float* out, cudaStream_t st) {
+    const TileGeom t = make_tile(d, 256);
+    auto k = k_box3_exact<2, false>;
+    CA_LAUNCH(k, dim3((unsigned)(t.nzb * ((w + t.by - 1) / t.by)), (unsigned)h, (unsigned)nl), dim3(t.bx, t.by), 0, st, in, h, w, d,
+              d, 1, 0, t.zq, t.nzb, out);
+    CA_CHECK_LAUNCH("box3_planes");
+    return CA_OK;
+}
+
 namespace {
 struct CorrPlan {
     int S, dF, dP, G;
-    size_t off_fix, off_mov, off_raw, off_i1, off_keys, total;
+    size_t off_fix, off_mov, off_raw, off_i1, off_keys, total, chunk_bytes;
 };
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -161,7 +216,9 @@ CorrPlan make_plan(int C, int h, int w, int d, int hw, int G) {
     p.dP = p.dF + ca_roundup4(4 + 2 * hw) - 4;
     const size_t plane = (size_t)h * w * p.dF * 4;
     if (G <= 0) {
-        G = (int)((48u << 20) / (plane * p.S));
+        static int env_g = -1;   // tuning knob: CA_CORR_CHUNK = (kH,kW) pairs per chunk
+        if (env_g < 0) { const char* e = getenv("CA_CORR_CHUNK"); env_g = e ? atoi(e) : 0; }
+        G = env_g > 0 ? env_g : (int)((48u << 20) / ((size_t)(h + 2) * (w + 2) * (p.dF + 8) * 4 * p.S));
         if (G < 1) G = 1;
     }
     if (G > p.S * p.S) G = p.S * p.S;
@@ -169,20 +226,30 @@ CorrPlan make_plan(int C, int h, int w, int d, int hw, int G) {
     size_t o = 0;
     p.off_fix = o; o = align256(o + (size_t)C * plane);
     p.off_mov = o; o = align256(o + (size_t)C * (h + 2 * hw) * (w + 2 * hw) * p.dP * 4);
-    p.off_raw = o; o = align256(o + (size_t)G * p.S * plane);
-    p.off_i1 = o; o = align256(o + (size_t)G * p.S * plane);
+    const size_t pplane = (size_t)(h + 2) * (w + 2) * (p.dF + 8) * 4;   // chunk planes carry a zero halo
+    p.chunk_bytes = (size_t)G * p.S * pplane;
+    p.off_raw = o; o = align256(o + p.chunk_bytes);
+    p.off_i1 = o; o = align256(o + p.chunk_bytes);
     p.off_keys = o; o = align256(o + (size_t)h * w * d * 8);
     p.total = o;
     return p;
 }
 
+static int g_raw_minb = 0;   // tuning knob (CA_RAW_MINB env, read once): min resident blocks per SM of k_raw_ssd
+
 template <int HW>
 void launch_raw(const float* fixp, const float* movp, int C, int h, int w, int d, int dF, int dP, int chunk_start, int g,
                 float* raw, cudaStream_t st) {
-    const int64_t nthreads = (int64_t)h * w * (dF >> 2);
-    auto kfn = k_raw_ssd<HW>;
-    CA_LAUNCH(kfn, dim3((unsigned)ca_divup(nthreads, 128), (unsigned)g), dim3(128), 0, st, fixp, movp, C, h, w, d, dF, dP,
-              chunk_start, raw);
+    const TileGeom t = make_tile(dF, 128);
+    const dim3 grid((unsigned)(t.nzb * ((w + t.by - 1) / t.by)), (unsigned)h, (unsigned)g), block(t.bx, t.by);
+    if (g_raw_minb == 0) {
+        const char* e = getenv("CA_RAW_MINB");
+        g_raw_minb = e ? atoi(e) : 6;
+        if (g_raw_minb != 4 && g_raw_minb != 8) g_raw_minb = 6;
+    }
+    if (g_raw_minb == 4) { auto k = k_raw_ssd<HW, 4>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, dF, dP, chunk_start, t.zq, t.nzb, raw); }
+    else if (g_raw_minb == 8) { auto k = k_raw_ssd<HW, 8>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, dF, dP, chunk_start, t.zq, t.nzb, raw); }
+    else { auto k = k_raw_ssd<HW, 6>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, dF, dP, chunk_start, t.zq, t.nzb, raw); }
 }
 }  // namespace
 
@@ -199,7 +266,7 @@ extern "C" int ca_correlate(const float* fix, const float* mov, int C, int h, in
         ca_set_error("correlate: disp_hw=%d unsupported (1..8)", disp_hw);
         return CA_ERR_UNSUPPORTED;
     }
-    CA_CHECK_ARG((int64_t)h * w * d < (1ll << 31), "correlate: coarse grid too large");
+    CA_CHECK_ARG((int64_t)h * w * ca_roundup4(d) < (1ll << 31) && h < 65536, "correlate: coarse grid too large");
     // largest chunk that fits the caller's workspace (>= 1 pair), capped at the default plan
     CorrPlan p = make_plan(C, h, w, d, disp_hw, 0);
     while (p.total > workspace_bytes && p.G > 1) p = make_plan(C, h, w, d, disp_hw, p.G - 1);
@@ -219,6 +286,11 @@ extern "C" int ca_correlate(const float* fix, const float* mov, int C, int h, in
         CA_LAUNCH(k_pad_features, dim3((unsigned)ca_min((int)ca_divup(tf, 256), 148 * 16)), dim3(256), 0, st, fix, C, h, w, d, 0, p.dF, fixp);
         CA_LAUNCH(k_pad_features, dim3((unsigned)ca_min((int)ca_divup(tm, 256), 148 * 16)), dim3(256), 0, st, mov, C, h, w, d, disp_hw, p.dP, movp);
         CA_CHECK_LAUNCH("correlate/pad");
+        // zero the halos of both chunk buffers once; the kernels only ever write interiors
+        if (cudaMemsetAsync(raw, 0, p.chunk_bytes, st) != cudaSuccess || cudaMemsetAsync(i1, 0, p.chunk_bytes, st) != cudaSuccess) {
+            ca_set_error("correlate: memset failed");
+            return CA_ERR_LAUNCH;
+        }
     }
     for (int cs = 0; cs < npairs; cs += p.G) {
         const int g = ca_min(p.G, npairs - cs);
@@ -234,11 +306,12 @@ extern "C" int ca_correlate(const float* fix, const float* mov, int C, int h, in
         }
         CA_CHECK_LAUNCH("correlate/raw");
         const int nl = g * S;
-        const int64_t nthreads = (int64_t)nl * h * w * (p.dF >> 2);
-        auto k1 = k_box3_exact<false>;
-        auto k2 = k_box3_exact<true>;
-        CA_LAUNCH(k1, dim3((unsigned)ca_divup(nthreads, 256)), dim3(256), 0, st, raw, nl, h, w, d, p.dF, S, cs, i1);
-        CA_LAUNCH(k2, dim3((unsigned)ca_divup(nthreads, 256)), dim3(256), 0, st, i1, nl, h, w, d, p.dF, S, cs, ssd);
+        const TileGeom t = make_tile(p.dF, 256);
+        const dim3 grid((unsigned)(t.nzb * ((w + t.by - 1) / t.by)), (unsigned)h, (unsigned)nl), block(t.bx, t.by);
+        auto k1 = k_box3_exact<0, true>;
+        auto k2 = k_box3_exact<1, true>;
+        CA_LAUNCH(k1, grid, block, 0, st, raw, h, w, d, p.dF, S, cs, t.zq, t.nzb, i1);
+        CA_LAUNCH(k2, grid, block, 0, st, i1, h, w, d, p.dF, S, cs, t.zq, t.nzb, ssd);
         CA_CHECK_LAUNCH("correlate/box3");
     }
     if (argmin) {

@@ -12,43 +12,45 @@
 // libdevice, <= 2 ulp) and the global mean (double here, float cascade there).
 #include "ca_platform.h"
 
-struct MindTable {
-    signed char ia[12], ib[12];   // output channel c = (nb[ia] - nb[ib])^2, nb = the 6-neighbourhood below
-    signed char inv_perm[12];     // un-permuted channel o lives at output channel inv_perm[o]
-    signed char off[6][3];        // neighbour offsets in units of the dilation, (H,W,D)
-};
+// The 6-neighbourhood (units of the dilation, (H,W,D)) and, per OUTPUT channel c (after the permutation at utils.py:66),
+// the two neighbours whose difference is squared: utils.py:30-47 selects the pairs (x>y) & (dist==2) in row-major
+// order.  Hard-wired so that every index is a compile-time constant (registers, no local memory);
+// mind_table_is_consistent() re-derives them the reference's way and ca_mindssc_pooled refuses to run on a mismatch.
+#define MIND_IA {4, 5, 2, 5, 2, 5, 1, 4, 5, 3, 4, 3}
+#define MIND_IB {2, 0, 0, 4, 1, 3, 0, 3, 1, 2, 1, 0}
+#define MIND_INV {6, 2, 4, 11, 9, 10, 0, 7, 1, 8, 5, 3}   /* un-permuted channel o lives at output channel INV[o] */
+#define MIND_OFF {{-1, 0, 0}, {0, 0, -1}, {0, -1, 0}, {0, 0, 1}, {1, 0, 0}, {0, 1, 0}}
 
-// utils.py:30-47: pairs (x>y) & (dist==2) in row-major order, then the permutation at :66
-static MindTable make_mind_table() {
+static bool mind_table_is_consistent() {
     static const int six[6][3] = {{0, 1, 1}, {1, 1, 0}, {1, 0, 1}, {1, 1, 2}, {2, 1, 1}, {1, 2, 1}};
     static const int perm[12] = {6, 8, 1, 11, 2, 10, 0, 7, 9, 4, 5, 3};
-    MindTable t;
+    const int ia[12] = MIND_IA, ib[12] = MIND_IB, inv[12] = MIND_INV, off[6][3] = MIND_OFF;
     int px[12], py[12], n = 0;
     for (int x = 0; x < 6; ++x)
         for (int y = 0; y < 6; ++y) {
             int dist = 0;
             for (int k = 0; k < 3; ++k) dist += (six[x][k] - six[y][k]) * (six[x][k] - six[y][k]);
-            if (x > y && dist == 2) { px[n] = x; py[n] = y; ++n; }
+            if (x > y && dist == 2 && n < 12) { px[n] = x; py[n] = y; ++n; }
         }
-    for (int c = 0; c < 12; ++c) {
-        t.ia[c] = (signed char)px[perm[c]];
-        t.ib[c] = (signed char)py[perm[c]];
-        t.inv_perm[perm[c]] = (signed char)c;
-    }
+    if (n != 12) return false;
+    for (int c = 0; c < 12; ++c)
+        if (ia[c] != px[perm[c]] || ib[c] != py[perm[c]] || inv[perm[c]] != c) return false;
     for (int k = 0; k < 6; ++k)
-        for (int a = 0; a < 3; ++a) t.off[k][a] = (signed char)(six[k][a] - 1);
-    return t;
+        for (int a = 0; a < 3; ++a)
+            if (off[k][a] != six[k][a] - 1) return false;
+    return true;
 }
 
-__global__ void __launch_bounds__(256) k_mind_phase_a(const float* __restrict__ img, int H, int W, int D, int radius,
-                                                      int dil, MindTable tb, float* __restrict__ mind,
-                                                      float* __restrict__ var, double* __restrict__ partial) {
-    __shared__ double red[256];
+// grid (ceil(D/128), W, H), block 128 along D: coalesced rows, no 64-bit index maths
+__global__ void __launch_bounds__(128) k_mind_phase_a(const float* __restrict__ img, int H, int W, int D, int radius,
+                                                      int dil, float* __restrict__ mind, float* __restrict__ var,
+                                                      double* __restrict__ partial) {
+    __shared__ double red[128];
+    constexpr int IA[12] = MIND_IA, IB[12] = MIND_IB, INV[12] = MIND_INV, OFF[6][3] = MIND_OFF;
     const int64_t V = (int64_t)H * W * D;
-    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int z = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, x = (int)blockIdx.z;
     float v = 0.f;
-    if (o < V) {
-        const int z = (int)(o % D), y = (int)((o / D) % W), x = (int)(o / ((int64_t)D * W));
+    if (z < D) {
         float acc[12];
 #pragma unroll
         for (int c = 0; c < 12; ++c) acc[c] = 0.f;
@@ -59,13 +61,13 @@ __global__ void __launch_bounds__(256) k_mind_phase_a(const float* __restrict__ 
                     float nb[6];
 #pragma unroll
                     for (int k = 0; k < 6; ++k) {
-                        const int qx = ca_clamp(tx + dil * tb.off[k][0], 0, H - 1), qy = ca_clamp(ty + dil * tb.off[k][1], 0, W - 1),
-                                  qz = ca_clamp(tz + dil * tb.off[k][2], 0, D - 1);
+                        const int qx = ca_clamp(tx + dil * OFF[k][0], 0, H - 1), qy = ca_clamp(ty + dil * OFF[k][1], 0, W - 1),
+                                  qz = ca_clamp(tz + dil * OFF[k][2], 0, D - 1);
                         nb[k] = __ldg(img + ((int64_t)qx * W + qy) * D + qz);
                     }
 #pragma unroll
                     for (int c = 0; c < 12; ++c) {
-                        const float df = __fsub_rn(nb[tb.ia[c]], nb[tb.ib[c]]);
+                        const float df = __fsub_rn(nb[IA[c]], nb[IB[c]]);
                         acc[c] = __fadd_rn(acc[c], __fmul_rn(df, df));
                     }
                 }
@@ -81,19 +83,20 @@ __global__ void __launch_bounds__(256) k_mind_phase_a(const float* __restrict__ 
         for (int c = 0; c < 12; ++c) acc[c] = __fsub_rn(acc[c], mn);
         float s = 0.f;
 #pragma unroll
-        for (int oc = 0; oc < 12; ++oc) s = __fadd_rn(s, acc[tb.inv_perm[oc]]);   // torch.mean(mind, 1): un-permuted order
+        for (int oc = 0; oc < 12; ++oc) s = __fadd_rn(s, acc[INV[oc]]);   // torch.mean(mind, 1): un-permuted order
         v = ca_div(s, 12.f);
+        const int64_t o = ((int64_t)x * W + y) * D + z;
 #pragma unroll
         for (int c = 0; c < 12; ++c) mind[c * V + o] = acc[c];
         var[o] = v;
     }
-    red[threadIdx.x] = (o < V) ? (double)v : 0.0;
+    red[threadIdx.x] = (z < D) ? (double)v : 0.0;
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
+    for (int s = 64; s > 0; s >>= 1) {
         if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
         __syncthreads();
     }
-    if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+    if (threadIdx.x == 0) partial[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = red[0];
 }
 
 // stats[0] = lo, stats[1] = hi  (utils.py:61: clamp(mind_var, mean*0.001, mean*1000), mean via .item() -> double)
@@ -115,37 +118,38 @@ __global__ void __launch_bounds__(1024) k_mind_stats(const double* __restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(256) k_mind_phase_b(const float* __restrict__ mind, const float* __restrict__ var,
+// grid (ceil(d/128), w, h), block 128 along the pooled D axis
+__global__ void __launch_bounds__(128) k_mind_phase_b(const float* __restrict__ mind, const float* __restrict__ var,
                                                       const float* __restrict__ stats, int H, int W, int D, int gs, int h,
                                                       int w, int d, float* __restrict__ out) {
     const int64_t V = (int64_t)H * W * D, n = (int64_t)h * w * d;
     const float lo = stats[0], hi = stats[1];
     const float cnt = (float)(gs * gs * gs);
-    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
-        const int z = (int)(o % d), y = (int)((o / d) % w), x = (int)(o / ((int64_t)d * w));
-        float acc[12];
+    const int z = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, x = (int)blockIdx.z;
+    if (z >= d) return;
+    float acc[12];
 #pragma unroll
-        for (int c = 0; c < 12; ++c) acc[c] = 0.f;
-        for (int a = 0; a < gs; ++a)
-            for (int b = 0; b < gs; ++b)
-                for (int e = 0; e < gs; ++e) {
-                    const int64_t q = ((int64_t)(x * gs + a) * W + (y * gs + b)) * D + (z * gs + e);
-                    float vv = __ldg(var + q);
-                    vv = vv < lo ? lo : (vv > hi ? hi : vv);
+    for (int c = 0; c < 12; ++c) acc[c] = 0.f;
+    for (int a = 0; a < gs; ++a)
+        for (int b = 0; b < gs; ++b)
+            for (int e = 0; e < gs; ++e) {
+                const int64_t q = ((int64_t)(x * gs + a) * W + (y * gs + b)) * D + (z * gs + e);
+                float vv = __ldg(var + q);
+                vv = vv < lo ? lo : (vv > hi ? hi : vv);
 #pragma unroll
-                    for (int c = 0; c < 12; ++c) {
-                        const float f = expf(-ca_div(__ldg(mind + c * V + q), vv));
-                        acc[c] = __fadd_rn(acc[c], f);
-                    }
+                for (int c = 0; c < 12; ++c) {
+                    const float f = expf(-ca_div(__ldg(mind + c * V + q), vv));
+                    acc[c] = __fadd_rn(acc[c], f);
                 }
+            }
+    const int64_t o = ((int64_t)x * w + y) * d + z;
 #pragma unroll
-        for (int c = 0; c < 12; ++c) out[c * n + o] = (gs == 1) ? acc[c] : ca_div(acc[c], cnt);
-    }
+    for (int c = 0; c < 12; ++c) out[c * n + o] = (gs == 1) ? acc[c] : ca_div(acc[c], cnt);
 }
 
 extern "C" size_t ca_mindssc_workspace_bytes(int H, int W, int D) {
     const int64_t V = (int64_t)H * W * D;
-    return (size_t)(13 * V * 4 + 8 * ca_divup(V, 256) + 512);
+    return (size_t)(13 * V * 4 + 8 * ((int64_t)H * W * ca_divup(D, 128)) + 1024);
 }
 
 extern "C" int ca_mindssc_pooled(const float* img, int H, int W, int D, int radius, int dilation, int gs_a, float* out_a,
@@ -161,13 +165,18 @@ extern "C" int ca_mindssc_pooled(const float* img, int H, int W, int D, int radi
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t V = (int64_t)H * W * D;
-    const int nblk = (int)ca_divup(V, 256);
+    CA_CHECK_ARG(W < 65536 && H < 65536, "mindssc: volume too large");
+    if (!mind_table_is_consistent()) { ca_set_error("mindssc: internal pair table inconsistent"); return CA_ERR_UNSUPPORTED; }
+    const int nzb = (int)ca_divup(D, 128);
+    const int64_t nblk64 = (int64_t)H * W * nzb;
+    CA_CHECK_ARG(nblk64 < (1ll << 31), "mindssc: volume too large");
+    const int nblk = (int)nblk64;
     float* mind = (float*)workspace;
     float* var = mind + 12 * V;
     double* partial = (double*)(((uintptr_t)(var + V) + 255) & ~(uintptr_t)255);
     float* stats = (float*)(partial + nblk);
-    const MindTable tb = make_mind_table();
-    CA_LAUNCH(k_mind_phase_a, dim3(nblk), dim3(256), 0, st, img, H, W, D, radius, dilation, tb, mind, var, partial);
+    CA_LAUNCH(k_mind_phase_a, dim3((unsigned)nzb, (unsigned)W, (unsigned)H), dim3(128), 0, st, img, H, W, D, radius, dilation, mind, var,
+              partial);
     CA_CHECK_LAUNCH("mind_phase_a");
     CA_LAUNCH(k_mind_stats, dim3(1), dim3(1024), 0, st, partial, nblk, V, stats);
     CA_CHECK_LAUNCH("mind_stats");
@@ -177,10 +186,8 @@ extern "C" int ca_mindssc_pooled(const float* img, int H, int W, int D, int radi
         if (gs == 0) continue;
         const int h = H / gs, w = W / gs, d = D / gs;
         if (h <= 0 || w <= 0 || d <= 0) { ca_set_error("mindssc: volume smaller than the pooling block"); return CA_ERR_BAD_ARGUMENT; }
-        const int64_t n = (int64_t)h * w * d;
-        int64_t nb = ca_divup(n, 256);
-        if (nb > 148 * 32) nb = 148 * 32;
-        CA_LAUNCH(k_mind_phase_b, dim3((unsigned)nb), dim3(256), 0, st, mind, var, stats, H, W, D, gs, h, w, d, out);
+        CA_LAUNCH(k_mind_phase_b, dim3((unsigned)ca_divup(d, 128), (unsigned)w, (unsigned)h), dim3(128), 0, st, mind, var, stats, H, W, D,
+                  gs, h, w, d, out);
         CA_CHECK_LAUNCH("mind_phase_b");
     }
     return CA_OK;

@@ -119,7 +119,7 @@ CA_API int ca_trilinear(const float* in, int C, int ih, int iw, int id, float* o
  * u_out (3,ha,wa,da): B^3(p) of the LAST forward, i.e. what the reference returns (the final update is applied
  * to p but does not show in u_out, MIND.py:181).  g_out: optional, dL/dp of the last iteration.
  * g0x (da), g0y (wa), g0z (ha): identity-grid axes of affine_grid (MIND.py:160). lr=1, betas=(0.9,0.999), eps=1e-8. */
-CA_API size_t ca_adam_workspace_bytes(int ha, int wa, int da);
+CA_API size_t ca_adam_workspace_bytes(int C, int ha, int wa, int da);
 CA_API int ca_adam_run(const float* fix, const float* mov, int C, int ha, int wa, int da, float lambda_weight, float* p,
                 float* m, float* v, int first_step, int niter, const float* g0x, const float* g0y, const float* g0z,
                 float* u_out, float* g_out, void* workspace, size_t workspace_bytes, ca_stream_t stream);

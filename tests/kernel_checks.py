@@ -75,7 +75,8 @@ def _min_corr_ws(C, h, w, d, hw):
     dP = dF + ((4 + 2 * hw + 3) & ~3) - 4
     a = lambda v: (v + 255) & ~255
     plane = h * w * dF * 4
-    return a(C * plane) + a(C * (h + 2 * hw) * (w + 2 * hw) * dP * 4) + 2 * a(S * plane) + a(h * w * d * 8)
+    pplane = (h + 2) * (w + 2) * (dF + 8) * 4
+    return a(C * plane) + a(C * (h + 2 * hw) * (w + 2 * hw) * dP * 4) + 2 * a(S * pplane) + a(h * w * d * 8)
 
 
 def check_coupled(lib, device, C=12, h=6, w=7, d=8, hw=2):

