@@ -25,6 +25,7 @@ _SIGS = {
     "ca_avgpool3d": (_i, [_vp, _i64, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ca_onehot_pooled": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp, _vp]),
     "ca_correlate_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "ca_correlate_min_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "ca_correlate": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "ca_coupled_convex_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "ca_coupled_convex": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

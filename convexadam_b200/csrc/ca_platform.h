@@ -81,3 +81,11 @@ static __device__ __forceinline__ float ca_ld_stream1(const float* p) {
     return *p;
 #endif
 }
+// streaming (write-once) 128-bit store: evict-first, the cost volume must not push the working set out of L2
+static __device__ __forceinline__ void ca_st_stream4(float4* p, const float4& v) {
+#if defined(__CUDA_ARCH__)
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}

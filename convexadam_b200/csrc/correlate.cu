@@ -2,13 +2,18 @@
 //
 // Replaces `correlate` (reference src/convexAdam/convex_adam_utils.py:72-89).  The reference materialises an
 // im2col of the zero-padded moving features (utils.py:76-77, 9 GB at 192x160x256) and loops over the H-shift;
-// here nothing of that exists: labels are produced in chunks of (kH,kW) pairs x all kD,
-//     raw  (k_raw_ssd)    : per thread 4 consecutive voxels along D x all S values of kD, channel loop outside
-//                           -> every feature load is a 128-bit vector load reused S times from registers
-//     box3 (k_box3_exact) : zero-padded 27-tap sum in ascending (dH,dW,dD) order, then one IEEE division by 27
-//     box3 again          : writes the chunk's label planes straight into the (L,h,w,d) volume
-// with the two chunk-sized intermediates (S planes each, ~51 MB at the north-star shape) recycled so that they stay
-// L2-resident while the final volume streams out to HBM once.
+// here nothing of that exists: labels are produced in chunks of G (kH,kW) pairs x all kD by two kernels,
+//     raw   (k_raw_ssd) : per thread 4 consecutive voxels along D x all S values of kD, channel loop outside
+//                         -> every feature load is a 128-bit vector load reused S times from registers
+//     box12 (k_box12)   : BOTH zero-padded 27-tap box filters fused.  A CTA owns one label plane x a tile of rows
+//                         and marches along H; every thread keeps, for 2 rows x 4 voxels, the partial sums of the
+//                         three outputs (x-1, x, x+1) a plane contributes to, so each input value is read once from
+//                         memory per plane and used for 27 additions out of registers (the +-1 neighbours along D
+//                         come from warp shuffles).  The first box's plane goes through a double-buffered
+//                         shared-memory tile to the second box, whose finished plane streams into the (L,h,w,d)
+//                         volume.  Sums are the reference's: ascending (dH,dW,dD), one accumulator, then /27.
+// The kernels are fp32-issue-bound by construction (94 dependent-order flops per cost-volume entry, no FMA
+// contraction allowed), not HBM-bound: see DESIGN.md for the arithmetic floor.
 //
 // EXACT mode: this is a bit-exact restatement of the torch-CPU arithmetic -- (f-m) rounded, squared (x*x)
 // rounded, channels accumulated sequentially from c=0, each box3 a sequential fp32 sum of the in-volume taps
@@ -38,7 +43,7 @@ __global__ void __launch_bounds__(256) k_pad_features(const float* __restrict__ 
     }
 }
 
-// ---- tile geometry shared by the raw-SSD and box kernels ---------------------------------------------------------
+// ---- tile geometry of the raw-SSD kernel ---------------------------------------------------------------------------
 // A block is (bx, by) threads: bx consecutive z-quads (4 voxels each) x by consecutive y rows; grid = (tiles, h, planes)
 // so that no thread ever needs a 64-bit div/mod (the kernels are issue-bound, index maths must be free).
 struct TileGeom {
@@ -54,11 +59,27 @@ static TileGeom make_tile(int dF, int nthreads) {
     return t;
 }
 
+// Chunk buffer of raw SSD planes: (G*S planes) x h x (w+4) x (dF+8) floats, voxel (x,y,z) of a plane at
+// [x][y+2][z+4].  Rows -2,-1,w,w+1 and the 4+4 pad columns are zero (memset once per call, kernels write interiors
+// only), columns d..dF-1 are written as zero: the box kernel reads rows/columns around a tile without bounds checks.
+struct RawLayout {
+    int rowPitch;       // dF + 8
+    int64_t xPitch;     // (w + 4) * rowPitch
+    int64_t plane;      // h * xPitch
+};
+static RawLayout make_raw_layout(int h, int w, int dF) {
+    RawLayout r;
+    r.rowPitch = dF + 8;
+    r.xPitch = (int64_t)(w + 4) * r.rowPitch;
+    r.plane = (int64_t)h * r.xPitch;
+    return r;
+}
+
 // raw[(g*S + kD), x, y, z] = sum_c (f_c(x,y,z) - mpad_c(x+kH, y+kW, z+kD))^2 for the pair (kH,kW) = chunk_start+g
 template <int HW, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_raw_ssd(const float* __restrict__ fixp, const float* __restrict__ movp,
                                                        int C, int h, int w, int d, int dF, int dP, int chunk_start,
-                                                       int zq, int nzb, float* __restrict__ raw) {
+                                                       int zq, int nzb, RawLayout rl, float* __restrict__ raw) {
     constexpr int S = 2 * HW + 1;
     constexpr int NM = (4 + 2 * HW + 3) & ~3;   // moving values touched by 4 voxels x S shifts, rounded to float4
     const int bz = (int)blockIdx.x % nzb, byi = (int)blockIdx.x / nzb;
@@ -99,10 +120,7 @@ __global__ void __launch_bounds__(128, MINB) k_raw_ssd(const float* __restrict__
                 acc[k][i] = __fadd_rn(acc[k][i], __fmul_rn(df, df));
             }
     }
-    // chunk planes carry a zero halo: (h+2, w+2, dF+8), interior at (+1, +1, +4) -- the box filters then need no
-    // bounds checks (the halo is zeroed once per call and never written)
-    const int64_t plane = (int64_t)(h + 2) * (w + 2) * (dF + 8);
-    float* rp = raw + (int64_t)blockIdx.z * S * plane + ((int64_t)(x + 1) * (w + 2) + (y + 1)) * (dF + 8) + 4 + z0;
+    float* rp = raw + (int64_t)blockIdx.z * S * rl.plane + (int64_t)x * rl.xPitch + (int64_t)(y + 2) * rl.rowPitch + 4 + z0;
 #pragma unroll
     for (int k = 0; k < S; ++k) {
         float4 o;
@@ -110,19 +128,192 @@ __global__ void __launch_bounds__(128, MINB) k_raw_ssd(const float* __restrict__
         o.y = (z0 + 1 < d) ? acc[k][1] : 0.f;
         o.z = (z0 + 2 < d) ? acc[k][2] : 0.f;
         o.w = (z0 + 3 < d) ? acc[k][3] : 0.f;
-        *reinterpret_cast<float4*>(rp + k * plane) = o;
+        *reinterpret_cast<float4*>(rp + k * rl.plane) = o;
     }
 }
 
-// One zero-padded box3 pass over label planes, 4 outputs per thread, ascending (dH,dW,dD) sums, exact /27.
-// PADIN : input planes are (h+2, w+2, dF+8) with a zero halo (interior at +1,+1,+4; columns >= d zero): no bounds
-//         checks, 9 rows at constant offsets.  !PADIN: plain (h,w,dF) planes, taps outside the volume skipped.
-// MODE 0: output plane in the padded layout (pad columns written as zero)
-// MODE 1: plane (g*S + kD) goes to label kD*S*S + chunk_start + g of the dense (L,h,w,d) cost volume
-// MODE 2: output plane plain (h,w,dF)
-template <int MODE, bool PADIN>
-__global__ void __launch_bounds__(256) k_box3_exact(const float* __restrict__ in, int h, int w, int d, int dF, int S,
-                                                    int chunk_start, int zq, int nzb, float* __restrict__ out) {
+// ---- the two box filters, fused ------------------------------------------------------------------------------------
+// acc <- acc + row taps (dD = -1, 0, +1) for 4 consecutive voxels; FRESH: the accumulator starts here (0 + t == t)
+template <bool FRESH>
+static __device__ __forceinline__ void box_add_row(float (&a)[4], float hl, const float4& v, float hr) {
+    if (FRESH) {
+        a[0] = __fadd_rn(__fadd_rn(hl, v.x), v.y);
+        a[1] = __fadd_rn(__fadd_rn(v.x, v.y), v.z);
+        a[2] = __fadd_rn(__fadd_rn(v.y, v.z), v.w);
+        a[3] = __fadd_rn(__fadd_rn(v.z, v.w), hr);
+    } else {
+        a[0] = __fadd_rn(__fadd_rn(__fadd_rn(a[0], hl), v.x), v.y);
+        a[1] = __fadd_rn(__fadd_rn(__fadd_rn(a[1], v.x), v.y), v.z);
+        a[2] = __fadd_rn(__fadd_rn(__fadd_rn(a[2], v.y), v.z), v.w);
+        a[3] = __fadd_rn(__fadd_rn(__fadd_rn(a[3], v.z), v.w), hr);
+    }
+}
+
+// Plane X (4 rows of it: y0-1 .. y0+2 for the thread's two output rows y0, y0+1) enters the three running sums:
+// set A = R starts output X+1 (its dH=-1 taps), set B continues output X, set C finishes output X-1.
+template <int R>
+static __device__ __forceinline__ void box_add_plane(float (&s)[3][2][4], const float4 (&v)[4], const float (&hl)[4],
+                                                     const float (&hr)[4]) {
+    constexpr int A = R, B = (R + 2) % 3, Cs = (R + 1) % 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+            const int dy = j - o - 1;
+            if (dy < -1 || dy > 1) continue;
+            if (dy == -1) box_add_row<true>(s[A][o], hl[j], v[j], hr[j]);
+            else box_add_row<false>(s[A][o], hl[j], v[j], hr[j]);
+            box_add_row<false>(s[B][o], hl[j], v[j], hr[j]);
+            box_add_row<false>(s[Cs][o], hl[j], v[j], hr[j]);
+        }
+}
+
+struct BoxLane {
+    bool first, last;       // first / last quad of a row: the neighbour is outside the volume (zero)
+    bool fb_l, fb_r;        // the neighbour quad lives in another warp: read the value from memory instead
+};
+// the D-neighbours of a quad: lane-1 holds z0-4..z0-1, lane+1 holds z0+4..z0+7 (threads are z-fastest)
+static __device__ __forceinline__ void box_halo(const float4& v, const float* quad, bool valid, const BoxLane& bl,
+                                                float& hl, float& hr) {
+    hl = __shfl_up_sync(0xffffffffu, v.w, 1);
+    hr = __shfl_down_sync(0xffffffffu, v.x, 1);
+    if (bl.fb_l) hl = valid ? quad[-1] : 0.f;
+    if (bl.fb_r) hr = valid ? quad[4] : 0.f;
+    if (bl.first) hl = 0.f;
+    if (bl.last) hr = 0.f;
+}
+
+struct Box12Args {
+    const float* raw;
+    float* ssd;
+    RawLayout rl;
+    int h, w, d, S, chunk_start;
+    int nq, RP, Ty;         // quads per row, row pairs per CTA (first box), output rows per CTA (second box) = 2*(RP-1)
+};
+
+template <int R>
+static __device__ __forceinline__ void box12_step(int X, const Box12Args& a, float (&s1)[3][2][4], float (&s2)[3][2][4],
+                                                  float4 (&cur)[4], const float* const (&rowp)[4], const bool (&rvalid)[4],
+                                                  const BoxLane& bl, float* p1, int p1pitch, int q, int rp, int ty0, float* outp,
+                                                  bool active1, bool active2) {
+    constexpr int Cs = (R + 1) % 3;
+    const int z0 = 4 * q;
+    if (X > a.h + 1) return;
+    // ---- first box: raw plane X in, box1 plane X-1 out (shared memory) ----
+    if (X < a.h) {
+        float hl[4], hr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) box_halo(cur[j], rowp[j] + (int64_t)X * a.rl.xPitch, rvalid[j], bl, hl[j], hr[j]);
+        box_add_plane<R>(s1, cur, hl, hr);
+    }
+    float* p1w = p1 + (X & 1) * (2 * a.RP) * p1pitch;
+    if (X >= 1 && X <= a.h && active1) {
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+            const int e = 2 * rp + o, y = ty0 - 1 + e;
+            const bool in = y >= 0 && y < a.w;
+            float4 r;
+            r.x = (in && z0 + 0 < a.d) ? ca_div27(s1[Cs][o][0]) : 0.f;
+            r.y = (in && z0 + 1 < a.d) ? ca_div27(s1[Cs][o][1]) : 0.f;
+            r.z = (in && z0 + 2 < a.d) ? ca_div27(s1[Cs][o][2]) : 0.f;
+            r.w = (in && z0 + 3 < a.d) ? ca_div27(s1[Cs][o][3]) : 0.f;
+            *reinterpret_cast<float4*>(p1w + e * p1pitch + z0) = r;
+        }
+    }
+    __syncthreads();
+    // ---- next raw plane: issued now, consumed after the second box's arithmetic ----
+    if (X + 1 < a.h) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            cur[j] = rvalid[j] ? __ldg(reinterpret_cast<const float4*>(rowp[j] + (int64_t)(X + 1) * a.rl.xPitch))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // ---- second box: box1 plane P = X-1 in, cost-volume plane P-1 out ----
+    const int P = X - 1;
+    if (P >= 0 && P < a.h) {
+        float4 v[4];
+        float hl[4], hr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = 2 * rp + j;
+            const bool ok = e < 2 * a.RP && active1;
+            const float* quad = p1w + (ok ? e : 0) * p1pitch + z0;
+            v[j] = ok ? *reinterpret_cast<const float4*>(quad) : make_float4(0.f, 0.f, 0.f, 0.f);
+            box_halo(v[j], quad, ok, bl, hl[j], hr[j]);
+        }
+        box_add_plane<R>(s2, v, hl, hr);
+    }
+    if (P >= 1 && active2) {
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+            const int y = ty0 + 2 * rp + o;
+            if (y >= a.w) continue;
+            float* op = outp + ((int64_t)(P - 1) * a.w + y) * a.d + z0;
+            const float r0 = ca_div27(s2[Cs][o][0]), r1 = ca_div27(s2[Cs][o][1]), r2 = ca_div27(s2[Cs][o][2]),
+                        r3 = ca_div27(s2[Cs][o][3]);
+            if ((a.d & 3) == 0) {
+                ca_st_stream4(reinterpret_cast<float4*>(op), make_float4(r0, r1, r2, r3));
+            } else {
+                if (z0 + 0 < a.d) op[0] = r0;
+                if (z0 + 1 < a.d) op[1] = r1;
+                if (z0 + 2 < a.d) op[2] = r2;
+                if (z0 + 3 < a.d) op[3] = r3;
+            }
+        }
+    }
+}
+
+// grid = (row tiles, planes of the chunk); block = nq*RP threads rounded up to whole warps, z-fastest
+__global__ void __launch_bounds__(512, 1) k_box12(Box12Args a) {
+    CA_DYN_SMEM(float, p1);
+    const int tid = (int)threadIdx.x;
+    const int q = tid % a.nq, rp = tid / a.nq;
+    const int lane = tid & 31;
+    const bool active1 = rp < a.RP;                 // threads beyond nq*RP only keep the warps whole
+    const bool active2 = rp < a.RP - 1;
+    const int ty0 = (int)blockIdx.x * a.Ty;
+    const int pl = (int)blockIdx.y;
+    const int g = pl / a.S, kD = pl - g * a.S;
+    const int64_t label = (int64_t)kD * a.S * a.S + a.chunk_start + g;
+    float* outp = a.ssd + label * a.h * a.w * a.d;
+    const int p1pitch = 4 * a.nq;
+    BoxLane bl;
+    bl.first = q == 0;
+    bl.last = q == a.nq - 1;
+    bl.fb_l = !bl.first && lane == 0;
+    bl.fb_r = !bl.last && lane == 31;
+    // raw rows y = ty0 - 2 + 2*rp + j  <->  buffer rows ty0 + 2*rp + j
+    const float* rowp[4];
+    bool rvalid[4];
+    const float* plane = a.raw + (int64_t)pl * a.rl.plane;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int br = ty0 + 2 * rp + j;
+        rvalid[j] = active1 && br < a.w + 4;
+        rowp[j] = plane + (int64_t)(rvalid[j] ? br : 0) * a.rl.rowPitch + 4 + 4 * q;
+    }
+    float s1[3][2][4], s2[3][2][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int o = 0; o < 2; ++o)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s1[i][o][k] = s2[i][o][k] = 0.f;
+    float4 cur[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        cur[j] = rvalid[j] ? __ldg(reinterpret_cast<const float4*>(rowp[j])) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int X = 0; X <= a.h + 1; X += 3) {
+        box12_step<0>(X, a, s1, s2, cur, rowp, rvalid, bl, p1, p1pitch, q, rp, ty0, outp, active1, active2);
+        box12_step<1>(X + 1, a, s1, s2, cur, rowp, rvalid, bl, p1, p1pitch, q, rp, ty0, outp, active1, active2);
+        box12_step<2>(X + 2, a, s1, s2, cur, rowp, rvalid, bl, p1, p1pitch, q, rp, ty0, outp, active1, active2);
+    }
+}
+
+// One zero-padded box3 pass over `nl` plain (h,w,dF) planes, 4 outputs per thread, ascending (dH,dW,dD) sums of the
+// in-volume taps, exact /27.  Used by the Adam stage for B^3 (adam.cu).
+__global__ void __launch_bounds__(256) k_box3_exact(const float* __restrict__ in, int h, int w, int d, int dF, int zq,
+                                                    int nzb, float* __restrict__ out) {
     const int bz = (int)blockIdx.x % nzb, byi = (int)blockIdx.x / nzb;
     const int q = bz * (int)blockDim.x + (int)threadIdx.x;
     const int y = byi * (int)blockDim.y + (int)threadIdx.y;
@@ -131,71 +322,35 @@ __global__ void __launch_bounds__(256) k_box3_exact(const float* __restrict__ in
     if (q >= zq || y >= w) return;
     const int z0 = q * 4;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    if (PADIN) {
-        const int wp = w + 2, dp = dF + 8;
-        const float* ip = in + ((int64_t)l * (h + 2) * wp + (int64_t)x * wp + y) * dp + 4 + z0;   // row (x-1, y-1) of the interior
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx)
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-                const float* row = ip + (dx * wp + dy) * dp;
-                const float a = row[-1];
-                const float4 c = *reinterpret_cast<const float4*>(row);
-                const float b = row[4];
-                s0 = __fadd_rn(__fadd_rn(__fadd_rn(s0, a), c.x), c.y);
-                s1 = __fadd_rn(__fadd_rn(__fadd_rn(s1, c.x), c.y), c.z);
-                s2 = __fadd_rn(__fadd_rn(__fadd_rn(s2, c.y), c.z), c.w);
-                s3 = __fadd_rn(__fadd_rn(__fadd_rn(s3, c.z), c.w), b);
-            }
-    } else {
-        const float* ip = in + (int64_t)l * h * w * dF + z0;
-        const bool has_a = z0 > 0, has_b = z0 + 4 < dF;
-        for (int dx = -1; dx <= 1; ++dx) {
-            const int xx = x + dx;
-            if (xx < 0 || xx >= h) continue;
-            for (int dy = -1; dy <= 1; ++dy) {
-                const int yy = y + dy;
-                if (yy < 0 || yy >= w) continue;
-                const float* row = ip + (xx * w + yy) * dF;
-                const float4 c = *reinterpret_cast<const float4*>(row);
-                const float a = has_a ? row[-1] : 0.f;
-                const float b = has_b ? row[4] : 0.f;
-                s0 = __fadd_rn(__fadd_rn(__fadd_rn(s0, a), c.x), c.y);
-                s1 = __fadd_rn(__fadd_rn(__fadd_rn(s1, c.x), c.y), c.z);
-                s2 = __fadd_rn(__fadd_rn(__fadd_rn(s2, c.y), c.z), c.w);
-                s3 = __fadd_rn(__fadd_rn(__fadd_rn(s3, c.z), c.w), b);
-            }
+    const float* ip = in + (int64_t)l * h * w * dF + z0;
+    const bool has_a = z0 > 0, has_b = z0 + 4 < dF;
+    for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= h) continue;
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= w) continue;
+            const float* row = ip + (xx * w + yy) * dF;
+            const float4 c = *reinterpret_cast<const float4*>(row);
+            const float a = has_a ? row[-1] : 0.f;
+            const float b = has_b ? row[4] : 0.f;
+            s0 = __fadd_rn(__fadd_rn(__fadd_rn(s0, a), c.x), c.y);
+            s1 = __fadd_rn(__fadd_rn(__fadd_rn(s1, c.x), c.y), c.z);
+            s2 = __fadd_rn(__fadd_rn(__fadd_rn(s2, c.y), c.z), c.w);
+            s3 = __fadd_rn(__fadd_rn(__fadd_rn(s3, c.z), c.w), b);
         }
     }
-    s0 = ca_div27(s0); s1 = ca_div27(s1); s2 = ca_div27(s2); s3 = ca_div27(s3);
-    if (MODE == 0 || MODE == 2) {
-        float4 o;
-        o.x = (z0 + 0 < d) ? s0 : 0.f; o.y = (z0 + 1 < d) ? s1 : 0.f; o.z = (z0 + 2 < d) ? s2 : 0.f; o.w = (z0 + 3 < d) ? s3 : 0.f;
-        if (MODE == 0)
-            *reinterpret_cast<float4*>(out + ((int64_t)l * (h + 2) * (w + 2) + (int64_t)(x + 1) * (w + 2) + (y + 1)) * (dF + 8) + 4 + z0) = o;
-        else
-            *reinterpret_cast<float4*>(out + ((int64_t)l * h * w + x * w + y) * dF + z0) = o;
-    } else {
-        const int g = l / S, kD = l - g * S;
-        const int64_t label = (int64_t)kD * S * S + chunk_start + g;
-        float* op = out + (label * h * w + x * w + y) * d + z0;
-        if ((d & 3) == 0) {
-            *reinterpret_cast<float4*>(op) = make_float4(s0, s1, s2, s3);
-        } else {
-            if (z0 + 0 < d) op[0] = s0;
-            if (z0 + 1 < d) op[1] = s1;
-            if (z0 + 2 < d) op[2] = s2;
-            if (z0 + 3 < d) op[3] = s3;
-        }
-    }
+    float4 o;
+    o.x = (z0 + 0 < d) ? ca_div27(s0) : 0.f; o.y = (z0 + 1 < d) ? ca_div27(s1) : 0.f;
+    o.z = (z0 + 2 < d) ? ca_div27(s2) : 0.f; o.w = (z0 + 3 < d) ? ca_div27(s3) : 0.f;
+    *reinterpret_cast<float4*>(out + ((int64_t)l * h * w + x * w + y) * dF + z0) = o;
 }
 
-// box3 of `nl` planes (h,w,d) with d % 4 == 0 (no pad columns), used by the Adam stage for B^3 (adam.cu)
+// box3 of `nl` planes (h,w,d) with d % 4 == 0 (no pad columns)
 int ca_launch_box3_planes(const float* in, int nl, int h, int w, int d, float* out, cudaStream_t st) {
     const TileGeom t = make_tile(d, 256);
-    auto k = k_box3_exact<2, false>;
-    CA_LAUNCH(k, dim3((unsigned)(t.nzb * ((w + t.by - 1) / t.by)), (unsigned)h, (unsigned)nl), dim3(t.bx, t.by), 0, st, in, h, w, d,
-              d, 1, 0, t.zq, t.nzb, out);
+    CA_LAUNCH(k_box3_exact, dim3((unsigned)(t.nzb * ((w + t.by - 1) / t.by)), (unsigned)h, (unsigned)nl), dim3(t.bx, t.by), 0, st, in,
+              h, w, d, d, t.zq, t.nzb, out);
     CA_CHECK_LAUNCH("box3_planes");
     return CA_OK;
 }
@@ -203,22 +358,37 @@ int ca_launch_box3_planes(const float* in, int nl, int h, int w, int d, float* o
 namespace {
 struct CorrPlan {
     int S, dF, dP, G;
-    size_t off_fix, off_mov, off_raw, off_i1, off_keys, total, chunk_bytes;
+    int nq, RP, Ty, ntiles, nthreads;
+    RawLayout rl;
+    size_t off_fix, off_mov, off_raw, off_keys, total, chunk_bytes, box_smem;
 };
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-// G = number of (kH,kW) pairs per chunk; G<=0 -> default (two chunk buffers of ~48 MB: L2 resident on B200)
+// G = number of (kH,kW) pairs per chunk; G<=0 -> default (raw chunk buffer of up to ~3 GB: a handful of launches)
 CorrPlan make_plan(int C, int h, int w, int d, int hw, int G) {
     CorrPlan p;
     p.S = 2 * hw + 1;
     p.dF = ca_roundup4(d);
     p.dP = p.dF + ca_roundup4(4 + 2 * hw) - 4;
+    p.rl = make_raw_layout(h, w, p.dF);
+    // box12 tiling: whole rows per CTA (nq quads), RP row pairs of the first box -> Ty = 2*(RP-1) output rows
+    p.nq = p.dF / 4;
+    int rp_max = 512 / p.nq;
+    if (rp_max > (w + 3) / 2 + 1) rp_max = (w + 3) / 2 + 1;     // one tile covers all rows
+    if (rp_max < 2) rp_max = 2;
+    const int ty_max = 2 * (rp_max - 1);
+    p.ntiles = (w + ty_max - 1) / ty_max;
+    p.Ty = (((w + p.ntiles - 1) / p.ntiles) + 1) & ~1;          // balanced tiles, even
+    p.RP = p.Ty / 2 + 1;
+    p.nthreads = (p.nq * p.RP + 31) & ~31;
+    p.box_smem = (size_t)2 * (2 * p.RP) * (4 * p.nq) * sizeof(float);
     const size_t plane = (size_t)h * w * p.dF * 4;
+    const size_t pair_bytes = (size_t)p.S * p.rl.plane * 4;
     if (G <= 0) {
         static int env_g = -1;   // tuning knob: CA_CORR_CHUNK = (kH,kW) pairs per chunk
         if (env_g < 0) { const char* e = getenv("CA_CORR_CHUNK"); env_g = e ? atoi(e) : 0; }
-        G = env_g > 0 ? env_g : (int)((48u << 20) / ((size_t)(h + 2) * (w + 2) * (p.dF + 8) * 4 * p.S));
+        G = env_g > 0 ? env_g : (int)(((size_t)3 << 30) / pair_bytes);
         if (G < 1) G = 1;
     }
     if (G > p.S * p.S) G = p.S * p.S;
@@ -226,10 +396,8 @@ CorrPlan make_plan(int C, int h, int w, int d, int hw, int G) {
     size_t o = 0;
     p.off_fix = o; o = align256(o + (size_t)C * plane);
     p.off_mov = o; o = align256(o + (size_t)C * (h + 2 * hw) * (w + 2 * hw) * p.dP * 4);
-    const size_t pplane = (size_t)(h + 2) * (w + 2) * (p.dF + 8) * 4;   // chunk planes carry a zero halo
-    p.chunk_bytes = (size_t)G * p.S * pplane;
+    p.chunk_bytes = (size_t)G * pair_bytes;
     p.off_raw = o; o = align256(o + p.chunk_bytes);
-    p.off_i1 = o; o = align256(o + p.chunk_bytes);
     p.off_keys = o; o = align256(o + (size_t)h * w * d * 8);
     p.total = o;
     return p;
@@ -239,7 +407,7 @@ static int g_raw_minb = 0;   // tuning knob (CA_RAW_MINB env, read once): min re
 
 template <int HW>
 void launch_raw(const float* fixp, const float* movp, int C, int h, int w, int d, int dF, int dP, int chunk_start, int g,
-                float* raw, cudaStream_t st) {
+                const RawLayout& rl, float* raw, cudaStream_t st) {
     const TileGeom t = make_tile(dF, 128);
     const dim3 grid((unsigned)(t.nzb * ((w + t.by - 1) / t.by)), (unsigned)h, (unsigned)g), block(t.bx, t.by);
     if (g_raw_minb == 0) {
@@ -247,15 +415,20 @@ void launch_raw(const float* fixp, const float* movp, int C, int h, int w, int d
         g_raw_minb = e ? atoi(e) : 6;
         if (g_raw_minb != 4 && g_raw_minb != 8) g_raw_minb = 6;
     }
-    if (g_raw_minb == 4) { auto k = k_raw_ssd<HW, 4>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, dF, dP, chunk_start, t.zq, t.nzb, raw); }
-    else if (g_raw_minb == 8) { auto k = k_raw_ssd<HW, 8>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, dF, dP, chunk_start, t.zq, t.nzb, raw); }
-    else { auto k = k_raw_ssd<HW, 6>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, dF, dP, chunk_start, t.zq, t.nzb, raw); }
+    if (g_raw_minb == 4) { auto k = k_raw_ssd<HW, 4>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, dF, dP, chunk_start, t.zq, t.nzb, rl, raw); }
+    else if (g_raw_minb == 8) { auto k = k_raw_ssd<HW, 8>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, dF, dP, chunk_start, t.zq, t.nzb, rl, raw); }
+    else { auto k = k_raw_ssd<HW, 6>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, dF, dP, chunk_start, t.zq, t.nzb, rl, raw); }
 }
 }  // namespace
 
 extern "C" size_t ca_correlate_workspace_bytes(int C, int h, int w, int d, int disp_hw) {
     if (C <= 0 || h <= 0 || w <= 0 || d <= 0 || disp_hw < 1) return 0;
     return make_plan(C, h, w, d, disp_hw, 0).total;
+}
+
+extern "C" size_t ca_correlate_min_workspace_bytes(int C, int h, int w, int d, int disp_hw) {
+    if (C <= 0 || h <= 0 || w <= 0 || d <= 0 || disp_hw < 1) return 0;
+    return make_plan(C, h, w, d, disp_hw, 1).total;
 }
 
 extern "C" int ca_correlate(const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, float* ssd,
@@ -266,53 +439,73 @@ extern "C" int ca_correlate(const float* fix, const float* mov, int C, int h, in
         ca_set_error("correlate: disp_hw=%d unsupported (1..8)", disp_hw);
         return CA_ERR_UNSUPPORTED;
     }
-    CA_CHECK_ARG((int64_t)h * w * ca_roundup4(d) < (1ll << 31) && h < 65536, "correlate: coarse grid too large");
+    if (d > 1024) {
+        ca_set_error("correlate: coarse depth %d unsupported (<= 1024)", d);
+        return CA_ERR_UNSUPPORTED;
+    }
+    CA_CHECK_ARG((int64_t)h * (w + 4) * (ca_roundup4(d) + 8) < (1ll << 31) && h < 65536, "correlate: coarse grid too large");
     // largest chunk that fits the caller's workspace (>= 1 pair), capped at the default plan
     CorrPlan p = make_plan(C, h, w, d, disp_hw, 0);
-    while (p.total > workspace_bytes && p.G > 1) p = make_plan(C, h, w, d, disp_hw, p.G - 1);
     if (p.total > workspace_bytes) {
-        ca_set_error("correlate: workspace too small (%zu < %zu)", workspace_bytes, p.total);
-        return CA_ERR_WORKSPACE;
+        const CorrPlan p1 = make_plan(C, h, w, d, disp_hw, 1);
+        if (p1.total > workspace_bytes) {
+            ca_set_error("correlate: workspace too small (%zu < %zu)", workspace_bytes, p1.total);
+            return CA_ERR_WORKSPACE;
+        }
+        const size_t pair_bytes = p1.chunk_bytes;
+        int G = 1 + (int)((workspace_bytes - p1.total) / pair_bytes);
+        p = make_plan(C, h, w, d, disp_hw, G);
+        while (p.total > workspace_bytes && p.G > 1) p = make_plan(C, h, w, d, disp_hw, p.G - 1);
     }
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
     float* fixp = (float*)(ws + p.off_fix);
     float* movp = (float*)(ws + p.off_mov);
     float* raw = (float*)(ws + p.off_raw);
-    float* i1 = (float*)(ws + p.off_i1);
     const int S = p.S, npairs = S * S;
     {
         const int64_t tf = (int64_t)C * h * w * p.dF, tm = (int64_t)C * (h + 2 * disp_hw) * (w + 2 * disp_hw) * p.dP;
         CA_LAUNCH(k_pad_features, dim3((unsigned)ca_min((int)ca_divup(tf, 256), 148 * 16)), dim3(256), 0, st, fix, C, h, w, d, 0, p.dF, fixp);
         CA_LAUNCH(k_pad_features, dim3((unsigned)ca_min((int)ca_divup(tm, 256), 148 * 16)), dim3(256), 0, st, mov, C, h, w, d, disp_hw, p.dP, movp);
         CA_CHECK_LAUNCH("correlate/pad");
-        // zero the halos of both chunk buffers once; the kernels only ever write interiors
-        if (cudaMemsetAsync(raw, 0, p.chunk_bytes, st) != cudaSuccess || cudaMemsetAsync(i1, 0, p.chunk_bytes, st) != cudaSuccess) {
+        // zero the halo rows / pad columns of the chunk buffer once; the raw kernel only ever writes interiors
+        if (cudaMemsetAsync(raw, 0, p.chunk_bytes, st) != cudaSuccess) {
             ca_set_error("correlate: memset failed");
             return CA_ERR_LAUNCH;
         }
     }
+#ifndef CA_EMU
+    {
+        static bool attr_done = false;   // opt in to > 48 KB of dynamic shared memory once
+        if (!attr_done) {
+            cudaFuncSetAttribute(k_box12, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            attr_done = true;
+        }
+    }
+#endif
+    if (p.box_smem > 160 * 1024) {
+        ca_set_error("correlate: row tile needs %zu bytes of shared memory", p.box_smem);
+        return CA_ERR_UNSUPPORTED;
+    }
     for (int cs = 0; cs < npairs; cs += p.G) {
         const int g = ca_min(p.G, npairs - cs);
         switch (disp_hw) {
-            case 1: launch_raw<1>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, raw, st); break;
-            case 2: launch_raw<2>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, raw, st); break;
-            case 3: launch_raw<3>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, raw, st); break;
-            case 4: launch_raw<4>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, raw, st); break;
-            case 5: launch_raw<5>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, raw, st); break;
-            case 6: launch_raw<6>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, raw, st); break;
-            case 7: launch_raw<7>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, raw, st); break;
-            default: launch_raw<8>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, raw, st); break;
+            case 1: launch_raw<1>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, p.rl, raw, st); break;
+            case 2: launch_raw<2>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, p.rl, raw, st); break;
+            case 3: launch_raw<3>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, p.rl, raw, st); break;
+            case 4: launch_raw<4>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, p.rl, raw, st); break;
+            case 5: launch_raw<5>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, p.rl, raw, st); break;
+            case 6: launch_raw<6>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, p.rl, raw, st); break;
+            case 7: launch_raw<7>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, p.rl, raw, st); break;
+            default: launch_raw<8>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, p.rl, raw, st); break;
         }
         CA_CHECK_LAUNCH("correlate/raw");
-        const int nl = g * S;
-        const TileGeom t = make_tile(p.dF, 256);
-        const dim3 grid((unsigned)(t.nzb * ((w + t.by - 1) / t.by)), (unsigned)h, (unsigned)nl), block(t.bx, t.by);
-        auto k1 = k_box3_exact<0, true>;
-        auto k2 = k_box3_exact<1, true>;
-        CA_LAUNCH(k1, grid, block, 0, st, raw, h, w, d, p.dF, S, cs, t.zq, t.nzb, i1);
-        CA_LAUNCH(k2, grid, block, 0, st, i1, h, w, d, p.dF, S, cs, t.zq, t.nzb, ssd);
-        CA_CHECK_LAUNCH("correlate/box3");
+        Box12Args a;
+        a.raw = raw; a.ssd = ssd; a.rl = p.rl;
+        a.h = h; a.w = w; a.d = d; a.S = S; a.chunk_start = cs;
+        a.nq = p.nq; a.RP = p.RP; a.Ty = p.Ty;
+        CA_LAUNCH(k_box12, dim3((unsigned)p.ntiles, (unsigned)(g * S)), dim3((unsigned)p.nthreads), p.box_smem, st, a);
+        CA_CHECK_LAUNCH("correlate/box12");
     }
     if (argmin) {
         unsigned long long* keys = (unsigned long long*)(ws + p.off_keys);

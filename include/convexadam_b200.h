@@ -78,8 +78,11 @@ CA_API int ca_onehot_pooled(const float* labels, int H, int W, int D, const int3
 /* ---- correlate (utils.py:72-89) -----------------------------------------------------------------------------
  * fix, mov: planar (C,h,w,d) f32 coarse features.  ssd: (L,h,w,d) f32, L = (2*disp_hw+1)^3, label
  * l = kD*S*S + kW*S + kH (reference layout).  argmin: (h,w,d) int64, first minimum; may be NULL.
- * Bit-exact restatement of the torch-CPU arithmetic (sequential channel sum, two zero-padded 27-tap sums, /27). */
+ * Bit-exact restatement of the torch-CPU arithmetic (sequential channel sum, two zero-padded 27-tap sums, /27).
+ * Workspace: ca_correlate_workspace_bytes is the preferred size (a few large launches); any size down to
+ * ca_correlate_min_workspace_bytes works (labels are then produced in smaller chunks) with identical results. */
 CA_API size_t ca_correlate_workspace_bytes(int C, int h, int w, int d, int disp_hw);
+CA_API size_t ca_correlate_min_workspace_bytes(int C, int h, int w, int d, int disp_hw);
 CA_API int ca_correlate(const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, float* ssd,
                  int64_t* argmin, void* workspace, size_t workspace_bytes, ca_stream_t stream);
 

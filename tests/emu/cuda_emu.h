@@ -122,4 +122,5 @@ template <class T> static inline T emu_shfl(T v, int src_lane) {
 }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_shfl(v, emu::lane_id() ^ m); }
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) { return emu_shfl(v, emu::lane_id() + d); }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) { return emu_shfl(v, emu::lane_id() - d); }
 template <class T> static inline T __shfl_sync(unsigned, T v, int l) { return emu_shfl(v, l); }

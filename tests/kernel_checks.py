@@ -63,20 +63,14 @@ def check_correlate(lib, device, cases=((12, 6, 5, 7, 2), (16, 4, 6, 8, 1), (3, 
         assert (N(am) == am_o).all(), f"correlate argmin {(C, h, w, d, hw)}"
         # smallest legal workspace (one (kH,kW) pair per chunk) must give the same bits
         small = lib.dll.ca_correlate_workspace_bytes(C, h, w, d, hw)
-        ssd2, am2 = lib.correlate(T(fix, device), T(mov, device), hw, workspace_bytes=_min_corr_ws(C, h, w, d, hw))
+        ssd2, am2 = lib.correlate(T(fix, device), T(mov, device), hw, workspace_bytes=_min_corr_ws(lib, C, h, w, d, hw))
         assert_bits_equal(N(ssd2), ssd_o, f"correlate ssd (min workspace) {(C, h, w, d, hw)}")
         assert (N(am2) == am_o).all()
-        assert small >= _min_corr_ws(C, h, w, d, hw)
+        assert small >= _min_corr_ws(lib, C, h, w, d, hw)
 
 
-def _min_corr_ws(C, h, w, d, hw):
-    S = 2 * hw + 1
-    dF = (d + 3) & ~3
-    dP = dF + ((4 + 2 * hw + 3) & ~3) - 4
-    a = lambda v: (v + 255) & ~255
-    plane = h * w * dF * 4
-    pplane = (h + 2) * (w + 2) * (dF + 8) * 4
-    return a(C * plane) + a(C * (h + 2 * hw) * (w + 2 * hw) * dP * 4) + 2 * a(S * pplane) + a(h * w * d * 8)
+def _min_corr_ws(lib, C, h, w, d, hw):
+    return int(lib.dll.ca_correlate_min_workspace_bytes(C, h, w, d, hw))
 
 
 def check_coupled(lib, device, C=12, h=6, w=7, d=8, hw=2):
