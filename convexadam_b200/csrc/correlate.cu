@@ -82,13 +82,15 @@ __global__ void __launch_bounds__(128, MINB) k_raw_ssd(const float* __restrict__
                                                        int zq, int nzb, RawLayout rl, float* __restrict__ raw) {
     constexpr int S = 2 * HW + 1;
     constexpr int NM = (4 + 2 * HW + 3) & ~3;   // moving values touched by 4 voxels x S shifts, rounded to float4
-    const int bz = (int)blockIdx.x % nzb, byi = (int)blockIdx.x / nzb;
+    // grid = (pairs of the chunk, tiles of a plane, h): the blocks in flight share one slab of the feature volumes
+    // (same x, all (kH,kW) shifts), so features come from L2, not HBM
+    const int bz = (int)blockIdx.y % nzb, byi = (int)blockIdx.y / nzb;
     const int q = bz * (int)blockDim.x + (int)threadIdx.x;
     const int y = byi * (int)blockDim.y + (int)threadIdx.y;
-    const int x = (int)blockIdx.y;
+    const int x = (int)blockIdx.z;
     if (q >= zq || y >= w) return;
     const int z0 = q * 4;
-    const int pi = chunk_start + (int)blockIdx.z;
+    const int pi = chunk_start + (int)blockIdx.x;
     const int kH = pi % S, kW = pi / S;
     const int hp = h + 2 * HW, wp = w + 2 * HW;
 
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(128, MINB) k_raw_ssd(const float* __restrict__
                 acc[k][i] = __fadd_rn(acc[k][i], __fmul_rn(df, df));
             }
     }
-    float* rp = raw + (int64_t)blockIdx.z * S * rl.plane + (int64_t)x * rl.xPitch + (int64_t)(y + 2) * rl.rowPitch + 4 + z0;
+    float* rp = raw + (int64_t)blockIdx.x * S * rl.plane + (int64_t)x * rl.xPitch + (int64_t)(y + 2) * rl.rowPitch + 4 + z0;
 #pragma unroll
     for (int k = 0; k < S; ++k) {
         float4 o;
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(128, MINB) k_raw_ssd(const float* __restrict__
         o.y = (z0 + 1 < d) ? acc[k][1] : 0.f;
         o.z = (z0 + 2 < d) ? acc[k][2] : 0.f;
         o.w = (z0 + 3 < d) ? acc[k][3] : 0.f;
-        *reinterpret_cast<float4*>(rp + k * rl.plane) = o;
+        ca_st_stream4(reinterpret_cast<float4*>(rp + k * rl.plane), o);
     }
 }
 
@@ -173,12 +175,11 @@ struct BoxLane {
     bool fb_l, fb_r;        // the neighbour quad lives in another warp: read the value from memory instead
 };
 // the D-neighbours of a quad: lane-1 holds z0-4..z0-1, lane+1 holds z0+4..z0+7 (threads are z-fastest)
-static __device__ __forceinline__ void box_halo(const float4& v, const float* quad, bool valid, const BoxLane& bl,
-                                                float& hl, float& hr) {
+static __device__ __forceinline__ void box_halo(const float4& v, const float* quad, const BoxLane& bl, float& hl, float& hr) {
     hl = __shfl_up_sync(0xffffffffu, v.w, 1);
     hr = __shfl_down_sync(0xffffffffu, v.x, 1);
-    if (bl.fb_l) hl = valid ? quad[-1] : 0.f;
-    if (bl.fb_r) hr = valid ? quad[4] : 0.f;
+    if (bl.fb_l) hl = quad[-1];
+    if (bl.fb_r) hr = quad[4];
     if (bl.first) hl = 0.f;
     if (bl.last) hr = 0.f;
 }
@@ -191,106 +192,130 @@ struct Box12Args {
     int nq, RP, Ty;         // quads per row, row pairs per CTA (first box), output rows per CTA (second box) = 2*(RP-1)
 };
 
-template <int R>
-static __device__ __forceinline__ void box12_step(int X, const Box12Args& a, float (&s1)[3][2][4], float (&s2)[3][2][4],
-                                                  float4 (&cur)[4], const float* const (&rowp)[4], const bool (&rvalid)[4],
-                                                  const BoxLane& bl, float* p1, int p1pitch, int q, int rp, int ty0, float* outp,
-                                                  bool active1, bool active2) {
+// Per-thread state of the march along H.  Rows that do not exist (outside the buffer, padding threads) point at an
+// all-zero row, so the inner loop carries no validity predicates.
+struct BoxThread {
+    const float* rawp[4];   // the thread's 4 raw rows (y0-2 .. y0+1 of the first box's tile) at plane X
+    const float* p1r[4];    // the same 4 row slots of the first box's plane in shared memory (buffer 0)
+    float* p1w[2];          // where the thread's two first-box rows go (buffer 0); nullptr: row is outside the volume
+    float* out[2];          // the thread's two cost-volume rows at plane X-2; nullptr: not an output row
+    int p1buf;              // floats between the two shared-memory plane buffers
+    int64_t xPitch, outPitch;
+    BoxLane bl;
+    bool zok[4];            // z0+i < d
+};
+
+template <int R, bool DALIGNED>
+static __device__ __forceinline__ void box12_step(int X, int h, BoxThread& t, float (&s1)[3][2][4], float (&s2)[3][2][4],
+                                                  float4 (&cur)[4]) {
     constexpr int Cs = (R + 1) % 3;
-    const int z0 = 4 * q;
-    if (X > a.h + 1) return;
+    if (X > h + 1) return;
+    const int boff = (X & 1) * t.p1buf;
     // ---- first box: raw plane X in, box1 plane X-1 out (shared memory) ----
-    if (X < a.h) {
+    if (X < h) {
         float hl[4], hr[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) box_halo(cur[j], rowp[j] + (int64_t)X * a.rl.xPitch, rvalid[j], bl, hl[j], hr[j]);
+        for (int j = 0; j < 4; ++j) box_halo(cur[j], t.rawp[j], t.bl, hl[j], hr[j]);
         box_add_plane<R>(s1, cur, hl, hr);
-    }
-    float* p1w = p1 + (X & 1) * (2 * a.RP) * p1pitch;
-    if (X >= 1 && X <= a.h && active1) {
 #pragma unroll
-        for (int o = 0; o < 2; ++o) {
-            const int e = 2 * rp + o, y = ty0 - 1 + e;
-            const bool in = y >= 0 && y < a.w;
-            float4 r;
-            r.x = (in && z0 + 0 < a.d) ? ca_div27(s1[Cs][o][0]) : 0.f;
-            r.y = (in && z0 + 1 < a.d) ? ca_div27(s1[Cs][o][1]) : 0.f;
-            r.z = (in && z0 + 2 < a.d) ? ca_div27(s1[Cs][o][2]) : 0.f;
-            r.w = (in && z0 + 3 < a.d) ? ca_div27(s1[Cs][o][3]) : 0.f;
-            *reinterpret_cast<float4*>(p1w + e * p1pitch + z0) = r;
-        }
+        for (int j = 0; j < 4; ++j) t.rawp[j] += t.xPitch;
+    }
+    if (X >= 1 && X <= h) {
+#pragma unroll
+        for (int o = 0; o < 2; ++o)
+            if (t.p1w[o]) {
+                float4 r;
+                r.x = ca_div27(s1[Cs][o][0]); r.y = ca_div27(s1[Cs][o][1]); r.z = ca_div27(s1[Cs][o][2]); r.w = ca_div27(s1[Cs][o][3]);
+                if (!DALIGNED) { r.y = t.zok[1] ? r.y : 0.f; r.z = t.zok[2] ? r.z : 0.f; r.w = t.zok[3] ? r.w : 0.f; }
+                *reinterpret_cast<float4*>(t.p1w[o] + boff) = r;
+            }
     }
     __syncthreads();
     // ---- next raw plane: issued now, consumed after the second box's arithmetic ----
-    if (X + 1 < a.h) {
+    if (X + 1 < h) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            cur[j] = rvalid[j] ? __ldg(reinterpret_cast<const float4*>(rowp[j] + (int64_t)(X + 1) * a.rl.xPitch))
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 4; ++j) cur[j] = __ldg(reinterpret_cast<const float4*>(t.rawp[j]));
     }
     // ---- second box: box1 plane P = X-1 in, cost-volume plane P-1 out ----
-    const int P = X - 1;
-    if (P >= 0 && P < a.h) {
+    if (X >= 1 && X <= h) {
         float4 v[4];
         float hl[4], hr[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int e = 2 * rp + j;
-            const bool ok = e < 2 * a.RP && active1;
-            const float* quad = p1w + (ok ? e : 0) * p1pitch + z0;
-            v[j] = ok ? *reinterpret_cast<const float4*>(quad) : make_float4(0.f, 0.f, 0.f, 0.f);
-            box_halo(v[j], quad, ok, bl, hl[j], hr[j]);
+            const float* quad = t.p1r[j] + boff;
+            v[j] = *reinterpret_cast<const float4*>(quad);
+            box_halo(v[j], quad, t.bl, hl[j], hr[j]);
         }
         box_add_plane<R>(s2, v, hl, hr);
     }
-    if (P >= 1 && active2) {
+    if (X >= 2) {
 #pragma unroll
-        for (int o = 0; o < 2; ++o) {
-            const int y = ty0 + 2 * rp + o;
-            if (y >= a.w) continue;
-            float* op = outp + ((int64_t)(P - 1) * a.w + y) * a.d + z0;
-            const float r0 = ca_div27(s2[Cs][o][0]), r1 = ca_div27(s2[Cs][o][1]), r2 = ca_div27(s2[Cs][o][2]),
-                        r3 = ca_div27(s2[Cs][o][3]);
-            if ((a.d & 3) == 0) {
-                ca_st_stream4(reinterpret_cast<float4*>(op), make_float4(r0, r1, r2, r3));
-            } else {
-                if (z0 + 0 < a.d) op[0] = r0;
-                if (z0 + 1 < a.d) op[1] = r1;
-                if (z0 + 2 < a.d) op[2] = r2;
-                if (z0 + 3 < a.d) op[3] = r3;
+        for (int o = 0; o < 2; ++o)
+            if (t.out[o]) {
+                const float r0 = ca_div27(s2[Cs][o][0]), r1 = ca_div27(s2[Cs][o][1]), r2 = ca_div27(s2[Cs][o][2]),
+                            r3 = ca_div27(s2[Cs][o][3]);
+                if (DALIGNED) {
+                    ca_st_stream4(reinterpret_cast<float4*>(t.out[o]), make_float4(r0, r1, r2, r3));
+                } else {
+                    if (t.zok[0]) t.out[o][0] = r0;
+                    if (t.zok[1]) t.out[o][1] = r1;
+                    if (t.zok[2]) t.out[o][2] = r2;
+                    if (t.zok[3]) t.out[o][3] = r3;
+                }
+                t.out[o] += t.outPitch;
             }
-        }
     }
 }
 
-// grid = (row tiles, planes of the chunk); block = nq*RP threads rounded up to whole warps, z-fastest
+// grid = (row tiles, planes of the chunk); block = nq*RP threads rounded up to whole warps, z-fastest.
+// Shared memory: two plane buffers of (2*RP rows + one all-zero row) x 4*nq floats.
+template <bool DALIGNED>
 __global__ void __launch_bounds__(512, 1) k_box12(Box12Args a) {
     CA_DYN_SMEM(float, p1);
     const int tid = (int)threadIdx.x;
     const int q = tid % a.nq, rp = tid / a.nq;
     const int lane = tid & 31;
+    const int z0 = 4 * q;
     const bool active1 = rp < a.RP;                 // threads beyond nq*RP only keep the warps whole
-    const bool active2 = rp < a.RP - 1;
     const int ty0 = (int)blockIdx.x * a.Ty;
     const int pl = (int)blockIdx.y;
     const int g = pl / a.S, kD = pl - g * a.S;
     const int64_t label = (int64_t)kD * a.S * a.S + a.chunk_start + g;
-    float* outp = a.ssd + label * a.h * a.w * a.d;
     const int p1pitch = 4 * a.nq;
-    BoxLane bl;
-    bl.first = q == 0;
-    bl.last = q == a.nq - 1;
-    bl.fb_l = !bl.first && lane == 0;
-    bl.fb_r = !bl.last && lane == 31;
-    // raw rows y = ty0 - 2 + 2*rp + j  <->  buffer rows ty0 + 2*rp + j
-    const float* rowp[4];
-    bool rvalid[4];
+    BoxThread t;
+    t.p1buf = (2 * a.RP + 1) * p1pitch;
+    t.xPitch = a.rl.xPitch;
+    t.outPitch = (int64_t)a.w * a.d;
+    t.bl.first = q == 0;
+    t.bl.last = q == a.nq - 1;
+    t.bl.fb_l = !t.bl.first && lane == 0;
+    t.bl.fb_r = !t.bl.last && lane == 31;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t.zok[i] = z0 + i < a.d;
+    float* zero_row = p1 + 2 * a.RP * p1pitch;
+    for (int i = tid; i < p1pitch; i += (int)blockDim.x) zero_row[i] = zero_row[t.p1buf + i] = 0.f;
+    // raw rows y = ty0 - 2 + 2*rp + j  <->  buffer rows ty0 + 2*rp + j; buffer row 0 is all zero
     const float* plane = a.raw + (int64_t)pl * a.rl.plane;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int br = ty0 + 2 * rp + j;
-        rvalid[j] = active1 && br < a.w + 4;
-        rowp[j] = plane + (int64_t)(rvalid[j] ? br : 0) * a.rl.rowPitch + 4 + 4 * q;
+        t.rawp[j] = plane + (int64_t)((active1 && br < a.w + 4) ? br : 0) * a.rl.rowPitch + 4 + z0;
+        const int e = 2 * rp + j;
+        t.p1r[j] = (active1 && e < 2 * a.RP) ? p1 + e * p1pitch + z0 : zero_row + z0;
+    }
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+        const int e = 2 * rp + o;
+        const int y1 = ty0 - 1 + e;                 // first-box row
+        const bool in1 = active1 && y1 >= 0 && y1 < a.w;
+        t.p1w[o] = in1 ? p1 + e * p1pitch + z0 : nullptr;
+        if (active1 && !in1) {                      // rows outside the volume stay zero in both buffers
+            *reinterpret_cast<float4*>(p1 + e * p1pitch + z0) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(p1 + t.p1buf + e * p1pitch + z0) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const int y2 = ty0 + e;                     // second-box (output) row
+        const bool in2 = rp < a.RP - 1 && y2 < a.w;
+        t.out[o] = in2 ? a.ssd + (label * a.h * a.w + y2) * a.d + z0 : nullptr;
     }
     float s1[3][2][4], s2[3][2][4];
 #pragma unroll
@@ -301,12 +326,12 @@ __global__ void __launch_bounds__(512, 1) k_box12(Box12Args a) {
             for (int k = 0; k < 4; ++k) s1[i][o][k] = s2[i][o][k] = 0.f;
     float4 cur[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-        cur[j] = rvalid[j] ? __ldg(reinterpret_cast<const float4*>(rowp[j])) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < 4; ++j) cur[j] = __ldg(reinterpret_cast<const float4*>(t.rawp[j]));
+    __syncthreads();
     for (int X = 0; X <= a.h + 1; X += 3) {
-        box12_step<0>(X, a, s1, s2, cur, rowp, rvalid, bl, p1, p1pitch, q, rp, ty0, outp, active1, active2);
-        box12_step<1>(X + 1, a, s1, s2, cur, rowp, rvalid, bl, p1, p1pitch, q, rp, ty0, outp, active1, active2);
-        box12_step<2>(X + 2, a, s1, s2, cur, rowp, rvalid, bl, p1, p1pitch, q, rp, ty0, outp, active1, active2);
+        box12_step<0, DALIGNED>(X, a.h, t, s1, s2, cur);
+        box12_step<1, DALIGNED>(X + 1, a.h, t, s1, s2, cur);
+        box12_step<2, DALIGNED>(X + 2, a.h, t, s1, s2, cur);
     }
 }
 
@@ -382,7 +407,7 @@ CorrPlan make_plan(int C, int h, int w, int d, int hw, int G) {
     p.Ty = (((w + p.ntiles - 1) / p.ntiles) + 1) & ~1;          // balanced tiles, even
     p.RP = p.Ty / 2 + 1;
     p.nthreads = (p.nq * p.RP + 31) & ~31;
-    p.box_smem = (size_t)2 * (2 * p.RP) * (4 * p.nq) * sizeof(float);
+    p.box_smem = (size_t)2 * (2 * p.RP + 1) * (4 * p.nq) * sizeof(float);
     const size_t plane = (size_t)h * w * p.dF * 4;
     const size_t pair_bytes = (size_t)p.S * p.rl.plane * 4;
     if (G <= 0) {
@@ -409,7 +434,7 @@ template <int HW>
 void launch_raw(const float* fixp, const float* movp, int C, int h, int w, int d, int dF, int dP, int chunk_start, int g,
                 const RawLayout& rl, float* raw, cudaStream_t st) {
     const TileGeom t = make_tile(dF, 128);
-    const dim3 grid((unsigned)(t.nzb * ((w + t.by - 1) / t.by)), (unsigned)h, (unsigned)g), block(t.bx, t.by);
+    const dim3 grid((unsigned)g, (unsigned)(t.nzb * ((w + t.by - 1) / t.by)), (unsigned)h), block(t.bx, t.by);
     if (g_raw_minb == 0) {
         const char* e = getenv("CA_RAW_MINB");
         g_raw_minb = e ? atoi(e) : 6;
@@ -478,7 +503,8 @@ extern "C" int ca_correlate(const float* fix, const float* mov, int C, int h, in
     {
         static bool attr_done = false;   // opt in to > 48 KB of dynamic shared memory once
         if (!attr_done) {
-            cudaFuncSetAttribute(k_box12, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaFuncSetAttribute(k_box12<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaFuncSetAttribute(k_box12<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
             attr_done = true;
         }
     }
@@ -504,7 +530,9 @@ extern "C" int ca_correlate(const float* fix, const float* mov, int C, int h, in
         a.raw = raw; a.ssd = ssd; a.rl = p.rl;
         a.h = h; a.w = w; a.d = d; a.S = S; a.chunk_start = cs;
         a.nq = p.nq; a.RP = p.RP; a.Ty = p.Ty;
-        CA_LAUNCH(k_box12, dim3((unsigned)p.ntiles, (unsigned)(g * S)), dim3((unsigned)p.nthreads), p.box_smem, st, a);
+        const dim3 bgrid((unsigned)p.ntiles, (unsigned)(g * S)), bblock((unsigned)p.nthreads);
+        if ((d & 3) == 0) { auto k = k_box12<true>; CA_LAUNCH(k, bgrid, bblock, p.box_smem, st, a); }
+        else { auto k = k_box12<false>; CA_LAUNCH(k, bgrid, bblock, p.box_smem, st, a); }
         CA_CHECK_LAUNCH("correlate/box12");
     }
     if (argmin) {
