@@ -19,7 +19,7 @@
 // rounded, channels accumulated sequentially from c=0, each box3 a sequential fp32 sum of the in-volume taps
 // followed by a true division by 27 (avg_pool3d, count_include_pad) -- so that the argmin over labels is the
 // reference's argmin.  Every arithmetic op is an explicit _rn intrinsic: nvcc must not contract them to FMAs.
-#include "ca_platform.h"
+#include "box_march.cuh"
 
 #include <cstdlib>
 
@@ -135,55 +135,6 @@ __global__ void __launch_bounds__(128, MINB) k_raw_ssd(const float* __restrict__
 }
 
 // ---- the two box filters, fused ------------------------------------------------------------------------------------
-// acc <- acc + row taps (dD = -1, 0, +1) for 4 consecutive voxels; FRESH: the accumulator starts here (0 + t == t)
-template <bool FRESH>
-static __device__ __forceinline__ void box_add_row(float (&a)[4], float hl, const float4& v, float hr) {
-    if (FRESH) {
-        a[0] = __fadd_rn(__fadd_rn(hl, v.x), v.y);
-        a[1] = __fadd_rn(__fadd_rn(v.x, v.y), v.z);
-        a[2] = __fadd_rn(__fadd_rn(v.y, v.z), v.w);
-        a[3] = __fadd_rn(__fadd_rn(v.z, v.w), hr);
-    } else {
-        a[0] = __fadd_rn(__fadd_rn(__fadd_rn(a[0], hl), v.x), v.y);
-        a[1] = __fadd_rn(__fadd_rn(__fadd_rn(a[1], v.x), v.y), v.z);
-        a[2] = __fadd_rn(__fadd_rn(__fadd_rn(a[2], v.y), v.z), v.w);
-        a[3] = __fadd_rn(__fadd_rn(__fadd_rn(a[3], v.z), v.w), hr);
-    }
-}
-
-// Plane X (4 rows of it: y0-1 .. y0+2 for the thread's two output rows y0, y0+1) enters the three running sums:
-// set A = R starts output X+1 (its dH=-1 taps), set B continues output X, set C finishes output X-1.
-template <int R>
-static __device__ __forceinline__ void box_add_plane(float (&s)[3][2][4], const float4 (&v)[4], const float (&hl)[4],
-                                                     const float (&hr)[4]) {
-    constexpr int A = R, B = (R + 2) % 3, Cs = (R + 1) % 3;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int o = 0; o < 2; ++o) {
-            const int dy = j - o - 1;
-            if (dy < -1 || dy > 1) continue;
-            if (dy == -1) box_add_row<true>(s[A][o], hl[j], v[j], hr[j]);
-            else box_add_row<false>(s[A][o], hl[j], v[j], hr[j]);
-            box_add_row<false>(s[B][o], hl[j], v[j], hr[j]);
-            box_add_row<false>(s[Cs][o], hl[j], v[j], hr[j]);
-        }
-}
-
-struct BoxLane {
-    bool first, last;       // first / last quad of a row: the neighbour is outside the volume (zero)
-    bool fb_l, fb_r;        // the neighbour quad lives in another warp: read the value from memory instead
-};
-// the D-neighbours of a quad: lane-1 holds z0-4..z0-1, lane+1 holds z0+4..z0+7 (threads are z-fastest)
-static __device__ __forceinline__ void box_halo(const float4& v, const float* quad, const BoxLane& bl, float& hl, float& hr) {
-    hl = __shfl_up_sync(0xffffffffu, v.w, 1);
-    hr = __shfl_down_sync(0xffffffffu, v.x, 1);
-    if (bl.fb_l) hl = quad[-1];
-    if (bl.fb_r) hr = quad[4];
-    if (bl.first) hl = 0.f;
-    if (bl.last) hr = 0.f;
-}
-
 struct Box12Args {
     const float* raw;
     float* ssd;
@@ -333,51 +284,6 @@ __global__ void __launch_bounds__(512, 1) k_box12(Box12Args a) {
         box12_step<1, DALIGNED>(X + 1, a.h, t, s1, s2, cur);
         box12_step<2, DALIGNED>(X + 2, a.h, t, s1, s2, cur);
     }
-}
-
-// One zero-padded box3 pass over `nl` plain (h,w,dF) planes, 4 outputs per thread, ascending (dH,dW,dD) sums of the
-// in-volume taps, exact /27.  Used by the Adam stage for B^3 (adam.cu).
-__global__ void __launch_bounds__(256) k_box3_exact(const float* __restrict__ in, int h, int w, int d, int dF, int zq,
-                                                    int nzb, float* __restrict__ out) {
-    const int bz = (int)blockIdx.x % nzb, byi = (int)blockIdx.x / nzb;
-    const int q = bz * (int)blockDim.x + (int)threadIdx.x;
-    const int y = byi * (int)blockDim.y + (int)threadIdx.y;
-    const int x = (int)blockIdx.y;
-    const int l = (int)blockIdx.z;
-    if (q >= zq || y >= w) return;
-    const int z0 = q * 4;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    const float* ip = in + (int64_t)l * h * w * dF + z0;
-    const bool has_a = z0 > 0, has_b = z0 + 4 < dF;
-    for (int dx = -1; dx <= 1; ++dx) {
-        const int xx = x + dx;
-        if (xx < 0 || xx >= h) continue;
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int yy = y + dy;
-            if (yy < 0 || yy >= w) continue;
-            const float* row = ip + (xx * w + yy) * dF;
-            const float4 c = *reinterpret_cast<const float4*>(row);
-            const float a = has_a ? row[-1] : 0.f;
-            const float b = has_b ? row[4] : 0.f;
-            s0 = __fadd_rn(__fadd_rn(__fadd_rn(s0, a), c.x), c.y);
-            s1 = __fadd_rn(__fadd_rn(__fadd_rn(s1, c.x), c.y), c.z);
-            s2 = __fadd_rn(__fadd_rn(__fadd_rn(s2, c.y), c.z), c.w);
-            s3 = __fadd_rn(__fadd_rn(__fadd_rn(s3, c.z), c.w), b);
-        }
-    }
-    float4 o;
-    o.x = (z0 + 0 < d) ? ca_div27(s0) : 0.f; o.y = (z0 + 1 < d) ? ca_div27(s1) : 0.f;
-    o.z = (z0 + 2 < d) ? ca_div27(s2) : 0.f; o.w = (z0 + 3 < d) ? ca_div27(s3) : 0.f;
-    *reinterpret_cast<float4*>(out + ((int64_t)l * h * w + x * w + y) * dF + z0) = o;
-}
-
-// box3 of `nl` planes (h,w,d) with d % 4 == 0 (no pad columns)
-int ca_launch_box3_planes(const float* in, int nl, int h, int w, int d, float* out, cudaStream_t st) {
-    const TileGeom t = make_tile(d, 256);
-    CA_LAUNCH(k_box3_exact, dim3((unsigned)(t.nzb * ((w + t.by - 1) / t.by)), (unsigned)h, (unsigned)nl), dim3(t.bx, t.by), 0, st, in,
-              h, w, d, d, t.zq, t.nzb, out);
-    CA_CHECK_LAUNCH("box3_planes");
-    return CA_OK;
 }
 
 namespace {
