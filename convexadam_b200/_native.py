@@ -27,6 +27,14 @@ _SIGS = {
     "ca_correlate_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "ca_correlate_min_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "ca_correlate": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "ca_correlate_slab_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
+    "ca_correlate_slab": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "ca_cc_select_workspace_bytes": (_sz, [_i64]),
+    "ca_cc_select": (_i, [_vp, _i64, _i, _vp, _vp, _f, _vp, _vp, _sz, _vp]),
+    "ca_cc_smooth": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "ca_adam_window_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "ca_adam_run_window": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                                _i, _vp]),
     "ca_coupled_convex_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "ca_coupled_convex": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "ca_inverse_consistency_workspace_bytes": (_sz, [_i, _i, _i]),
@@ -174,6 +182,44 @@ class Lib:
                                        self._p(ws), nb, self._stream(fix)))
         return ssd, am
 
+    def correlate_slab(self, fix, mov, disp_hw, x_begin, x_end, want_argmin=True, out=None):
+        """correlate for the H planes [x_begin, x_end) of the coarse grid only (fix/mov: whole (C,h,w,d) volumes)."""
+        fix = self._t(fix)
+        mov = self._t(mov)
+        Cn, h, w, d = fix.shape
+        L = (2 * disp_hw + 1) ** 3
+        hs = x_end - x_begin
+        ssd = out if out is not None else torch.empty((L, hs, w, d), dtype=torch.float32, device=fix.device)
+        am = torch.empty((hs, w, d), dtype=torch.int64, device=fix.device) if want_argmin else None
+        nb = self.dll.ca_correlate_slab_workspace_bytes(Cn, h, w, d, disp_hw, x_begin, x_end)
+        ws = self._ws(nb, fix)
+        self._chk(self.dll.ca_correlate_slab(self._p(fix), self._p(mov), Cn, h, w, d, disp_hw, x_begin, x_end, self._p(ssd),
+                                            self._p(am), self._p(ws), nb, self._stream(fix)))
+        return ssd, am
+
+    def cc_select(self, ssd, disp_hw, mesh=None, soft=None, coeff=0.0):
+        """One pass of coupled_convex over a slab: ssd (L,hs,w,d), soft (3,hs,w,d) -> labels (hs,w,d) int64."""
+        ssd = self._t(ssd)
+        n = ssd[0].numel()
+        sel = torch.empty(ssd.shape[1:], dtype=torch.int64, device=ssd.device)
+        mesh = self._t(mesh.reshape(3, -1)) if mesh is not None else None
+        soft = self._t(soft) if soft is not None else None
+        nb = self.dll.ca_cc_select_workspace_bytes(n)
+        ws = self._ws(nb, ssd)
+        self._chk(self.dll.ca_cc_select(self._p(ssd), n, disp_hw, self._p(mesh), self._p(soft), float(coeff), self._p(sel),
+                                       self._p(ws), nb, self._stream(ssd)))
+        return sel
+
+    def cc_smooth(self, sel_window, mesh, disp_hw):
+        """box3(mesh[:, sel]) for the inner planes of a (P,w,d) label window (negative label = outside the volume)."""
+        sel_window = self._t(sel_window, torch.int64)
+        mesh = self._t(mesh.reshape(3, -1))
+        P, w, d = sel_window.shape
+        soft = torch.empty((3, P - 2, w, d), dtype=torch.float32, device=sel_window.device)
+        self._chk(self.dll.ca_cc_smooth(self._p(sel_window), self._p(mesh), P, w, d, disp_hw, self._p(soft),
+                                       self._stream(sel_window)))
+        return soft
+
     def coupled_convex(self, ssd, argmin, mesh, disp_hw, want_sel=False):
         ssd = self._t(ssd)
         argmin = self._t(argmin, torch.int64)
@@ -235,6 +281,30 @@ class Lib:
                                       self._p(v), first_step, niter, self._p(gx), self._p(gy), self._p(gz), self._p(u),
                                       self._p(g), self._p(ws), nb, self._stream(fix)))
         return (u, g) if want_grad else u
+
+    def adam_window(self, fix, mov, lambda_weight, lo, hi, p, m, v, first_step, niter, ws=None, features_ready=False):
+        """Adam iterations on the H planes [lo, hi) of the grid (p, m, v: (3, hi-lo, wa, da), updated in place).
+        Returns (u, ws): pass `ws` back with features_ready=True to skip the feature re-layout on later calls."""
+        fix = self._t(fix)
+        mov = self._t(mov)
+        for s in (p, m, v):
+            if not s.is_contiguous() or s.dtype != torch.float32:
+                raise TypeError("adam_window: p, m, v must be contiguous float32 (updated in place)")
+            self._t(s)
+        Cn, ha, wa, da = fix.shape
+        if tuple(p.shape) != (3, hi - lo, wa, da):
+            raise ValueError("adam_window: state shape does not match the window")
+        gx, gy, gz = self.identity_axes(ha, wa, da, fix.device)
+        u = torch.empty_like(p)
+        nb = self.dll.ca_adam_window_workspace_bytes(Cn, ha, wa, da, lo, hi)
+        if ws is None:
+            ws = self._ws(nb, fix)
+            features_ready = False
+        self._chk(self.dll.ca_adam_run_window(self._p(fix), self._p(mov), Cn, ha, wa, da, lo, hi, lambda_weight, self._p(p),
+                                             self._p(m), self._p(v), first_step, niter, self._p(gx), self._p(gy), self._p(gz),
+                                             self._p(u), self._p(None), self._p(ws), nb, int(features_ready),
+                                             self._stream(fix)))
+        return u, ws
 
     def pack_field(self, field, round_half=False, out=None):
         field = self._t(field)

@@ -80,8 +80,13 @@ def convex_adam_pt(
     dtype: torch.dtype = torch.float16,
     verbose: bool = False,
     device: torch.device = None,
+    split_over=None,
 ) -> np.ndarray:
     """Coupled convex optimisation with adam instance optimisation (reference MIND.py:64-202).
+
+    split_over (extension, not in the reference): a torch.distributed process group (or True for the default
+    group) over which this ONE pair is split into H slabs -- every rank calls with the same images and gets the
+    same field (convexadam_b200/slab.py; for pairs whose cost volume does not fit one GPU).
 
     dtype: float32 computes and returns fp32 values (the reference's CPU policy, parity-pinned against it);
     float16 (the reference's GPU default) currently keeps the cost volume in fp32 and rounds the returned field
@@ -106,7 +111,11 @@ def convex_adam_pt(
             mask_moving = torch.from_numpy(nib.load(path_moving_mask).get_fdata()).float()
             fixed_dev = _fill_outside_mask(fixed_dev, mask_fixed, device)
             moving_dev = _fill_outside_mask(moving_dev, mask_moving, device)
-        disp = pipeline.register_mind(fixed_dev, moving_dev, prm, lib)
+        if split_over is not None and split_over is not False:
+            from . import slab
+            disp = slab.register_mind_slab(fixed_dev, moving_dev, prm, lib, None if split_over is True else split_over)
+        else:
+            disp = pipeline.register_mind(fixed_dev, moving_dev, prm, lib)
         packed = lib.pack_field(disp, round_half=(dtype == torch.float16))
         host = torch.empty(packed.shape, dtype=torch.float64, pin_memory=True)
         host.copy_(packed, non_blocking=True)

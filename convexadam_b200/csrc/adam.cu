@@ -19,6 +19,7 @@ int ca_launch_avgpool3d(const float* in, int64_t nc, int T, int H, int W, int k,
 
 struct AdamGeom {
     int ha, wa, da, C;
+    int lo, hl;       // the field arrays hold the H planes [lo, lo+hl) of the grid (whole grid: 0, ha)
     float sc[3];      // (size-1)/2 per axis  (MIND.py:170)
     float gmul[3];    // d(position)/d(u) = (size/2) / sc
     float reg[3];     // 2*lambda / count per axis (MIND.py:167-169)
@@ -45,11 +46,12 @@ __global__ void __launch_bounds__(128) k_adam_grad(const float* __restrict__ u, 
                                                    const float* __restrict__ g0x, const float* __restrict__ g0y,
                                                    const float* __restrict__ g0z, float* __restrict__ gu) {
     const int ha = g.ha, wa = g.wa, da = g.da;
-    const int n = ha * wa * da;
+    const int n = g.hl * wa * da;                   // field arrays: window-local indexing
     const int z = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    const int y = (int)blockIdx.y, x = (int)blockIdx.z;
+    const int y = (int)blockIdx.y, xl = (int)blockIdx.z, x = xl + g.lo;
     if (z >= da) return;
-    const int o = (x * wa + y) * da + z;
+    const int o = (xl * wa + y) * da + z;
+    const int of = (x * wa + y) * da + z;           // feature arrays: whole-grid indexing
     const float u0 = u[o], u1 = u[n + o], u2 = u[2 * n + o];
     // diffusion regulariser first (its 18 neighbour loads are independent of everything else and go out together
     // with u): d/du_c(x) of lambda * mean_k (u[x+e_k]-u[x])^2, one-sided at the faces
@@ -64,8 +66,11 @@ __global__ void __launch_bounds__(128) k_adam_grad(const float* __restrict__ u, 
         for (int ch = 0; ch < 3; ++ch)
 #pragma unroll
             for (int ax = 0; ax < 3; ++ax) {
-                lo[ch][ax] = idx[ax] > 0 ? u[ch * n + o - strd[ax]] : 0.f;
-                hi[ch][ax] = idx[ax] < dims[ax] - 1 ? u[ch * n + o + strd[ax]] : 0.f;
+                // a window edge that is not a face of the grid has no neighbour plane: that row of the window is margin
+                // the caller discards (slab.py), it only must not be read out of bounds
+                const bool has_lo = ax == 0 ? xl > 0 : idx[ax] > 0, has_hi = ax == 0 ? xl < g.hl - 1 : idx[ax] < dims[ax] - 1;
+                lo[ch][ax] = has_lo ? u[ch * n + o - strd[ax]] : uc[ch];
+                hi[ch][ax] = has_hi ? u[ch * n + o + strd[ax]] : uc[ch];
             }
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(128) k_adam_grad(const float* __restrict__ u, 
     float4 val[8], nval[8], f, nf;
 #pragma unroll
     for (int t = 0; t < 8; ++t) nval[t] = inb[t] ? __ldg(movcl + off[t]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    nf = __ldg(fixcl + o * CG);
+    nf = __ldg(fixcl + of * CG);
     for (int cg = 0; cg < CG; ++cg) {
 #pragma unroll
         for (int t = 0; t < 8; ++t) val[t] = nval[t];
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(128) k_adam_grad(const float* __restrict__ u, 
         if (cg + 1 < CG) {
 #pragma unroll
             for (int t = 0; t < 8; ++t) nval[t] = inb[t] ? __ldg(movcl + off[t] + cg + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-            nf = __ldg(fixcl + o * CG + cg + 1);
+            nf = __ldg(fixcl + of * CG + cg + 1);
         }
         float4 smp = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -320,30 +325,34 @@ static int field_box(const float* in, float* out, int ha, int wa, int da, const 
     return CA_OK;
 }
 
-extern "C" size_t ca_adam_workspace_bytes(int C, int ha, int wa, int da) {
-    const size_t n = (size_t)ha * wa * da;
-    return n * 3 * 4 * 3 + 2 * n * (size_t)((C + 3) & ~3) * 4 + 1024 + ((size_t)da + 64) * 4;
+extern "C" size_t ca_adam_window_workspace_bytes(int C, int ha, int wa, int da, int lo, int hi) {
+    if (C <= 0 || ha <= 0 || wa <= 0 || da <= 0 || lo < 0 || hi > ha || lo >= hi) return 0;
+    const size_t n = (size_t)ha * wa * da, nw = (size_t)(hi - lo) * wa * da;
+    return nw * 3 * 4 * 3 + 2 * n * (size_t)((C + 3) & ~3) * 4 + 1024 + ((size_t)da + 64) * 4;
 }
+extern "C" size_t ca_adam_workspace_bytes(int C, int ha, int wa, int da) { return ca_adam_window_workspace_bytes(C, ha, wa, da, 0, ha); }
 
-extern "C" int ca_adam_run(const float* fix, const float* mov, int C, int ha, int wa, int da, float lambda_weight, float* p,
-                           float* m, float* v, int first_step, int niter, const float* g0x, const float* g0y,
-                           const float* g0z, float* u_out, float* g_out, void* workspace, size_t workspace_bytes,
-                           ca_stream_t stream) {
+extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int ha, int wa, int da, int lo, int hi,
+                                  float lambda_weight, float* p, float* m, float* v, int first_step, int niter, const float* g0x,
+                                  const float* g0y, const float* g0z, float* u_out, float* g_out, void* workspace,
+                                  size_t workspace_bytes, int features_ready, ca_stream_t stream) {
     CA_CHECK_ARG(fix && mov && p && m && v && g0x && g0y && g0z && u_out && workspace, "adam_run: null pointer");
     CA_CHECK_ARG(C > 0 && ha > 1 && wa > 1 && da > 1, "adam_run: bad dims (each Adam-grid axis must be >= 2)");
+    CA_CHECK_ARG(lo >= 0 && hi <= ha && lo < hi, "adam_run: bad window [%d, %d) of %d planes", lo, hi, ha);
     CA_CHECK_ARG(first_step >= 1 && niter >= 0, "adam_run: bad step range");
     CA_CHECK_ARG((int64_t)ha * wa * da * ((C + 3) / 4) < (1ll << 31) && wa < 65536 && ha < 65536, "adam_run: grid too large");
-    if (workspace_bytes < ca_adam_workspace_bytes(C, ha, wa, da)) {
+    if (workspace_bytes < ca_adam_window_workspace_bytes(C, ha, wa, da, lo, hi)) {
         ca_set_error("adam_run: workspace too small");
         return CA_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t n = (int64_t)ha * wa * da;
+    const int hl = hi - lo;
+    const int64_t n = (int64_t)ha * wa * da, nw = (int64_t)hl * wa * da;
     float* t0 = (float*)workspace;
-    float* t1 = t0 + 3 * n;
-    float* gu = t1 + 3 * n;
+    float* t1 = t0 + 3 * nw;
+    float* gu = t1 + 3 * nw;
     const int CG = (C + 3) / 4;
-    float4* fixcl = (float4*)(((uintptr_t)(gu + 3 * n) + 255) & ~(uintptr_t)255);
+    float4* fixcl = (float4*)(((uintptr_t)(gu + 3 * nw) + 255) & ~(uintptr_t)255);
     float4* movcl = fixcl + n * CG;
     float* zero_row = (float*)(((uintptr_t)(movcl + n * CG) + 255) & ~(uintptr_t)255);   // da + 16 zeros for k_field_box
     // marching box passes need float4 rows; any other shape takes the generic avg_pool3d kernel
@@ -353,17 +362,17 @@ extern "C" int ca_adam_run(const float* fix, const float* mov, int C, int ha, in
         return CA_ERR_LAUNCH;
     }
     auto box = [&](const float* in, float* out) -> int {
-        if (fast) return field_box(in, out, ha, wa, da, zero_row, nullptr, st);
-        return ca_launch_avgpool3d(in, 3, ha, wa, da, 3, 1, 1, out, st);
+        if (fast) return field_box(in, out, hl, wa, da, zero_row, nullptr, st);
+        return ca_launch_avgpool3d(in, 3, hl, wa, da, 3, 1, 1, out, st);
     };
-    if (niter > 0) {
+    if (niter > 0 && !features_ready) {
         const unsigned gb = adam_grid(n, 256);
         CA_LAUNCH(k_planar_to_cl, dim3(gb), dim3(256), 0, st, fix, C, CG, n, fixcl);
         CA_LAUNCH(k_planar_to_cl, dim3(gb), dim3(256), 0, st, mov, C, CG, n, movcl);
         CA_CHECK_LAUNCH("adam/planar_to_cl");
     }
     AdamGeom g;
-    g.ha = ha; g.wa = wa; g.da = da; g.C = C;
+    g.ha = ha; g.wa = wa; g.da = da; g.C = C; g.lo = lo; g.hl = hl;
     const int dims[3] = {ha, wa, da};
     const double cnt[3] = {3.0 * (ha - 1) * wa * da, 3.0 * ha * (wa - 1) * da, 3.0 * ha * wa * (da - 1)};
     for (int a = 0; a < 3; ++a) {
@@ -380,7 +389,7 @@ extern "C" int ca_adam_run(const float* fix, const float* mov, int C, int ha, in
         if ((rc = box(t0, t1)) != CA_OK) return rc;
         if ((rc = box(t1, u_out)) != CA_OK) return rc;
         const int bx = da >= 128 ? 128 : (da >= 64 ? 64 : 32);
-        CA_LAUNCH(k_adam_grad, dim3((unsigned)((da + bx - 1) / bx), (unsigned)wa, (unsigned)ha), dim3(bx), 0, st, u_out, fixcl, movcl, CG,
+        CA_LAUNCH(k_adam_grad, dim3((unsigned)((da + bx - 1) / bx), (unsigned)wa, (unsigned)hl), dim3(bx), 0, st, u_out, fixcl, movcl, CG,
                   g, g0x, g0y, g0z, gu);
         CA_CHECK_LAUNCH("adam_grad");
         if ((rc = box(gu, t0)) != CA_OK) return rc;
@@ -396,13 +405,21 @@ extern "C" int ca_adam_run(const float* fix, const float* mov, int C, int ha, in
         upd.s.neg_step_size = (float)(-(lr / bc1));
         if (fast) {
             // third pass of B^3 g_u fused with the Adam step; dL/dp is stored only when the caller asks for it
-            if ((rc = field_box(t1, g_out, ha, wa, da, zero_row, &upd, st)) != CA_OK) return rc;
+            if ((rc = field_box(t1, g_out, hl, wa, da, zero_row, &upd, st)) != CA_OK) return rc;
         } else {
             float* gp = g_out ? g_out : t0;
             if ((rc = box(t1, gp)) != CA_OK) return rc;
-            CA_LAUNCH(k_adam_update, dim3(adam_grid(3 * n, 256)), dim3(256), 0, st, p, m, v, gp, 3 * n, upd.s);
+            CA_LAUNCH(k_adam_update, dim3(adam_grid(3 * nw, 256)), dim3(256), 0, st, p, m, v, gp, 3 * nw, upd.s);
             CA_CHECK_LAUNCH("adam_update");
         }
     }
     return CA_OK;
+}
+
+extern "C" int ca_adam_run(const float* fix, const float* mov, int C, int ha, int wa, int da, float lambda_weight, float* p,
+                           float* m, float* v, int first_step, int niter, const float* g0x, const float* g0y,
+                           const float* g0z, float* u_out, float* g_out, void* workspace, size_t workspace_bytes,
+                           ca_stream_t stream) {
+    return ca_adam_run_window(fix, mov, C, ha, wa, da, 0, ha, lambda_weight, p, m, v, first_step, niter, g0x, g0y, g0z, u_out,
+                              g_out, workspace, workspace_bytes, 0, stream);
 }

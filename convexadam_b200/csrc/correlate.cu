@@ -59,19 +59,19 @@ static TileGeom make_tile(int dF, int nthreads) {
     return t;
 }
 
-// Chunk buffer of raw SSD planes: (G*S planes) x h x (w+4) x (dF+8) floats, voxel (x,y,z) of a plane at
-// [x][y+2][z+4].  Rows -2,-1,w,w+1 and the 4+4 pad columns are zero (memset once per call, kernels write interiors
+// Chunk buffer of raw SSD planes: (G*S planes) x nx x (w+4) x (dF+8) floats, voxel (x,y,z) of a plane at
+// [x-r0][y+2][z+4], where [r0, r0+nx) are the H planes a slab of outputs needs (the whole volume: r0 = 0, nx = h).  Rows -2,-1,w,w+1 and the 4+4 pad columns are zero (memset once per call, kernels write interiors
 // only), columns d..dF-1 are written as zero: the box kernel reads rows/columns around a tile without bounds checks.
 struct RawLayout {
     int rowPitch;       // dF + 8
     int64_t xPitch;     // (w + 4) * rowPitch
-    int64_t plane;      // h * xPitch
+    int64_t plane;      // nx * xPitch
 };
-static RawLayout make_raw_layout(int h, int w, int dF) {
+static RawLayout make_raw_layout(int nx, int w, int dF) {
     RawLayout r;
     r.rowPitch = dF + 8;
     r.xPitch = (int64_t)(w + 4) * r.rowPitch;
-    r.plane = (int64_t)h * r.xPitch;
+    r.plane = (int64_t)nx * r.xPitch;
     return r;
 }
 
@@ -79,7 +79,7 @@ static RawLayout make_raw_layout(int h, int w, int dF) {
 template <int HW, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_raw_ssd(const float* __restrict__ fixp, const float* __restrict__ movp,
                                                        int C, int h, int w, int d, int dF, int dP, int chunk_start,
-                                                       int zq, int nzb, RawLayout rl, float* __restrict__ raw) {
+                                                       int zq, int nzb, RawLayout rl, int r0, float* __restrict__ raw) {
     constexpr int S = 2 * HW + 1;
     constexpr int NM = (4 + 2 * HW + 3) & ~3;   // moving values touched by 4 voxels x S shifts, rounded to float4
     // grid = (pairs of the chunk, tiles of a plane, h): the blocks in flight share one slab of the feature volumes
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128, MINB) k_raw_ssd(const float* __restrict__
     const int bz = (int)blockIdx.y % nzb, byi = (int)blockIdx.y / nzb;
     const int q = bz * (int)blockDim.x + (int)threadIdx.x;
     const int y = byi * (int)blockDim.y + (int)threadIdx.y;
-    const int x = (int)blockIdx.z;
+    const int x = r0 + (int)blockIdx.z;
     if (q >= zq || y >= w) return;
     const int z0 = q * 4;
     const int pi = chunk_start + (int)blockIdx.x;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(128, MINB) k_raw_ssd(const float* __restrict__
                 acc[k][i] = __fadd_rn(acc[k][i], __fmul_rn(df, df));
             }
     }
-    float* rp = raw + (int64_t)blockIdx.x * S * rl.plane + (int64_t)x * rl.xPitch + (int64_t)(y + 2) * rl.rowPitch + 4 + z0;
+    float* rp = raw + (int64_t)blockIdx.x * S * rl.plane + (int64_t)blockIdx.z * rl.xPitch + (int64_t)(y + 2) * rl.rowPitch + 4 + z0;
 #pragma unroll
     for (int k = 0; k < S; ++k) {
         float4 o;
@@ -139,7 +139,10 @@ struct Box12Args {
     const float* raw;
     float* ssd;
     RawLayout rl;
-    int h, w, d, S, chunk_start;
+    int w, d, S, chunk_start;
+    int r0, r1;             // raw planes present in the chunk buffer: global H range [r0, r1)
+    int b0, b1;             // first-box planes the outputs need: [b0, b1) = [xb-1, xe+1) clipped to the volume
+    int xb, xe;             // output planes [xb, xe) of the (L, xe-xb, w, d) slab
     int nq, RP, Ty;         // quads per row, row pairs per CTA (first box), output rows per CTA (second box) = 2*(RP-1)
 };
 
@@ -157,13 +160,13 @@ struct BoxThread {
 };
 
 template <int R, bool DALIGNED>
-static __device__ __forceinline__ void box12_step(int X, int h, BoxThread& t, float (&s1)[3][2][4], float (&s2)[3][2][4],
-                                                  float4 (&cur)[4]) {
+static __device__ __forceinline__ void box12_step(int X, const Box12Args& a, BoxThread& t, float (&s1)[3][2][4],
+                                                  float (&s2)[3][2][4], float4 (&cur)[4]) {
     constexpr int Cs = (R + 1) % 3;
-    if (X > h + 1) return;
+    if (X > a.xe + 1) return;
     const int boff = (X & 1) * t.p1buf;
     // ---- first box: raw plane X in, box1 plane X-1 out (shared memory) ----
-    if (X < h) {
+    if (X < a.r1) {
         float hl[4], hr[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) box_halo(cur[j], t.rawp[j], t.bl, hl[j], hr[j]);
@@ -171,7 +174,8 @@ static __device__ __forceinline__ void box12_step(int X, int h, BoxThread& t, fl
 #pragma unroll
         for (int j = 0; j < 4; ++j) t.rawp[j] += t.xPitch;
     }
-    if (X >= 1 && X <= h) {
+    const bool p1ok = X - 1 >= a.b0 && X - 1 < a.b1;
+    if (p1ok) {
 #pragma unroll
         for (int o = 0; o < 2; ++o)
             if (t.p1w[o]) {
@@ -183,12 +187,12 @@ static __device__ __forceinline__ void box12_step(int X, int h, BoxThread& t, fl
     }
     __syncthreads();
     // ---- next raw plane: issued now, consumed after the second box's arithmetic ----
-    if (X + 1 < h) {
+    if (X + 1 < a.r1) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) cur[j] = __ldg(reinterpret_cast<const float4*>(t.rawp[j]));
     }
     // ---- second box: box1 plane P = X-1 in, cost-volume plane P-1 out ----
-    if (X >= 1 && X <= h) {
+    if (p1ok) {
         float4 v[4];
         float hl[4], hr[4];
 #pragma unroll
@@ -198,8 +202,13 @@ static __device__ __forceinline__ void box12_step(int X, int h, BoxThread& t, fl
             box_halo(v[j], quad, t.bl, hl[j], hr[j]);
         }
         box_add_plane<R>(s2, v, hl, hr);
+    } else {
+#pragma unroll
+        for (int o = 0; o < 2; ++o)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s2[R][o][k] = 0.f;      // a plane outside the volume: the fresh sum starts at 0
     }
-    if (X >= 2) {
+    if (X - 2 >= a.xb) {
 #pragma unroll
         for (int o = 0; o < 2; ++o)
             if (t.out[o]) {
@@ -266,7 +275,7 @@ __global__ void __launch_bounds__(512, 1) k_box12(Box12Args a) {
         }
         const int y2 = ty0 + e;                     // second-box (output) row
         const bool in2 = rp < a.RP - 1 && y2 < a.w;
-        t.out[o] = in2 ? a.ssd + (label * a.h * a.w + y2) * a.d + z0 : nullptr;
+        t.out[o] = in2 ? a.ssd + (label * (a.xe - a.xb) * a.w + y2) * a.d + z0 : nullptr;
     }
     float s1[3][2][4], s2[3][2][4];
 #pragma unroll
@@ -279,10 +288,11 @@ __global__ void __launch_bounds__(512, 1) k_box12(Box12Args a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) cur[j] = __ldg(reinterpret_cast<const float4*>(t.rawp[j]));
     __syncthreads();
-    for (int X = 0; X <= a.h + 1; X += 3) {
-        box12_step<0, DALIGNED>(X, a.h, t, s1, s2, cur);
-        box12_step<1, DALIGNED>(X + 1, a.h, t, s1, s2, cur);
-        box12_step<2, DALIGNED>(X + 2, a.h, t, s1, s2, cur);
+    // march over the global planes r0 .. xe+1 (the second box lags one plane behind the first)
+    for (int X = a.r0; X <= a.xe + 1; X += 3) {
+        box12_step<0, DALIGNED>(X, a, t, s1, s2, cur);
+        box12_step<1, DALIGNED>(X + 1, a, t, s1, s2, cur);
+        box12_step<2, DALIGNED>(X + 2, a, t, s1, s2, cur);
     }
 }
 
@@ -290,19 +300,23 @@ namespace {
 struct CorrPlan {
     int S, dF, dP, G;
     int nq, RP, Ty, ntiles, nthreads;
+    int r0, r1, b0, b1;
     RawLayout rl;
     size_t off_fix, off_mov, off_raw, off_keys, total, chunk_bytes, box_smem;
 };
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-// G = number of (kH,kW) pairs per chunk; G<=0 -> default (raw chunk buffer of up to ~3 GB: a handful of launches)
-CorrPlan make_plan(int C, int h, int w, int d, int hw, int G) {
+// G = number of (kH,kW) pairs per chunk; G<=0 -> default (raw chunk buffer of up to ~3 GB: a handful of launches).
+// [xb, xe) = the H planes of the cost volume to produce (a slab of a spatially split pair; the whole volume: 0, h).
+CorrPlan make_plan(int C, int h, int w, int d, int hw, int xb, int xe, int G) {
     CorrPlan p;
     p.S = 2 * hw + 1;
     p.dF = ca_roundup4(d);
     p.dP = p.dF + ca_roundup4(4 + 2 * hw) - 4;
-    p.rl = make_raw_layout(h, w, p.dF);
+    p.r0 = ca_max(0, xb - 2); p.r1 = ca_min(h, xe + 2);
+    p.b0 = ca_max(0, xb - 1); p.b1 = ca_min(h, xe + 1);
+    p.rl = make_raw_layout(p.r1 - p.r0, w, p.dF);
     // box12 tiling: whole rows per CTA (nq quads), RP row pairs of the first box -> Ty = 2*(RP-1) output rows
     p.nq = p.dF / 4;
     int rp_max = 512 / p.nq;
@@ -329,7 +343,7 @@ CorrPlan make_plan(int C, int h, int w, int d, int hw, int G) {
     p.off_mov = o; o = align256(o + (size_t)C * (h + 2 * hw) * (w + 2 * hw) * p.dP * 4);
     p.chunk_bytes = (size_t)G * pair_bytes;
     p.off_raw = o; o = align256(o + p.chunk_bytes);
-    p.off_keys = o; o = align256(o + (size_t)h * w * d * 8);
+    p.off_keys = o; o = align256(o + (size_t)(xe - xb) * w * d * 8);
     p.total = o;
     return p;
 }
@@ -337,35 +351,39 @@ CorrPlan make_plan(int C, int h, int w, int d, int hw, int G) {
 static int g_raw_minb = 0;   // tuning knob (CA_RAW_MINB env, read once): min resident blocks per SM of k_raw_ssd
 
 template <int HW>
-void launch_raw(const float* fixp, const float* movp, int C, int h, int w, int d, int dF, int dP, int chunk_start, int g,
-                const RawLayout& rl, float* raw, cudaStream_t st) {
-    const TileGeom t = make_tile(dF, 128);
-    const dim3 grid((unsigned)g, (unsigned)(t.nzb * ((w + t.by - 1) / t.by)), (unsigned)h), block(t.bx, t.by);
+void launch_raw(const float* fixp, const float* movp, int C, int h, int w, int d, int chunk_start, int g, const CorrPlan& p,
+                float* raw, cudaStream_t st) {
+    const TileGeom t = make_tile(p.dF, 128);
+    const dim3 grid((unsigned)g, (unsigned)(t.nzb * ((w + t.by - 1) / t.by)), (unsigned)(p.r1 - p.r0)), block(t.bx, t.by);
     if (g_raw_minb == 0) {
         const char* e = getenv("CA_RAW_MINB");
         g_raw_minb = e ? atoi(e) : 6;
         if (g_raw_minb != 4 && g_raw_minb != 8) g_raw_minb = 6;
     }
-    if (g_raw_minb == 4) { auto k = k_raw_ssd<HW, 4>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, dF, dP, chunk_start, t.zq, t.nzb, rl, raw); }
-    else if (g_raw_minb == 8) { auto k = k_raw_ssd<HW, 8>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, dF, dP, chunk_start, t.zq, t.nzb, rl, raw); }
-    else { auto k = k_raw_ssd<HW, 6>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, dF, dP, chunk_start, t.zq, t.nzb, rl, raw); }
+    if (g_raw_minb == 4) { auto k = k_raw_ssd<HW, 4>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, p.dF, p.dP, chunk_start, t.zq, t.nzb, p.rl, p.r0, raw); }
+    else if (g_raw_minb == 8) { auto k = k_raw_ssd<HW, 8>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, p.dF, p.dP, chunk_start, t.zq, t.nzb, p.rl, p.r0, raw); }
+    else { auto k = k_raw_ssd<HW, 6>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, p.dF, p.dP, chunk_start, t.zq, t.nzb, p.rl, p.r0, raw); }
 }
 }  // namespace
 
-extern "C" size_t ca_correlate_workspace_bytes(int C, int h, int w, int d, int disp_hw) {
-    if (C <= 0 || h <= 0 || w <= 0 || d <= 0 || disp_hw < 1) return 0;
-    return make_plan(C, h, w, d, disp_hw, 0).total;
+extern "C" size_t ca_correlate_slab_workspace_bytes(int C, int h, int w, int d, int disp_hw, int x_begin, int x_end) {
+    if (C <= 0 || h <= 0 || w <= 0 || d <= 0 || disp_hw < 1 || x_begin < 0 || x_end > h || x_begin >= x_end) return 0;
+    return make_plan(C, h, w, d, disp_hw, x_begin, x_end, 0).total;
 }
-
+extern "C" size_t ca_correlate_workspace_bytes(int C, int h, int w, int d, int disp_hw) {
+    return ca_correlate_slab_workspace_bytes(C, h, w, d, disp_hw, 0, h);
+}
 extern "C" size_t ca_correlate_min_workspace_bytes(int C, int h, int w, int d, int disp_hw) {
     if (C <= 0 || h <= 0 || w <= 0 || d <= 0 || disp_hw < 1) return 0;
-    return make_plan(C, h, w, d, disp_hw, 1).total;
+    return make_plan(C, h, w, d, disp_hw, 0, h, 1).total;
 }
 
-extern "C" int ca_correlate(const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, float* ssd,
-                            int64_t* argmin, void* workspace, size_t workspace_bytes, ca_stream_t stream) {
+extern "C" int ca_correlate_slab(const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, int x_begin,
+                                 int x_end, float* ssd, int64_t* argmin, void* workspace, size_t workspace_bytes,
+                                 ca_stream_t stream) {
     CA_CHECK_ARG(fix && mov && ssd && workspace, "correlate: null pointer");
     CA_CHECK_ARG(C > 0 && h > 0 && w > 0 && d > 0, "correlate: bad dims");
+    CA_CHECK_ARG(x_begin >= 0 && x_end <= h && x_begin < x_end, "correlate: bad slab [%d, %d) of %d planes", x_begin, x_end, h);
     if (disp_hw < 1 || disp_hw > 8) {
         ca_set_error("correlate: disp_hw=%d unsupported (1..8)", disp_hw);
         return CA_ERR_UNSUPPORTED;
@@ -376,17 +394,17 @@ extern "C" int ca_correlate(const float* fix, const float* mov, int C, int h, in
     }
     CA_CHECK_ARG((int64_t)h * (w + 4) * (ca_roundup4(d) + 8) < (1ll << 31) && h < 65536, "correlate: coarse grid too large");
     // largest chunk that fits the caller's workspace (>= 1 pair), capped at the default plan
-    CorrPlan p = make_plan(C, h, w, d, disp_hw, 0);
+    CorrPlan p = make_plan(C, h, w, d, disp_hw, x_begin, x_end, 0);
     if (p.total > workspace_bytes) {
-        const CorrPlan p1 = make_plan(C, h, w, d, disp_hw, 1);
+        const CorrPlan p1 = make_plan(C, h, w, d, disp_hw, x_begin, x_end, 1);
         if (p1.total > workspace_bytes) {
             ca_set_error("correlate: workspace too small (%zu < %zu)", workspace_bytes, p1.total);
             return CA_ERR_WORKSPACE;
         }
         const size_t pair_bytes = p1.chunk_bytes;
         int G = 1 + (int)((workspace_bytes - p1.total) / pair_bytes);
-        p = make_plan(C, h, w, d, disp_hw, G);
-        while (p.total > workspace_bytes && p.G > 1) p = make_plan(C, h, w, d, disp_hw, p.G - 1);
+        p = make_plan(C, h, w, d, disp_hw, x_begin, x_end, G);
+        while (p.total > workspace_bytes && p.G > 1) p = make_plan(C, h, w, d, disp_hw, x_begin, x_end, p.G - 1);
     }
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
@@ -422,19 +440,20 @@ extern "C" int ca_correlate(const float* fix, const float* mov, int C, int h, in
     for (int cs = 0; cs < npairs; cs += p.G) {
         const int g = ca_min(p.G, npairs - cs);
         switch (disp_hw) {
-            case 1: launch_raw<1>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, p.rl, raw, st); break;
-            case 2: launch_raw<2>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, p.rl, raw, st); break;
-            case 3: launch_raw<3>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, p.rl, raw, st); break;
-            case 4: launch_raw<4>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, p.rl, raw, st); break;
-            case 5: launch_raw<5>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, p.rl, raw, st); break;
-            case 6: launch_raw<6>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, p.rl, raw, st); break;
-            case 7: launch_raw<7>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, p.rl, raw, st); break;
-            default: launch_raw<8>(fixp, movp, C, h, w, d, p.dF, p.dP, cs, g, p.rl, raw, st); break;
+            case 1: launch_raw<1>(fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
+            case 2: launch_raw<2>(fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
+            case 3: launch_raw<3>(fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
+            case 4: launch_raw<4>(fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
+            case 5: launch_raw<5>(fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
+            case 6: launch_raw<6>(fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
+            case 7: launch_raw<7>(fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
+            default: launch_raw<8>(fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
         }
         CA_CHECK_LAUNCH("correlate/raw");
         Box12Args a;
         a.raw = raw; a.ssd = ssd; a.rl = p.rl;
-        a.h = h; a.w = w; a.d = d; a.S = S; a.chunk_start = cs;
+        a.w = w; a.d = d; a.S = S; a.chunk_start = cs;
+        a.r0 = p.r0; a.r1 = p.r1; a.b0 = p.b0; a.b1 = p.b1; a.xb = x_begin; a.xe = x_end;
         a.nq = p.nq; a.RP = p.RP; a.Ty = p.Ty;
         const dim3 bgrid((unsigned)p.ntiles, (unsigned)(g * S)), bblock((unsigned)p.nthreads);
         if ((d & 3) == 0) { auto k = k_box12<true>; CA_LAUNCH(k, bgrid, bblock, p.box_smem, st, a); }
@@ -443,11 +462,16 @@ extern "C" int ca_correlate(const float* fix, const float* mov, int C, int h, in
     }
     if (argmin) {
         unsigned long long* keys = (unsigned long long*)(ws + p.off_keys);
-        const int64_t n = (int64_t)h * w * d;
+        const int64_t n = (int64_t)(x_end - x_begin) * w * d;
         int rc = ca_launch_cost_argmin(ssd, n, S * S * S, nullptr, nullptr, 0.f, keys, st);
         if (rc != CA_OK) return rc;
         rc = ca_launch_keys_to_i64(keys, n, argmin, st);
         if (rc != CA_OK) return rc;
     }
     return CA_OK;
+}
+
+extern "C" int ca_correlate(const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, float* ssd,
+                            int64_t* argmin, void* workspace, size_t workspace_bytes, ca_stream_t stream) {
+    return ca_correlate_slab(fix, mov, C, h, w, d, disp_hw, 0, h, ssd, argmin, workspace, workspace_bytes, stream);
 }

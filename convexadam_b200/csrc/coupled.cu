@@ -181,3 +181,57 @@ extern "C" int ca_coupled_convex(const float* ssd, const int64_t* argmin, const 
     }
     return CA_OK;
 }
+
+// ---- the same stage in pieces, for a pair that is split into H slabs over several GPUs --------------------------------
+// The host runs the loop of utils.py:98-107 itself and exchanges one plane of selected labels with the neighbouring
+// slabs before each smoothing step (convexadam_b200/slab.py).
+
+// soft[c](x) = box3(mesh[c, sel])(x) for the planes [1, P-1) of a (P, w, d) window of labels; a negative label marks a
+// plane outside the volume (zero padding of avg_pool3d: the tap is skipped).
+__global__ void __launch_bounds__(256) k_soft_from_label_window(const int64_t* __restrict__ sel, const float* __restrict__ mesh,
+                                                                int P, int w, int d, int L, float* __restrict__ soft) {
+    const int64_t n = (int64_t)(P - 2) * w * d;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+        const int z = (int)(o % d), y = (int)((o / d) % w), x = (int)(o / ((int64_t)d * w)) + 1;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int xx = x - 1; xx < x + 2; ++xx)
+            for (int yy = ca_max(y - 1, 0); yy < ca_min(y + 2, w); ++yy)
+                for (int zz = ca_max(z - 1, 0); zz < ca_min(z + 2, d); ++zz) {
+                    const int64_t l = sel[((int64_t)xx * w + yy) * d + zz];
+                    if (l < 0) continue;
+                    a0 = __fadd_rn(a0, __ldg(mesh + l));
+                    a1 = __fadd_rn(a1, __ldg(mesh + L + l));
+                    a2 = __fadd_rn(a2, __ldg(mesh + 2 * L + l));
+                }
+        soft[o] = ca_div(a0, 27.f);
+        soft[n + o] = ca_div(a1, 27.f);
+        soft[2 * n + o] = ca_div(a2, 27.f);
+    }
+}
+
+extern "C" size_t ca_cc_select_workspace_bytes(int64_t n) { return (size_t)n * 8 + 256; }
+
+extern "C" int ca_cc_select(const float* ssd, int64_t n, int disp_hw, const float* mesh, const float* soft, float coeff,
+                            int64_t* sel, void* workspace, size_t workspace_bytes, ca_stream_t stream) {
+    CA_CHECK_ARG(ssd && sel && workspace && n > 0 && disp_hw >= 1, "cc_select: bad argument");
+    CA_CHECK_ARG((mesh == nullptr) == (soft == nullptr), "cc_select: mesh and soft go together");
+    if (workspace_bytes < ca_cc_select_workspace_bytes(n)) {
+        ca_set_error("cc_select: workspace too small");
+        return CA_ERR_WORKSPACE;
+    }
+    const int S = 2 * disp_hw + 1;
+    unsigned long long* keys = (unsigned long long*)workspace;
+    int rc = ca_launch_cost_argmin(ssd, n, S * S * S, mesh, soft, coeff, keys, (cudaStream_t)stream);
+    if (rc != CA_OK) return rc;
+    return ca_launch_keys_to_i64(keys, n, sel, (cudaStream_t)stream);
+}
+
+extern "C" int ca_cc_smooth(const int64_t* sel_window, const float* mesh, int P, int w, int d, int disp_hw, float* soft,
+                            ca_stream_t stream) {
+    CA_CHECK_ARG(sel_window && mesh && soft && P >= 3 && w > 0 && d > 0 && disp_hw >= 1, "cc_smooth: bad argument");
+    const int S = 2 * disp_hw + 1;
+    const int64_t n = (int64_t)(P - 2) * w * d;
+    CA_LAUNCH(k_soft_from_label_window, dim3(small_grid(n)), dim3(256), 0, (cudaStream_t)stream, sel_window, mesh, P, w, d, S * S * S, soft);
+    CA_CHECK_LAUNCH("cc_smooth");
+    return CA_OK;
+}

@@ -54,6 +54,13 @@ def convex_stage(lib: Lib, fix_s, mov_s, shape, prm: Params, ssd_buf=None):
     _mark("correlate")
     soft_ = lib.coupled_convex(ssd, am, mesh, prm.disp_hw)
     _mark("coupled_convex")
+    return ic_and_upsample(lib, soft, soft_, shape, prm)
+
+
+def ic_and_upsample(lib: Lib, soft, soft_, shape, prm: Params):
+    """Inverse consistency of the two coarse fields and upsampling to full resolution (MIND.py:133-141)."""
+    H, W, D = shape
+    _, h, w, d = soft.shape
     # scale = tensor([h-1, w-1, d-1]) / 2 (MIND.py:134); (disp/scale).flip(1) (:139)
     scale = tuple(float(torch.tensor(float(s - 1)) / 2) for s in (h, w, d))
     a = lib.field_affine(soft, flip=True, div=scale)
@@ -74,10 +81,23 @@ def adam_stage(lib: Lib, disp_hr, fix_a, mov_a, shape, prm: Params):
         raise ValueError("selected_niter must be >= 1 when lambda_weight > 0")
     ha, wa, da = fix_a.shape[1:]
     gsa = float(prm.grid_sp_adam)
-    p = lib.field_affine(lib.trilinear(disp_hr, (ha, wa, da)), div=(gsa, gsa, gsa))      # :153,156
+    p = adam_start(lib, disp_hr, (ha, wa, da), prm)
     m = torch.zeros_like(p)
     v = torch.zeros_like(p)
     u = lib.adam_run(fix_a, mov_a, float(prm.lambda_weight), p, m, v, 1, int(prm.selected_niter))
+    return adam_finish(lib, u, shape, prm)
+
+
+def adam_start(lib: Lib, disp_hr, grid, prm: Params):
+    """Initial Adam parameters: the start field resized to the Adam grid, in Adam-grid voxels (MIND.py:153,156)."""
+    gsa = float(prm.grid_sp_adam)
+    return lib.field_affine(lib.trilinear(disp_hr, tuple(grid)), div=(gsa, gsa, gsa))
+
+
+def adam_finish(lib: Lib, u, shape, prm: Params):
+    """u of the last forward -> dense field in voxels, optional 3x box smoothing (MIND.py:181-191)."""
+    H, W, D = shape
+    gsa = float(prm.grid_sp_adam)
     out = lib.trilinear(lib.field_affine(u, mul2=gsa), (H, W, D))                           # :181-182
     if prm.selected_smooth > 0:
         if prm.selected_smooth % 2 == 0:

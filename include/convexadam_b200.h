@@ -85,6 +85,13 @@ CA_API size_t ca_correlate_workspace_bytes(int C, int h, int w, int d, int disp_
 CA_API size_t ca_correlate_min_workspace_bytes(int C, int h, int w, int d, int disp_hw);
 CA_API int ca_correlate(const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, float* ssd,
                  int64_t* argmin, void* workspace, size_t workspace_bytes, ca_stream_t stream);
+/* The same for the H planes [x_begin, x_end) only: ssd (L, x_end-x_begin, w, d), argmin (x_end-x_begin, w, d).  The
+ * features are still the whole (C,h,w,d) volumes (a slab needs 2 + 2*disp_hw planes of context).  Used when one
+ * oversized pair is split into H slabs over several GPUs; values are those of the full call. */
+CA_API size_t ca_correlate_slab_workspace_bytes(int C, int h, int w, int d, int disp_hw, int x_begin, int x_end);
+CA_API int ca_correlate_slab(const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, int x_begin,
+                      int x_end, float* ssd, int64_t* argmin, void* workspace, size_t workspace_bytes,
+                      ca_stream_t stream);
 
 /* ---- coupled_convex (utils.py:93-109) -----------------------------------------------------------------------
  * ssd (L,h,w,d); argmin (h,w,d) int64; mesh (3,L) f32 = disp_mesh_t of MIND.py:127 (pass the values torch's
@@ -94,6 +101,17 @@ CA_API size_t ca_coupled_convex_workspace_bytes(int h, int w, int d, int disp_hw
 CA_API int ca_coupled_convex(const float* ssd, const int64_t* argmin, const float* mesh, int h, int w, int d, int disp_hw,
                       float* disp_soft, int64_t* sel_out, void* workspace, size_t workspace_bytes,
                       ca_stream_t stream);
+
+/* coupled_convex in pieces (the loop of utils.py:98-107 run by the host, for H slabs with a halo exchange in between):
+ * ca_cc_select: sel(x) = argmin_l ( ssd_l(x) + coeff * || mesh_l - soft(x) ||^2 ) over n voxels (utils.py:104-105);
+ *               mesh == soft == NULL gives the plain argmin of utils.py:87.  ssd (L,n), soft (3,n), sel (n) int64.
+ * ca_cc_smooth: soft = box3(mesh[:, sel]) (utils.py:96,107) for the planes [1, P-1) of a (P,w,d) window of labels whose
+ *               first/last plane come from the neighbouring slab; a negative label = outside the volume. soft (3,P-2,w,d). */
+CA_API size_t ca_cc_select_workspace_bytes(int64_t n);
+CA_API int ca_cc_select(const float* ssd, int64_t n, int disp_hw, const float* mesh, const float* soft, float coeff,
+                 int64_t* sel, void* workspace, size_t workspace_bytes, ca_stream_t stream);
+CA_API int ca_cc_smooth(const int64_t* sel_window, const float* mesh, int P, int w, int d, int disp_hw, float* soft,
+                 ca_stream_t stream);
 
 /* ---- inverse_consistency (utils.py:114-129) -------------------------------------------------------------------
  * f1, f2: (3,h,w,d) f32, normalised units, channel 0 = x (last array axis) as in the reference call at
@@ -126,6 +144,17 @@ CA_API size_t ca_adam_workspace_bytes(int C, int ha, int wa, int da);
 CA_API int ca_adam_run(const float* fix, const float* mov, int C, int ha, int wa, int da, float lambda_weight, float* p,
                 float* m, float* v, int first_step, int niter, const float* g0x, const float* g0y, const float* g0z,
                 float* u_out, float* g_out, void* workspace, size_t workspace_bytes, ca_stream_t stream);
+
+/* The same on a window of the Adam grid: p, m, v, u_out, g_out hold the H planes [lo, hi) only, (3, hi-lo, wa, da);
+ * fix, mov and the grid axes stay whole-grid.  Window edges that are not faces of the grid are treated like faces, so
+ * after one iteration only the planes at least 7 away from such an edge are exact (3 + 1 + 3: B^3, the regulariser's
+ * neighbours, B^3): the caller owns the interior and refreshes the margin of p from its neighbours every iteration.
+ * features_ready != 0: the channel-last copies of fix/mov made by an earlier call are still in `workspace`. */
+CA_API size_t ca_adam_window_workspace_bytes(int C, int ha, int wa, int da, int lo, int hi);
+CA_API int ca_adam_run_window(const float* fix, const float* mov, int C, int ha, int wa, int da, int lo, int hi,
+                       float lambda_weight, float* p, float* m, float* v, int first_step, int niter, const float* g0x,
+                       const float* g0y, const float* g0z, float* u_out, float* g_out, void* workspace,
+                       size_t workspace_bytes, int features_ready, ca_stream_t stream);
 
 /* ---- output packing (MIND.py:198-202) --------------------------------------------------------------------------
  * field (3,H,W,D) f32 -> out (H,W,D,3) f64; round_half != 0 rounds every value through IEEE half first

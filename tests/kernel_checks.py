@@ -93,6 +93,65 @@ def check_coupled(lib, device, C=12, h=6, w=7, d=8, hw=2):
     assert_bits_equal(N(soft), soft_o, "coupled_convex soft (ragged)")
 
 
+def check_correlate_slab(lib, device, C=4, h=9, w=6, d=8, hw=2, slabs=((0, 3), (3, 4), (4, 9), (0, 1), (8, 9), (2, 7))):
+    """ca_correlate_slab == the same planes of the full call, bit for bit (slab edges inside and at the faces)."""
+    r = rng(70)
+    fix = T(r.rand(C, h, w, d).astype(np.float32), device)
+    mov = T(r.rand(C, h, w, d).astype(np.float32), device)
+    ssd, am = lib.correlate(fix, mov, hw)
+    for (a, b) in slabs:
+        s2, a2 = lib.correlate_slab(fix, mov, hw, a, b)
+        assert_bits_equal(N(s2), N(ssd[:, a:b]), f"correlate_slab ssd [{a},{b})")
+        assert (N(a2) == N(am[a:b])).all(), f"correlate_slab argmin [{a},{b})"
+
+
+def check_cc_pieces(lib, device, C=6, h=7, w=5, d=8, hw=2, cut=3):
+    """The host-run coupled-convex loop over two H slabs with a one-plane label exchange == ca_coupled_convex."""
+    r = rng(71)
+    fix = T(r.rand(C, h, w, d).astype(np.float32), device)
+    mov = T(r.rand(C, h, w, d).astype(np.float32), device)
+    ssd, am = lib.correlate(fix, mov, hw)
+    mesh = lib.disp_mesh(hw, device)
+    want = lib.coupled_convex(ssd, am, mesh, hw)
+    slabs = [(0, cut), (cut, h)]
+    ssds = [ssd[:, a:b].contiguous() for a, b in slabs]
+    sels = [am[a:b].contiguous() for a, b in slabs]
+    pad = torch.full((1, w, d), -1, dtype=torch.int64, device=device)
+    softs = None
+    for j in range(7):
+        wins = [torch.cat([pad, sels[0], sels[1][:1]], 0), torch.cat([sels[0][-1:], sels[1], pad], 0)]
+        softs = [lib.cc_smooth(wv.contiguous(), mesh, hw) for wv in wins]
+        if j == 6:
+            break
+        coeff = (0.003, 0.01, 0.03, 0.1, 0.3, 1.0)[j]
+        sels = [lib.cc_select(ssds[i], hw, mesh, softs[i], coeff) for i in range(2)]
+    got = torch.cat(softs, 1)
+    assert_bits_equal(N(got), N(want), "coupled_convex in slabs")
+    assert (N(lib.cc_select(ssd, hw)) == N(am)).all(), "cc_select without regulariser == argmin"
+
+
+def check_adam_window(lib, device, C=5, shape=(40, 6, 8), lam=1.25, lo=3, hi=37, iters=2):
+    """Adam on a window of the grid: after k iterations the planes >= 7k away from a cut edge equal the full run."""
+    r = rng(72)
+    fix = T(r.rand(C, *shape).astype(np.float32), device)
+    mov = T(r.rand(C, *shape).astype(np.float32), device)
+    p0 = (r.randn(3, *shape) * 1.2).astype(np.float32)
+    p, m, v = T(p0, device), T(np.zeros_like(p0), device), T(np.zeros_like(p0), device)
+    for k in range(iters):
+        u_full = lib.adam_run(fix, mov, lam, p, m, v, k + 1, 1)
+    pw, mw, vw = (T(p0[:, lo:hi], device), T(np.zeros_like(p0[:, lo:hi]), device), T(np.zeros_like(p0[:, lo:hi]), device))
+    ws = None
+    for k in range(iters):
+        u_win, ws = lib.adam_window(fix, mov, lam, lo, hi, pw, mw, vw, k + 1, 1, ws=ws, features_ready=k > 0)
+    a = lo + (7 * iters if lo > 0 else 0)
+    b = hi - (7 * iters if hi < shape[0] else 0)
+    assert b > a
+    assert_bits_equal(N(pw[:, a - lo:b - lo]), N(p[:, a:b]), "adam window p")
+    ua = lo + (7 * (iters - 1) + 4 if lo > 0 else 0)
+    ub = hi - (7 * (iters - 1) + 4 if hi < shape[0] else 0)
+    assert_bits_equal(N(u_win[:, ua - lo:ub - lo]), N(u_full[:, ua:ub]), "adam window u")
+
+
 def check_mesh_and_axes(lib, device):
     for hw in (1, 2, 3, 4, 6, 8):
         assert_bits_equal(N(lib.disp_mesh(hw, device)), orc.disp_mesh(hw), f"mesh hw={hw}")

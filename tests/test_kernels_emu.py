@@ -30,3 +30,6 @@ def test_inverse_consistency(lib): kc.check_inverse_consistency(lib, DEV, shape=
 def test_trilinear_affine_pack(lib): kc.check_trilinear_affine_pack(lib, DEV)
 def test_onehot(lib): kc.check_onehot(lib, DEV)
 def test_adam(lib): kc.check_adam(lib, DEV, shape=(6, 7, 8), steps=(1, 3))
+def test_correlate_slab(lib): kc.check_correlate_slab(lib, DEV)
+def test_cc_pieces(lib): kc.check_cc_pieces(lib, DEV)
+def test_adam_window(lib): kc.check_adam_window(lib, DEV)

@@ -36,6 +36,15 @@ def test_correlate(lib, dev):
                                         (12, 6, 5, 7, 5), (12, 8, 6, 12, 6), (4, 4, 4, 4, 7), (12, 5, 5, 8, 8)))
 
 
+def test_correlate_slab(lib, dev):
+    kc.check_correlate_slab(lib, dev)
+    kc.check_correlate_slab(lib, dev, C=12, h=20, w=14, d=24, hw=3, slabs=((0, 10), (10, 20), (7, 8), (18, 20)))
+
+
+def test_cc_pieces(lib, dev): kc.check_cc_pieces(lib, dev, C=12, h=11, w=9, d=12, hw=3, cut=5)
+def test_adam_window(lib, dev): kc.check_adam_window(lib, dev, C=12, shape=(44, 10, 16))
+
+
 def test_coupled(lib, dev):
     kc.check_coupled(lib, dev, h=12, w=10, d=16, hw=3)
     kc.check_coupled(lib, dev, h=6, w=7, d=9, hw=6)
