@@ -30,7 +30,8 @@ _SIGS = {
     "ca_correlate_slab_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "ca_correlate_slab": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "ca_cc_select_workspace_bytes": (_sz, [_i64]),
-    "ca_cc_select": (_i, [_vp, _i64, _i, _vp, _vp, _f, _vp, _vp, _sz, _vp]),
+    "ca_cc_blockmin": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _sz, _vp]),
+    "ca_cc_select": (_i, [_vp, _i64, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ca_cc_smooth": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "ca_adam_window_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "ca_adam_run_window": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
@@ -197,17 +198,33 @@ class Lib:
                                             self._p(am), self._p(ws), nb, self._stream(fix)))
         return ssd, am
 
-    def cc_select(self, ssd, disp_hw, mesh=None, soft=None, coeff=0.0):
-        """One pass of coupled_convex over a slab: ssd (L,hs,w,d), soft (3,hs,w,d) -> labels (hs,w,d) int64."""
+    def cc_blockmin(self, ssd, disp_hw, want_argmin=True):
+        """Block minima (S*S planes) and slab minima (S more planes) of a slab's cost volume, (S*S+S,hs,w,d), and its plain
+        argmin, in one pass."""
+        ssd = self._t(ssd)
+        n = ssd[0].numel()
+        S = 2 * disp_hw + 1
+        bmin = torch.empty((S * S + S,) + tuple(ssd.shape[1:]), dtype=torch.float32, device=ssd.device)
+        am = torch.empty(ssd.shape[1:], dtype=torch.int64, device=ssd.device) if want_argmin else None
+        nb = self.dll.ca_cc_select_workspace_bytes(n)
+        ws = self._ws(nb, ssd)
+        self._chk(self.dll.ca_cc_blockmin(self._p(ssd), n, disp_hw, self._p(bmin), self._p(am), self._p(ws), nb, self._stream(ssd)))
+        return bmin, am
+
+    def cc_select(self, ssd, disp_hw, mesh=None, soft=None, coeff=0.0, bmin=None, prev=None):
+        """One pass of coupled_convex over a slab: ssd (L,hs,w,d), soft (3,hs,w,d) -> labels (hs,w,d) int64.
+        bmin (from cc_blockmin) + prev (the previous selection) switch on the exact pruning."""
         ssd = self._t(ssd)
         n = ssd[0].numel()
         sel = torch.empty(ssd.shape[1:], dtype=torch.int64, device=ssd.device)
         mesh = self._t(mesh.reshape(3, -1)) if mesh is not None else None
         soft = self._t(soft) if soft is not None else None
+        bmin = self._t(bmin) if bmin is not None else None
+        prev = self._t(prev, torch.int64) if prev is not None else None
         nb = self.dll.ca_cc_select_workspace_bytes(n)
         ws = self._ws(nb, ssd)
-        self._chk(self.dll.ca_cc_select(self._p(ssd), n, disp_hw, self._p(mesh), self._p(soft), float(coeff), self._p(sel),
-                                       self._p(ws), nb, self._stream(ssd)))
+        self._chk(self.dll.ca_cc_select(self._p(ssd), n, disp_hw, self._p(mesh), self._p(soft), float(coeff), self._p(bmin),
+                                       self._p(prev), self._p(sel), self._p(ws), nb, self._stream(ssd)))
         return sel
 
     def cc_smooth(self, sel_window, mesh, disp_hw):
@@ -222,7 +239,7 @@ class Lib:
 
     def coupled_convex(self, ssd, argmin, mesh, disp_hw, want_sel=False):
         ssd = self._t(ssd)
-        argmin = self._t(argmin, torch.int64)
+        argmin = self._t(argmin, torch.int64) if argmin is not None else None      # None: taken inside, no extra pass
         mesh = self._t(mesh.reshape(3, -1))
         L, h, w, d = ssd.shape
         if L != (2 * disp_hw + 1) ** 3 or mesh.shape[1] != L:

@@ -14,6 +14,7 @@
 #include "ca_platform.h"
 
 #include <cmath>
+#include <cstdlib>
 
 static __device__ __forceinline__ unsigned long long pack_key(float cost, int label) {
     return ((unsigned long long)__float_as_uint(cost) << 32) | (unsigned)label;
@@ -106,6 +107,245 @@ __global__ void __launch_bounds__(256) k_i64_to_keys(const int64_t* __restrict__
         keys[o] = (unsigned long long)in[o] & 0xffffffffull;
 }
 
+// ---- exact pruning of the six passes -----------------------------------------------------------------------------------
+// Labels come in blocks of S consecutive ones (same kD and kW, all kH): mesh[1] and mesh[2] are constant inside a block.
+// With bmin_b(x) = min of ssd over block b, every label l of the block satisfies, in the reference's own rounded
+// arithmetic (every step below is monotone in its arguments),
+//     cost_l = RN(ssd_l + RN(coeff * RN(RN(q0 + q1) + q2)))  >=  RN(bmin_b + RN(coeff * RN(q1 + q2)))  =: lb_b
+// (q_c = RN(RN(mesh_c - s_c)^2), q0 >= 0).  If lb_b exceeds the cost U of ANY label (here: the previous pass's winner,
+// evaluated exactly), no label of block b can be the argmin nor tie with it, so the block is skipped without reading
+// it.  The winner's own block, and every block holding an equal cost, has lb <= U and is scanned in label order with
+// the same strict `<` as the full pass: the selection is the reference's, bit for bit, ties included.
+
+// one streaming pass over the volume: bmin (S*S, n) block minima, smin (S, n) minima over the S blocks that share kD
+// ("slabs" of S*S labels), and the plain argmin (utils.py:87) merged into keys.  blockIdx.y = slab.
+template <int VEC>
+__global__ void __launch_bounds__(256) k_blockmin_argmin(const float* __restrict__ ssd, int64_t n, int S, float* __restrict__ bmin,
+                                                         float* __restrict__ smin, unsigned long long* __restrict__ keys) {
+    const int slab = (int)blockIdx.y;
+    const int64_t v0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (v0 >= n) return;
+    float best[VEC], sm[VEC];
+    int bl[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { best[i] = INFINITY; sm[i] = INFINITY; bl[i] = slab * S * S; }
+    const float* sp = ssd + v0;
+    for (int b = slab * S; b < (slab + 1) * S; ++b) {
+        float bm[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) bm[i] = INFINITY;
+#pragma unroll 4
+        for (int k = 0; k < S; ++k) {
+            const int l = b * S + k;
+            float c[VEC];
+            if (VEC == 4) {
+                const float4 c4 = ca_ld_stream4(reinterpret_cast<const float4*>(sp + (int64_t)l * n));
+                c[0] = c4.x; c[1 % VEC] = c4.y; c[2 % VEC] = c4.z; c[3 % VEC] = c4.w;
+            } else {
+                c[0] = ca_ld_stream1(sp + (int64_t)l * n);
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                bm[i] = fminf(bm[i], c[i]);
+                if (c[i] < best[i]) { best[i] = c[i]; bl[i] = l; }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) sm[i] = fminf(sm[i], bm[i]);
+        if (VEC == 4) *reinterpret_cast<float4*>(bmin + (int64_t)b * n + v0) = make_float4(bm[0], bm[1 % VEC], bm[2 % VEC], bm[3 % VEC]);
+        else bmin[(int64_t)b * n + v0] = bm[0];
+    }
+    if (VEC == 4) *reinterpret_cast<float4*>(smin + (int64_t)slab * n + v0) = make_float4(sm[0], sm[1 % VEC], sm[2 % VEC], sm[3 % VEC]);
+    else smin[(int64_t)slab * n + v0] = sm[0];
+    if (keys) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) atomicMin(keys + v0 + i, pack_key(best[i], bl[i]));
+    }
+}
+
+// componentwise distance of s to the box [lo, hi], squared and summed in the reference's order: a lower bound of
+// RN(RN(q0 + q1) + q2) for every displacement vector inside the box (|RN(m - s)| >= RN(distance), all steps monotone)
+static __device__ __forceinline__ float box_dist(const float4& lo, const float4& hi, float s0, float s1, float s2) {
+    const float e0 = fmaxf(fmaxf(__fsub_rn(lo.x, s0), __fsub_rn(s0, hi.x)), 0.f);
+    const float e1 = fmaxf(fmaxf(__fsub_rn(lo.y, s1), __fsub_rn(s1, hi.y)), 0.f);
+    const float e2 = fmaxf(fmaxf(__fsub_rn(lo.z, s2), __fsub_rn(s2, hi.z)), 0.f);
+    return __fadd_rn(__fadd_rn(__fmul_rn(e0, e0), __fmul_rn(e1, e1)), __fmul_rn(e2, e2));
+}
+
+// bounding boxes of the displacement vectors of every block of S labels and every slab of S blocks:
+// boxes = [blo (B) | bhi (B) | slo (S) | shi (S)] float4.  One CTA; the mesh is a per-call constant.
+__global__ void __launch_bounds__(256) k_mesh_boxes(const float* __restrict__ mesh, int L, int S, float4* __restrict__ boxes) {
+    const int B = S * S;
+    float4* blo = boxes;
+    float4* bhi = blo + B;
+    float4* slo = bhi + B;
+    float4* shi = slo + S;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float4 lo = make_float4(mesh[b * S], mesh[L + b * S], mesh[2 * L + b * S], 0.f), hi = lo;
+        for (int k = 1; k < S; ++k) {
+            const int l = b * S + k;
+            lo.x = fminf(lo.x, mesh[l]); lo.y = fminf(lo.y, mesh[L + l]); lo.z = fminf(lo.z, mesh[2 * L + l]);
+            hi.x = fmaxf(hi.x, mesh[l]); hi.y = fmaxf(hi.y, mesh[L + l]); hi.z = fmaxf(hi.z, mesh[2 * L + l]);
+        }
+        blo[b] = lo; bhi[b] = hi;
+    }
+    __syncthreads();
+    for (int sl = threadIdx.x; sl < S; sl += blockDim.x) {
+        float4 lo = blo[sl * S], hi = bhi[sl * S];
+        for (int k = 1; k < S; ++k) {
+            const float4 a = blo[sl * S + k], c = bhi[sl * S + k];
+            lo.x = fminf(lo.x, a.x); lo.y = fminf(lo.y, a.y); lo.z = fminf(lo.z, a.z);
+            hi.x = fmaxf(hi.x, c.x); hi.y = fmaxf(hi.y, c.y); hi.z = fmaxf(hi.z, c.z);
+        }
+        slo[sl] = lo; shi[sl] = hi;
+    }
+}
+
+// one coupled-convex pass that reads the slab minima (S*n floats), the block minima of the slabs that survive, and the
+// labels of the blocks that survive.  The label index is uniform across a warp, so mesh[l] is a broadcast load.
+template <int VEC, int S>
+__global__ void __launch_bounds__(128, 4) k_cost_argmin_pruned(const float* __restrict__ ssd, const float* __restrict__ bmin,
+                                                            const float* __restrict__ smin, int64_t n, int L,
+                                                            const float* __restrict__ mesh, const float4* __restrict__ boxes,
+                                                            const float* __restrict__ soft, float coeff, int row_len,
+                                                            const unsigned long long* __restrict__ prev,
+                                                            unsigned long long* __restrict__ keys) {
+    CA_DYN_SMEM(float4, sbox);
+    const int B = S * S;
+    for (int i = threadIdx.x; i < 2 * B + 2 * S; i += blockDim.x) sbox[i] = boxes[i];
+    __syncthreads();
+    const float4* blo = sbox;
+    const float4* bhi = blo + B;
+    const float4* slo = bhi + B;
+    const float4* shi = slo + S;
+    // a warp covers 4 rows x 32 voxels (row_len > 0) rather than 128 voxels of one row: neighbours in both directions
+    // share their surviving blocks, so the union a warp has to scan is smaller
+    int64_t v0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (VEC == 4 && row_len > 0) {
+        const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const int64_t warp = gt >> 5;
+        const int lane = (int)(gt & 31);
+        const int tpr = row_len / 32;
+        v0 = ((warp / tpr) * 4 + (lane >> 3)) * row_len + (warp % tpr) * 32 + (lane & 7) * 4;
+    }
+    if (v0 >= n) return;
+    float s0[VEC], s1[VEC], s2[VEC], best[VEC], U[VEC];
+    int bl[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        best[i] = INFINITY;
+        bl[i] = 0;
+        s0[i] = soft[v0 + i]; s1[i] = soft[n + v0 + i]; s2[i] = soft[2 * n + v0 + i];
+    }
+    // The bound U: the exact cost, under the new soft field and coefficient, of (a) the previous selection and (b) a label
+    // close to soft(x) found by descending the boxes (slab -> block -> label).  Any label gives a valid bound.
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        int cand[2];
+        cand[0] = (int)(unsigned)(prev[v0 + i] & 0xffffffffull);
+        int bs = 0;
+        float bd = INFINITY;
+        for (int sl = 0; sl < S; ++sl) {
+            const float dd = box_dist(slo[sl], shi[sl], s0[i], s1[i], s2[i]);
+            if (dd < bd) { bd = dd; bs = sl; }
+        }
+        int bb = bs * S;
+        bd = INFINITY;
+        for (int k = 0; k < S; ++k) {
+            const float dd = box_dist(blo[bs * S + k], bhi[bs * S + k], s0[i], s1[i], s2[i]);
+            if (dd < bd) { bd = dd; bb = bs * S + k; }
+        }
+        cand[1] = bb * S;
+        bd = INFINITY;
+        for (int k = 0; k < S; ++k) {
+            const int l = bb * S + k;
+            const float d0 = __ldg(mesh + l) - s0[i], d1 = __ldg(mesh + L + l) - s1[i], d2 = __ldg(mesh + 2 * L + l) - s2[i];
+            const float dd = d0 * d0 + d1 * d1 + d2 * d2;
+            if (dd < bd) { bd = dd; cand[1] = l; }
+        }
+        U[i] = INFINITY;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int r = cand[t];
+            const float d0 = __fsub_rn(__ldg(mesh + r), s0[i]), d1 = __fsub_rn(__ldg(mesh + L + r), s1[i]), d2 = __fsub_rn(__ldg(mesh + 2 * L + r), s2[i]);
+            const float dist = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+            U[i] = fminf(U[i], __fadd_rn(__ldg(ssd + (int64_t)r * n + v0 + i), __fmul_rn(coeff, dist)));
+        }
+    }
+    // level 1: which slabs can hold the argmin (S independent loads, no branches)
+    unsigned slab_mask = 0;
+#pragma unroll
+    for (int sl = 0; sl < S; ++sl) {
+        float sm[VEC];
+        if (VEC == 4) {
+            const float4 b4 = ca_ld_stream4(reinterpret_cast<const float4*>(smin + (int64_t)sl * n + v0));
+            sm[0] = b4.x; sm[1 % VEC] = b4.y; sm[2 % VEC] = b4.z; sm[3 % VEC] = b4.w;
+        } else {
+            sm[0] = ca_ld_stream1(smin + (int64_t)sl * n + v0);
+        }
+        const float4 lo = slo[sl], hi = shi[sl];
+        bool need = false;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) need = need || !(__fadd_rn(sm[i], __fmul_rn(coeff, box_dist(lo, hi, s0[i], s1[i], s2[i]))) > U[i]);
+        slab_mask |= need ? (1u << sl) : 0u;
+    }
+    const float* sp = ssd + v0;
+    for (int sl = 0; sl < S; ++sl) {
+        if (!((slab_mask >> sl) & 1u)) continue;
+        // level 2: the blocks of this slab
+        for (int bb = 0; bb < S; bb += 4) {
+            float bmv[4][VEC];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int b = sl * S + ca_min(bb + u, S - 1);
+                if (VEC == 4) {
+                    const float4 b4 = ca_ld_stream4(reinterpret_cast<const float4*>(bmin + (int64_t)b * n + v0));
+                    bmv[u][0] = b4.x; bmv[u][1 % VEC] = b4.y; bmv[u][2 % VEC] = b4.z; bmv[u][3 % VEC] = b4.w;
+                } else {
+                    bmv[u][0] = ca_ld_stream1(bmin + (int64_t)b * n + v0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (bb + u >= S) break;
+                const int b = sl * S + bb + u;
+                const float4 lo = blo[b], hi = bhi[b];
+                bool need = false;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i)
+                    need = need || !(__fadd_rn(bmv[u][i], __fmul_rn(coeff, box_dist(lo, hi, s0[i], s1[i], s2[i]))) > U[i]);
+                if (!need) continue;
+                float cv[S][VEC];                 // the S rows of the block: independent loads, all in flight together
+#pragma unroll
+                for (int k = 0; k < S; ++k) {
+                    const int l = b * S + k;
+                    if (VEC == 4) {
+                        const float4 c4 = ca_ld_stream4(reinterpret_cast<const float4*>(sp + (int64_t)l * n));
+                        cv[k][0] = c4.x; cv[k][1 % VEC] = c4.y; cv[k][2 % VEC] = c4.z; cv[k][3 % VEC] = c4.w;
+                    } else {
+                        cv[k][0] = ca_ld_stream1(sp + (int64_t)l * n);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < S; ++k) {
+                    const int l = b * S + k;
+                    const float* c = cv[k];
+                    const float m0 = __ldg(mesh + l), m1 = __ldg(mesh + L + l), m2 = __ldg(mesh + 2 * L + l);
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        const float d0 = __fsub_rn(m0, s0[i]), d1 = __fsub_rn(m1, s1[i]), d2 = __fsub_rn(m2, s2[i]);
+                        const float dist = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+                        const float cost = __fadd_rn(c[i], __fmul_rn(coeff, dist));
+                        if (cost < best[i]) { best[i] = cost; bl[i] = l; }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) keys[v0 + i] = pack_key(best[i], bl[i]);
+}
+
 static inline unsigned small_grid(int64_t n) {
     int64_t b = ca_divup(n, 256);
     if (b > 148 * 16) b = 148 * 16;
@@ -146,17 +386,74 @@ int ca_launch_keys_to_i64(const unsigned long long* keys, int64_t n, int64_t* ou
     return CA_OK;
 }
 
+static int g_cc_prune = -1;   // CA_CC_PRUNE=0 disables the exact pruning (A/B timing of the plain streaming passes)
+static bool cc_prune_enabled() {
+    if (g_cc_prune < 0) { const char* e = getenv("CA_CC_PRUNE"); g_cc_prune = (e && atoi(e) == 0) ? 0 : 1; }
+    return g_cc_prune == 1;
+}
+
+// bmin (S*S,n) followed by smin (S,n) in one buffer, and, when keys != nullptr, the plain argmin as keys
+int ca_launch_blockmin_argmin(const float* ssd, int64_t n, int S, float* bmin, unsigned long long* keys, cudaStream_t st) {
+    float* smin = bmin + (int64_t)S * S * n;
+    const int vec = (n % 4 == 0 && ((((uintptr_t)ssd) | ((uintptr_t)bmin)) & 15) == 0) ? 4 : 1;
+    const unsigned gx = (unsigned)ca_divup(ca_divup(n, vec), 256);
+    if (keys && cudaMemsetAsync(keys, 0xff, (size_t)n * 8, st) != cudaSuccess) {
+        ca_set_error("blockmin_argmin: memset failed");
+        return CA_ERR_LAUNCH;
+    }
+    const dim3 grid(gx, (unsigned)S), block(256);
+    if (vec == 4) { auto k = k_blockmin_argmin<4>; CA_LAUNCH(k, grid, block, 0, st, ssd, n, S, bmin, smin, keys); }
+    else { auto k = k_blockmin_argmin<1>; CA_LAUNCH(k, grid, block, 0, st, ssd, n, S, bmin, smin, keys); }
+    CA_CHECK_LAUNCH("blockmin_argmin");
+    return CA_OK;
+}
+
+// boxes of the mesh for the pruned passes: 2*S*S + 2*S float4 placed after bmin/smin in the same buffer
+static float4* cc_boxes_of(float* bmin, int64_t n, int S) {
+    return (float4*)(((uintptr_t)(bmin + (int64_t)(S * S + S) * n) + 255) & ~(uintptr_t)255);
+}
+static size_t cc_bmin_bytes(int64_t n, int S) { return ((size_t)S * S + S) * n * 4 + 256 + (size_t)(2 * S * S + 2 * S) * 16; }
+
+int ca_launch_mesh_boxes(const float* mesh, int S, float4* boxes, cudaStream_t st) {
+    CA_LAUNCH(k_mesh_boxes, dim3(1), dim3(256), 0, st, mesh, S * S * S, S, boxes);
+    CA_CHECK_LAUNCH("mesh_boxes");
+    return CA_OK;
+}
+
+// one pruned pass; keys holds the previous selection on entry and the new one on exit (each thread reads its own
+// entries before it writes them)
+int ca_launch_cost_argmin_pruned(const float* ssd, const float* bmin, int64_t n, int S, const float* mesh, const float4* boxes,
+                                 const float* soft, float coeff, int row_len, unsigned long long* keys, cudaStream_t st) {
+    if (row_len <= 0 || row_len % 32 != 0 || (n / row_len) % 4 != 0 || n % row_len != 0) row_len = 0;   // 4x32 warp tiles need whole tiles
+    const int L = S * S * S, B = S * S;
+    const float* smin = bmin + (int64_t)B * n;
+    const int vec = (n % 4 == 0 && ((((uintptr_t)ssd) | ((uintptr_t)bmin)) & 15) == 0) ? 4 : 1;
+    const unsigned gx = (unsigned)ca_divup(ca_divup(n, vec), 128);
+    const size_t smem = ((size_t)2 * B + 2 * S) * sizeof(float4);
+#define CA_PRUNED(SS)                                                                                                                   \
+    case SS:                                                                                                                            \
+        if (vec == 4) { auto k = k_cost_argmin_pruned<4, SS>; CA_LAUNCH(k, dim3(gx), dim3(128), smem, st, ssd, bmin, smin, n, L, mesh, boxes, soft, coeff, row_len, keys, keys); } \
+        else { auto k = k_cost_argmin_pruned<1, SS>; CA_LAUNCH(k, dim3(gx), dim3(128), smem, st, ssd, bmin, smin, n, L, mesh, boxes, soft, coeff, row_len, keys, keys); }        \
+        break;
+    switch (S) {
+        CA_PRUNED(3) CA_PRUNED(5) CA_PRUNED(7) CA_PRUNED(9) CA_PRUNED(11) CA_PRUNED(13) CA_PRUNED(15) CA_PRUNED(17)
+        default: ca_set_error("cost_argmin_pruned: disp_hw out of range"); return CA_ERR_UNSUPPORTED;
+    }
+#undef CA_PRUNED
+    CA_CHECK_LAUNCH("cost_argmin_pruned");
+    return CA_OK;
+}
+
 extern "C" size_t ca_coupled_convex_workspace_bytes(int h, int w, int d, int disp_hw) {
-    (void)disp_hw;
-    const size_t n = (size_t)h * w * d;
-    return n * 8 + 256;
+    const size_t n = (size_t)h * w * d, S = 2 * (size_t)disp_hw + 1;
+    return n * 8 + 256 + cc_bmin_bytes((int64_t)n, (int)S) + 256;
 }
 
 extern "C" int ca_coupled_convex(const float* ssd, const int64_t* argmin, const float* mesh, int h, int w, int d,
                                  int disp_hw, float* disp_soft, int64_t* sel_out, void* workspace, size_t workspace_bytes,
                                  ca_stream_t stream) {
-    CA_CHECK_ARG(ssd && argmin && mesh && disp_soft && workspace, "coupled_convex: null pointer");
-    CA_CHECK_ARG(h > 0 && w > 0 && d > 0 && disp_hw >= 1, "coupled_convex: bad dims");
+    CA_CHECK_ARG(ssd && mesh && disp_soft && workspace, "coupled_convex: null pointer");
+    CA_CHECK_ARG(h > 0 && w > 0 && d > 0 && disp_hw >= 1 && disp_hw <= 8, "coupled_convex: bad dims");
     if (workspace_bytes < ca_coupled_convex_workspace_bytes(h, w, d, disp_hw)) {
         ca_set_error("coupled_convex: workspace too small");
         return CA_ERR_WORKSPACE;
@@ -166,11 +463,23 @@ extern "C" int ca_coupled_convex(const float* ssd, const int64_t* argmin, const 
     const int S = 2 * disp_hw + 1, L = S * S * S;
     const int64_t n = (int64_t)h * w * d;
     unsigned long long* keys = (unsigned long long*)workspace;
-    CA_LAUNCH(k_i64_to_keys, dim3(small_grid(n)), dim3(256), 0, st, argmin, n, keys);
+    float* bmin = (float*)(((uintptr_t)(keys + n) + 255) & ~(uintptr_t)255);
+    const bool prune = cc_prune_enabled();
+    int rc;
+    // argmin == NULL: the plain argmin of utils.py:87 is taken here, in the same pass that builds the block minima
+    if (argmin) CA_LAUNCH(k_i64_to_keys, dim3(small_grid(n)), dim3(256), 0, st, argmin, n, keys);
+    float4* boxes = cc_boxes_of(bmin, n, S);
+    if (prune) {
+        if ((rc = ca_launch_blockmin_argmin(ssd, n, S, bmin, argmin ? nullptr : keys, st)) != CA_OK) return rc;
+        if ((rc = ca_launch_mesh_boxes(mesh, S, boxes, st)) != CA_OK) return rc;
+    } else if (!argmin) {
+        if ((rc = ca_launch_cost_argmin(ssd, n, L, nullptr, nullptr, 0.f, keys, st)) != CA_OK) return rc;
+    }
     CA_LAUNCH(k_soft_from_keys, dim3(small_grid(n)), dim3(256), 0, st, keys, mesh, h, w, d, L, disp_soft);
     CA_CHECK_LAUNCH("coupled_convex/init");
     for (int j = 0; j < 6; ++j) {
-        int rc = ca_launch_cost_argmin(ssd, n, L, mesh, disp_soft, coeffs[j], keys, st);
+        if (prune) rc = ca_launch_cost_argmin_pruned(ssd, bmin, n, S, mesh, boxes, disp_soft, coeffs[j], d, keys, st);
+        else rc = ca_launch_cost_argmin(ssd, n, L, mesh, disp_soft, coeffs[j], keys, st);
         if (rc != CA_OK) return rc;
         if (sel_out) {
             rc = ca_launch_keys_to_i64(keys, n, sel_out + (int64_t)j * n, st);
@@ -209,21 +518,47 @@ __global__ void __launch_bounds__(256) k_soft_from_label_window(const int64_t* _
     }
 }
 
-extern "C" size_t ca_cc_select_workspace_bytes(int64_t n) { return (size_t)n * 8 + 256; }
+extern "C" size_t ca_cc_select_workspace_bytes(int64_t n) { return (size_t)n * 8 + 256 + (2 * 17 * 17 + 2 * 17) * 16 + 256; }
+
+// block minima (S*S, n) of a slab's cost volume and, when argmin != NULL, its plain argmin (utils.py:87) in the same pass
+extern "C" int ca_cc_blockmin(const float* ssd, int64_t n, int disp_hw, float* bmin, int64_t* argmin, void* workspace,
+                              size_t workspace_bytes, ca_stream_t stream) {
+    CA_CHECK_ARG(ssd && bmin && workspace && n > 0 && disp_hw >= 1 && disp_hw <= 8, "cc_blockmin: bad argument");
+    if (workspace_bytes < ca_cc_select_workspace_bytes(n)) {
+        ca_set_error("cc_blockmin: workspace too small");
+        return CA_ERR_WORKSPACE;
+    }
+    unsigned long long* keys = (unsigned long long*)workspace;
+    int rc = ca_launch_blockmin_argmin(ssd, n, 2 * disp_hw + 1, bmin, argmin ? keys : nullptr, (cudaStream_t)stream);
+    if (rc != CA_OK || !argmin) return rc;
+    return ca_launch_keys_to_i64(keys, n, argmin, (cudaStream_t)stream);
+}
 
 extern "C" int ca_cc_select(const float* ssd, int64_t n, int disp_hw, const float* mesh, const float* soft, float coeff,
-                            int64_t* sel, void* workspace, size_t workspace_bytes, ca_stream_t stream) {
-    CA_CHECK_ARG(ssd && sel && workspace && n > 0 && disp_hw >= 1, "cc_select: bad argument");
+                            const float* bmin, const int64_t* prev, int64_t* sel, void* workspace, size_t workspace_bytes,
+                            ca_stream_t stream) {
+    CA_CHECK_ARG(ssd && sel && workspace && n > 0 && disp_hw >= 1 && disp_hw <= 8, "cc_select: bad argument");
     CA_CHECK_ARG((mesh == nullptr) == (soft == nullptr), "cc_select: mesh and soft go together");
+    CA_CHECK_ARG((bmin == nullptr) == (prev == nullptr) && (!bmin || mesh), "cc_select: bmin, prev (and mesh, soft) go together");
     if (workspace_bytes < ca_cc_select_workspace_bytes(n)) {
         ca_set_error("cc_select: workspace too small");
         return CA_ERR_WORKSPACE;
     }
+    cudaStream_t st = (cudaStream_t)stream;
     const int S = 2 * disp_hw + 1;
     unsigned long long* keys = (unsigned long long*)workspace;
-    int rc = ca_launch_cost_argmin(ssd, n, S * S * S, mesh, soft, coeff, keys, (cudaStream_t)stream);
+    int rc;
+    if (bmin && cc_prune_enabled()) {
+        CA_LAUNCH(k_i64_to_keys, dim3(small_grid(n)), dim3(256), 0, st, prev, n, keys);
+        CA_CHECK_LAUNCH("cc_select/keys");
+        float4* boxes = (float4*)(((uintptr_t)(keys + n) + 255) & ~(uintptr_t)255);
+        if ((rc = ca_launch_mesh_boxes(mesh, S, boxes, st)) != CA_OK) return rc;
+        rc = ca_launch_cost_argmin_pruned(ssd, bmin, n, S, mesh, boxes, soft, coeff, 0, keys, st);
+    } else {
+        rc = ca_launch_cost_argmin(ssd, n, S * S * S, mesh, soft, coeff, keys, st);
+    }
     if (rc != CA_OK) return rc;
-    return ca_launch_keys_to_i64(keys, n, sel, (cudaStream_t)stream);
+    return ca_launch_keys_to_i64(keys, n, sel, st);
 }
 
 extern "C" int ca_cc_smooth(const int64_t* sel_window, const float* mesh, int P, int w, int d, int disp_hw, float* soft,

@@ -44,15 +44,16 @@ def convex_stage(lib: Lib, fix_s, mov_s, shape, prm: Params, ssd_buf=None):
     L = (2 * prm.disp_hw + 1) ** 3
     if ssd_buf is None or ssd_buf.shape != (L, h, w, d):
         ssd_buf = torch.empty((L, h, w, d), dtype=torch.float32, device=dev)
-    ssd, am = lib.correlate(fix_s, mov_s, prm.disp_hw, out=ssd_buf)
+    # the argmin of utils.py:87 is taken inside coupled_convex, in the pass that builds its block minima
+    ssd, _ = lib.correlate(fix_s, mov_s, prm.disp_hw, want_argmin=False, out=ssd_buf)
     _mark("correlate")
-    soft = lib.coupled_convex(ssd, am, mesh, prm.disp_hw)
+    soft = lib.coupled_convex(ssd, None, mesh, prm.disp_hw)
     _mark("coupled_convex")
     if not prm.ic:
         return soft
-    ssd, am = lib.correlate(mov_s, fix_s, prm.disp_hw, out=ssd_buf)
+    ssd, _ = lib.correlate(mov_s, fix_s, prm.disp_hw, want_argmin=False, out=ssd_buf)
     _mark("correlate")
-    soft_ = lib.coupled_convex(ssd, am, mesh, prm.disp_hw)
+    soft_ = lib.coupled_convex(ssd, None, mesh, prm.disp_hw)
     _mark("coupled_convex")
     return ic_and_upsample(lib, soft, soft_, shape, prm)
 

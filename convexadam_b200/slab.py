@@ -89,10 +89,11 @@ class _Comm:
         return torch.cat([p.narrow(dim, 0, e - b) for p, (b, e) in zip(parts, ranges)], dim).contiguous()
 
 
-def coupled_convex_slab(lib: Lib, comm: _Comm, ssd, argmin, mesh, disp_hw):
-    """coupled_convex (utils.py:93-109) on this rank's slab: ssd (L,hs,w,d), argmin (hs,w,d) -> disp_soft (3,hs,w,d)."""
+def coupled_convex_slab(lib: Lib, comm: _Comm, ssd, mesh, disp_hw):
+    """argmin (utils.py:87) + coupled_convex (utils.py:93-109) on this rank's slab: ssd (L,hs,w,d) -> disp_soft
+    (3,hs,w,d).  One full pass builds the block minima and the argmin; the six regularised passes are pruned."""
     _, hs, w, d = ssd.shape
-    sel = argmin
+    bmin, sel = lib.cc_blockmin(ssd, disp_hw)
     outside = torch.full((1, w, d), -1, dtype=torch.int64, device=ssd.device)
     soft = None
     for j in range(len(CC_COEFFS) + 1):
@@ -101,7 +102,7 @@ def coupled_convex_slab(lib: Lib, comm: _Comm, ssd, argmin, mesh, disp_hw):
         soft = lib.cc_smooth(window, mesh, disp_hw)                                   # utils.py:96 / :107
         if j == len(CC_COEFFS):
             break
-        sel = lib.cc_select(ssd, disp_hw, mesh, soft, CC_COEFFS[j])                   # utils.py:104-105
+        sel = lib.cc_select(ssd, disp_hw, mesh, soft, CC_COEFFS[j], bmin=bmin, prev=sel)   # utils.py:104-105
     return soft
 
 
@@ -160,8 +161,8 @@ def register_features_slab(lib: Lib, comm: _Comm, fix_s, mov_s, fix_a, mov_a, sh
     ssd = torch.empty((L, x1 - x0, w, d), dtype=torch.float32, device=fix_s.device)      # reused for the backward direction
 
     def one_direction(f, m):
-        _, am = lib.correlate_slab(f, m, prm.disp_hw, x0, x1, out=ssd)
-        return comm.gather_planes(coupled_convex_slab(lib, comm, ssd, am, mesh, prm.disp_hw), ranges)
+        lib.correlate_slab(f, m, prm.disp_hw, x0, x1, want_argmin=False, out=ssd)
+        return comm.gather_planes(coupled_convex_slab(lib, comm, ssd, mesh, prm.disp_hw), ranges)
 
     soft = one_direction(fix_s, mov_s)
     if prm.ic:

@@ -94,22 +94,32 @@ CA_API int ca_correlate_slab(const float* fix, const float* mov, int C, int h, i
                       ca_stream_t stream);
 
 /* ---- coupled_convex (utils.py:93-109) -----------------------------------------------------------------------
- * ssd (L,h,w,d); argmin (h,w,d) int64; mesh (3,L) f32 = disp_mesh_t of MIND.py:127 (pass the values torch's
- * affine_grid produces -- they are not integral).  disp_soft: (3,h,w,d) f32 out, coarse-voxel units.
- * sel_out: optional (6,h,w,d) int64, the argmin of each of the six passes (for parity tests). */
+ * ssd (L,h,w,d); argmin (h,w,d) int64, or NULL: the plain argmin of utils.py:87 is then taken here (saves one pass
+ * over the volume when ca_correlate was called with argmin == NULL); mesh (3,L) f32 = disp_mesh_t of MIND.py:127
+ * (pass the values torch's affine_grid produces -- they are not integral).  disp_soft: (3,h,w,d) f32 out,
+ * coarse-voxel units.  sel_out: optional (6,h,w,d) int64, the argmin of each of the six passes (for parity tests).
+ * One streaming pass builds per-voxel minima over blocks of 2*disp_hw+1 consecutive labels; the six passes then read
+ * those (1/(2*disp_hw+1) of the volume) plus only the blocks whose lower bound does not exceed the cost of the
+ * previous selection -- an exact pruning, the selections are bit-identical to the full passes (coupled.cu). */
 CA_API size_t ca_coupled_convex_workspace_bytes(int h, int w, int d, int disp_hw);
 CA_API int ca_coupled_convex(const float* ssd, const int64_t* argmin, const float* mesh, int h, int w, int d, int disp_hw,
                       float* disp_soft, int64_t* sel_out, void* workspace, size_t workspace_bytes,
                       ca_stream_t stream);
 
 /* coupled_convex in pieces (the loop of utils.py:98-107 run by the host, for H slabs with a halo exchange in between):
+ * ca_cc_blockmin: bmin (S*S + S, n): per-voxel minima over the S*S blocks of S consecutive labels, followed by the minima
+ *               over the S slabs of S blocks; and (argmin != NULL) the plain argmin of utils.py:87 in the same pass.
  * ca_cc_select: sel(x) = argmin_l ( ssd_l(x) + coeff * || mesh_l - soft(x) ||^2 ) over n voxels (utils.py:104-105);
  *               mesh == soft == NULL gives the plain argmin of utils.py:87.  ssd (L,n), soft (3,n), sel (n) int64.
+ *               bmin + prev (the previous selection) enable the exact pruning; both NULL = full pass.
  * ca_cc_smooth: soft = box3(mesh[:, sel]) (utils.py:96,107) for the planes [1, P-1) of a (P,w,d) window of labels whose
  *               first/last plane come from the neighbouring slab; a negative label = outside the volume. soft (3,P-2,w,d). */
 CA_API size_t ca_cc_select_workspace_bytes(int64_t n);
+CA_API int ca_cc_blockmin(const float* ssd, int64_t n, int disp_hw, float* bmin, int64_t* argmin, void* workspace,
+                   size_t workspace_bytes, ca_stream_t stream);
 CA_API int ca_cc_select(const float* ssd, int64_t n, int disp_hw, const float* mesh, const float* soft, float coeff,
-                 int64_t* sel, void* workspace, size_t workspace_bytes, ca_stream_t stream);
+                 const float* bmin, const int64_t* prev, int64_t* sel, void* workspace, size_t workspace_bytes,
+                 ca_stream_t stream);
 CA_API int ca_cc_smooth(const int64_t* sel_window, const float* mesh, int P, int w, int d, int disp_hw, float* soft,
                  ca_stream_t stream);
 

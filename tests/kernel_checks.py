@@ -116,6 +116,14 @@ def check_cc_pieces(lib, device, C=6, h=7, w=5, d=8, hw=2, cut=3):
     slabs = [(0, cut), (cut, h)]
     ssds = [ssd[:, a:b].contiguous() for a, b in slabs]
     sels = [am[a:b].contiguous() for a, b in slabs]
+    bmins = []
+    for i in range(2):
+        bm, a2 = lib.cc_blockmin(ssds[i], hw)
+        assert (N(a2) == N(sels[i])).all(), "cc_blockmin argmin"
+        S = 2 * hw + 1
+        assert_bits_equal(N(bm[:S * S]), N(ssds[i]).reshape(S * S, S, *ssds[i].shape[1:]).min(1), "cc_blockmin block minima")
+        assert_bits_equal(N(bm[S * S:]), N(ssds[i]).reshape(S, S * S, *ssds[i].shape[1:]).min(1), "cc_blockmin slab minima")
+        bmins.append(bm)
     pad = torch.full((1, w, d), -1, dtype=torch.int64, device=device)
     softs = None
     for j in range(7):
@@ -124,9 +132,14 @@ def check_cc_pieces(lib, device, C=6, h=7, w=5, d=8, hw=2, cut=3):
         if j == 6:
             break
         coeff = (0.003, 0.01, 0.03, 0.1, 0.3, 1.0)[j]
-        sels = [lib.cc_select(ssds[i], hw, mesh, softs[i], coeff) for i in range(2)]
+        if j % 2 == 0:     # alternate the pruned and the full pass: both must give the reference's selection
+            sels = [lib.cc_select(ssds[i], hw, mesh, softs[i], coeff, bmin=bmins[i], prev=sels[i]) for i in range(2)]
+        else:
+            sels = [lib.cc_select(ssds[i], hw, mesh, softs[i], coeff) for i in range(2)]
     got = torch.cat(softs, 1)
     assert_bits_equal(N(got), N(want), "coupled_convex in slabs")
+    want2, sel2 = lib.coupled_convex(ssd, None, mesh, hw, want_sel=True)       # argmin taken inside
+    assert_bits_equal(N(want2), N(want), "coupled_convex with internal argmin")
     assert (N(lib.cc_select(ssd, hw)) == N(am)).all(), "cc_select without regulariser == argmin"
 
 
