@@ -38,6 +38,9 @@ _SIGS = {
                                 _i, _vp]),
     "ca_coupled_convex_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "ca_coupled_convex": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "ca_correlate_fast": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "ca_coupled_convex_certified_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "ca_coupled_convex_certified": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ca_inverse_consistency_workspace_bytes": (_sz, [_i, _i, _i]),
     "ca_inverse_consistency": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ca_field_affine": (_i, [_vp, _vp, _i64, _i, C.POINTER(_f), C.POINTER(_f), _f, _vp]),
@@ -168,7 +171,8 @@ class Lib:
                                            self._p(out), self._stream(labels)))
         return out
 
-    def correlate(self, fix, mov, disp_hw, want_argmin=True, workspace_bytes=None, out=None):
+    def correlate(self, fix, mov, disp_hw, want_argmin=True, workspace_bytes=None, out=None, fast=False):
+        """fast=True: the approximate volume of ca_correlate_fast (no argmin; feed it to coupled_convex_certified)."""
         fix = self._t(fix)
         mov = self._t(mov)
         if fix.shape != mov.shape or fix.dim() != 4:
@@ -176,9 +180,13 @@ class Lib:
         Cn, h, w, d = fix.shape
         L = (2 * disp_hw + 1) ** 3
         ssd = out if out is not None else torch.empty((L, h, w, d), dtype=torch.float32, device=fix.device)
-        am = torch.empty((h, w, d), dtype=torch.int64, device=fix.device) if want_argmin else None
+        am = torch.empty((h, w, d), dtype=torch.int64, device=fix.device) if (want_argmin and not fast) else None
         nb = workspace_bytes or self.dll.ca_correlate_workspace_bytes(Cn, h, w, d, disp_hw)
         ws = self._ws(nb, fix)
+        if fast:
+            self._chk(self.dll.ca_correlate_fast(self._p(fix), self._p(mov), Cn, h, w, d, disp_hw, self._p(ssd), self._p(ws), nb,
+                                                self._stream(fix)))
+            return ssd, None
         self._chk(self.dll.ca_correlate(self._p(fix), self._p(mov), Cn, h, w, d, disp_hw, self._p(ssd), self._p(am),
                                        self._p(ws), nb, self._stream(fix)))
         return ssd, am
@@ -251,6 +259,31 @@ class Lib:
         self._chk(self.dll.ca_coupled_convex(self._p(ssd), self._p(argmin), self._p(mesh), h, w, d, disp_hw, self._p(soft),
                                             self._p(sel), self._p(ws), nb, self._stream(ssd)))
         return (soft, sel) if want_sel else soft
+
+    def coupled_convex_certified(self, ssd, fix, mov, mesh, disp_hw, want_sel=False, want_flagged=False):
+        """coupled_convex (argmin included) on the approximate volume of correlate(fast=True); selections proven equal
+        to the exact path's.  Returns soft[, sel (7,h,w,d): argmin + six passes][, flagged (7,) int32 counts]."""
+        ssd = self._t(ssd)
+        fix = self._t(fix)
+        mov = self._t(mov)
+        mesh = self._t(mesh.reshape(3, -1))
+        L, h, w, d = ssd.shape
+        if L != (2 * disp_hw + 1) ** 3 or mesh.shape[1] != L or tuple(fix.shape[1:]) != (h, w, d) or fix.shape != mov.shape:
+            raise ValueError("coupled_convex_certified: shape mismatch")
+        soft = torch.empty((3, h, w, d), dtype=torch.float32, device=ssd.device)
+        sel = torch.empty((7, h, w, d), dtype=torch.int64, device=ssd.device) if want_sel else None
+        flg = torch.zeros((8,), dtype=torch.int32, device=ssd.device) if want_flagged else None
+        nb = self.dll.ca_coupled_convex_certified_workspace_bytes(h, w, d, disp_hw)
+        ws = self._ws(nb, ssd)
+        self._chk(self.dll.ca_coupled_convex_certified(self._p(ssd), self._p(fix), self._p(mov), fix.shape[0], self._p(mesh), h, w, d,
+                                                      disp_hw, self._p(soft), self._p(sel), self._p(flg), self._p(ws), nb,
+                                                      self._stream(ssd)))
+        out = (soft,)
+        if want_sel:
+            out += (sel,)
+        if want_flagged:
+            out += (flg[:7],)
+        return out if len(out) > 1 else soft
 
     def inverse_consistency(self, f1, f2, iters):
         f1 = self._t(f1)

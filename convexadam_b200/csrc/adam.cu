@@ -2,7 +2,7 @@
 //
 // Replaces the autograd loop of the reference (src/convexAdam/convex_adam_MIND.py:147-181, nnUNet.py:95-133):
 // ~70 torch launches + a backward graph per iteration there; here, per iteration,
-//     u   = B^3 p                      three exact box3 passes (F.avg_pool3d(3,1,1), MIND.py:166)
+//     u   = B^3 p                      three box3 passes (F.avg_pool3d(3,1,1), MIND.py:166) fused into two separable kernels
 //     g_u = dL/du                      ONE kernel: trilinear sample of the moving features at x + u*size/(size-1),
 //                                      SSD residual, analytic d/d(position), diffusion regulariser (MIND.py:167-177)
 //     g_p = B^3 g_u                    box3 is symmetric (zero padding, /27 everywhere) so backward == forward
@@ -170,126 +170,130 @@ __global__ void __launch_bounds__(256) k_adam_update(float* __restrict__ p, floa
     }
 }
 
-// ---- one B pass (F.avg_pool3d(x, 3, stride=1, padding=1), MIND.py:166) as a march along H ---------------------------
-// in/out: (3, h, w, d) with d % 4 == 0.  A thread owns two rows x four voxels and a segment of Lx planes; it reads the
-// planes xs-1 .. xe once each (planes/rows outside the volume are an all-zero row) and keeps three running sums, see
-// box_march.cuh.  No shared memory, no block synchronisation.  UPDATE: the finished value is dL/dp, and instead of
-// being stored it drives the Adam step of (p, m, v) in place -- the last pass of B^3 g_u and the update in one kernel.
-struct FieldBoxArgs {
+// ---- B^3 = three F.avg_pool3d(x, 3, stride=1, padding=1) passes (MIND.py:166), fused ---------------------------------
+// box3 with zero padding is separable per axis, and so is the truncation of each intermediate to the volume, hence
+//     B^3 = T_H T_W T_D,   T = (1-D box3 with zero padding)^3 along one axis, / 27.
+// Two kernels instead of three full 27-tap passes: k_box3_h applies T_H (a thread owns a column segment and slides
+// three cascaded 3-tap sums along it in registers), k_box3_p applies T_W T_D to one plane held in shared memory and,
+// in UPDATE mode, feeds the finished value dL/dp straight into the Adam step of (p, m, v).
+// The additions are associated differently from torch's ordered 27-tap sums: u agrees with the reference's to a few
+// ulp (tests: 2e-6 relative), which the stage's own tolerance (Adam amplifies 1-ulp feature noise) absorbs.
+struct Box3Args {
     const float* in;
     float* out;
-    const float* zero_row;
-    int h, w, d, nq, Lx, rpb;     // rpb = row pairs per block
+    int h, w, d, nq;
+    int Ty, ntiles, Ly;           // k_box3_p: output rows per CTA, row tiles per plane, rows per thread
     float *p, *m, *v;
     AdamScalars s;
 };
 
-// per-thread state of the march: cp[j] = the thread's row j of the CURRENT plane (rows that do not exist point at the
-// all-zero row and have stride 0), eoff = element offset of the thread's first output row in plane X-1
-struct FieldBoxThread {
-    const float* cp[4];
-    int64_t stride[4];
-    int64_t eoff, plane;
-    BoxLane bl;
-    bool ook[2];
-};
+static __device__ __forceinline__ float4 f4add3(const float4& a, const float4& b, const float4& c) {
+    return make_float4((a.x + b.x) + c.x, (a.y + b.y) + c.y, (a.z + b.z) + c.z, (a.w + b.w) + c.w);
+}
+static __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
-template <int R, bool UPDATE>
-static __device__ __forceinline__ void field_box_step(int X, int xs, int xe, const FieldBoxArgs& a, FieldBoxThread& t,
-                                                      float (&acc)[3][2][4], float4 (&cur)[4]) {
-    constexpr int Cs = (R + 1) % 3;
-    if (X > xe) return;
-    // next plane first: its latency hides behind this plane's additions (planes outside the volume are zero)
-    float4 nxt[4];
-    if (X + 1 < a.h && X + 1 <= xe) {
+// T_H: grid = (ceil(w*nq / 128), H segments, 3 channels); a thread owns (row y, quad q) and the planes [xs, xe)
+template <int LX>
+__global__ void __launch_bounds__(128) k_box3_h(Box3Args a) {
+    const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (t >= a.w * a.nq) return;
+    const int xs = (int)blockIdx.y * LX, xe = ca_min(a.h, xs + LX);
+    const int64_t plane = (int64_t)a.w * a.d;
+    const float* ip = a.in + (int64_t)blockIdx.z * a.h * plane + (int64_t)t * 4;
+    float* op = a.out + (int64_t)blockIdx.z * a.h * plane + (int64_t)t * 4;
+    float4 v[LX + 6];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) nxt[j] = __ldg(reinterpret_cast<const float4*>(t.cp[j] + t.stride[j]));
-    } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) nxt[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < LX + 6; ++i) {           // all loads of the segment go out together
+        const int X = xs - 3 + i;
+        v[i] = (X >= 0 && X < a.h && X < xe + 3) ? __ldg(reinterpret_cast<const float4*>(ip + (int64_t)X * plane)) : f4zero();
     }
-    if (X >= 0 && X < a.h) {
-        float hl[4], hr[4];
+    float4 i2 = f4zero(), i1 = f4zero(), a2 = f4zero(), a1 = f4zero(), b2 = f4zero(), b1 = f4zero();
+    const float c27 = 1.0f / 27.0f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) box_halo(cur[j], t.cp[j], t.bl, hl[j], hr[j]);
-        box_add_plane<R>(acc, cur, hl, hr);
-    } else {
-#pragma unroll
-        for (int o = 0; o < 2; ++o)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc[R][o][k] = 0.f;      // a zero plane: the fresh sum starts at 0, the others keep their value
-    }
-    if (X - 1 >= xs) {
-#pragma unroll
-        for (int o = 0; o < 2; ++o) {
-            if (!t.ook[o]) continue;
-            const int64_t off = t.eoff + (int64_t)o * a.d;
-            float4 r;
-            r.x = ca_div27(acc[Cs][o][0]); r.y = ca_div27(acc[Cs][o][1]); r.z = ca_div27(acc[Cs][o][2]); r.w = ca_div27(acc[Cs][o][3]);
-            if (UPDATE) {
-                float4 pp = *reinterpret_cast<const float4*>(a.p + off), mm = *reinterpret_cast<const float4*>(a.m + off),
-                       vv = *reinterpret_cast<const float4*>(a.v + off);
-                adam_update1(pp.x, mm.x, vv.x, r.x, a.s); adam_update1(pp.y, mm.y, vv.y, r.y, a.s);
-                adam_update1(pp.z, mm.z, vv.z, r.z, a.s); adam_update1(pp.w, mm.w, vv.w, r.w, a.s);
-                *reinterpret_cast<float4*>(a.p + off) = pp;
-                *reinterpret_cast<float4*>(a.m + off) = mm;
-                *reinterpret_cast<float4*>(a.v + off) = vv;
-                if (a.out) *reinterpret_cast<float4*>(a.out + off) = r;
-            } else {
-                *reinterpret_cast<float4*>(a.out + off) = r;
-            }
-        }
-    }
-    t.eoff += t.plane;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        t.cp[j] += t.stride[j];
-        cur[j] = nxt[j];
+    for (int i = 0; i < LX + 6; ++i) {
+        const int X = xs - 3 + i;                // plane X arrives: a[X-1], b[X-2], c[X-3] complete
+        float4 an = f4add3(i2, i1, v[i]);
+        if (X - 1 < 0 || X - 1 >= a.h) an = f4zero();
+        float4 bn = f4add3(a2, a1, an);
+        if (X - 2 < 0 || X - 2 >= a.h) bn = f4zero();
+        const float4 cn = f4add3(b2, b1, bn);
+        if (X - 3 >= xs && X - 3 < xe)
+            *reinterpret_cast<float4*>(op + (int64_t)(X - 3) * plane) = make_float4(cn.x * c27, cn.y * c27, cn.z * c27, cn.w * c27);
+        i2 = i1; i1 = v[i]; a2 = a1; a1 = an; b2 = b1; b1 = bn;
     }
 }
 
-// grid = (row-pair blocks, H segments, 3 channels); block = nq * rpb threads rounded up to whole warps, z-fastest
+// T_W T_D on one plane: grid = (row tiles, h, 3 channels).  Shared memory: two buffers of (Ty + 6) rows x d floats.
 template <bool UPDATE>
-__global__ void __launch_bounds__(256, 1) k_field_box(FieldBoxArgs a) {
-    const int tid = (int)threadIdx.x;
-    const int q = tid % a.nq, rpl = tid / a.nq;
-    const int lane = tid & 31;
-    const int rp = (int)blockIdx.x * a.rpb + rpl;
-    const int y0 = 2 * rp;
-    const bool active = rpl < a.rpb && y0 < a.w;
-    const int xs = (int)blockIdx.y * a.Lx, xe = ca_min(a.h, xs + a.Lx);
-    FieldBoxThread t;
-    t.plane = (int64_t)a.w * a.d;
-    const int64_t chan = (int64_t)blockIdx.z * a.h * t.plane;
-    t.bl.first = q == 0;
-    t.bl.last = q == a.nq - 1;
-    t.bl.fb_l = !t.bl.first && lane == 0;
-    t.bl.fb_r = !t.bl.last && lane == 31;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int y = y0 - 1 + j;
-        const bool ok = active && y >= 0 && y < a.w;
-        t.stride[j] = ok ? t.plane : 0;
-        t.cp[j] = ok ? a.in + chan + (int64_t)(xs - 1) * t.plane + (int64_t)y * a.d + 4 * q : a.zero_row + 4;
+__global__ void __launch_bounds__(256) k_box3_p(Box3Args a) {
+    CA_DYN_SMEM(float, sm);
+    const int tid = (int)threadIdx.x, nthr = (int)blockDim.x;
+    const int ty0 = (int)blockIdx.x * a.Ty;
+    const int nrows = ca_min(a.Ty, a.w - ty0) + 6;              // rows ty0-3 .. ty0+Ty+2 of the plane
+    const int nq = a.nq, d = a.d;
+    float* A = sm;
+    float* B = sm + (size_t)(a.Ty + 6) * d;
+    const int64_t plane_off = ((int64_t)blockIdx.z * a.h + blockIdx.y) * a.w * d;
+    for (int i = tid; i < nrows * nq; i += nthr) {
+        const int r = i / nq, q = i - r * nq, y = ty0 - 3 + r;
+        *reinterpret_cast<float4*>(A + r * d + 4 * q) =
+            (y >= 0 && y < a.w) ? __ldg(reinterpret_cast<const float4*>(a.in + plane_off + (int64_t)y * d + 4 * q)) : f4zero();
     }
-    t.eoff = chan + (int64_t)(xs - 2) * t.plane + (int64_t)y0 * a.d + 4 * q;     // plane X-1 at the first step X = xs-1
-    t.ook[0] = active;
-    t.ook[1] = active && y0 + 1 < a.w;
-    float acc[3][2][4];
+    __syncthreads();
+    // T_D: the quad with its neighbours; positions z0-4 .. z0+7 -> r[0..11]
+    for (int i = tid; i < nrows * nq; i += nthr) {
+        const int rr = i / nq, q = i - rr * nq;
+        const float* row = A + rr * d;
+        const float4 lo = q > 0 ? *reinterpret_cast<const float4*>(row + 4 * q - 4) : f4zero();
+        const float4 mi = *reinterpret_cast<const float4*>(row + 4 * q);
+        const float4 hi = q < nq - 1 ? *reinterpret_cast<const float4*>(row + 4 * q + 4) : f4zero();
+        const float r[12] = {lo.x, lo.y, lo.z, lo.w, mi.x, mi.y, mi.z, mi.w, hi.x, hi.y, hi.z, hi.w};
+        float s1[12], s2[12];
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+        for (int j = 2; j <= 9; ++j) s1[j] = (r[j - 1] + r[j]) + r[j + 1];
+        if (q == 0) s1[2] = s1[3] = 0.f;                        // positions -2, -1 lie outside the volume
+        if (q == nq - 1) s1[8] = s1[9] = 0.f;                   // positions d, d+1
 #pragma unroll
-        for (int o = 0; o < 2; ++o)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc[i][o][k] = 0.f;
-    float4 cur[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        cur[j] = xs >= 1 ? __ldg(reinterpret_cast<const float4*>(t.cp[j])) : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int X = xs - 1; X <= xe; X += 3) {
-        field_box_step<0, UPDATE>(X, xs, xe, a, t, acc, cur);
-        field_box_step<1, UPDATE>(X + 1, xs, xe, a, t, acc, cur);
-        field_box_step<2, UPDATE>(X + 2, xs, xe, a, t, acc, cur);
+        for (int j = 3; j <= 8; ++j) s2[j] = (s1[j - 1] + s1[j]) + s1[j + 1];
+        if (q == 0) s2[3] = 0.f;
+        if (q == nq - 1) s2[8] = 0.f;
+        float4 o;
+        o.x = (s2[3] + s2[4]) + s2[5]; o.y = (s2[4] + s2[5]) + s2[6]; o.z = (s2[5] + s2[6]) + s2[7]; o.w = (s2[6] + s2[7]) + s2[8];
+        *reinterpret_cast<float4*>(B + rr * d + 4 * q) = o;
+    }
+    __syncthreads();
+    // T_W: a thread owns quad q and the output rows [y0, y0+Ly) of the tile and slides along W
+    const float c729 = 1.0f / 729.0f;
+    const int nchunks = (a.Ty + a.Ly - 1) / a.Ly;
+    for (int i = tid; i < nchunks * nq; i += nthr) {
+        const int ch = i / nq, q = i - ch * nq;
+        const int y0 = ty0 + ch * a.Ly, y1 = ca_min(ca_min(y0 + a.Ly, ty0 + a.Ty), a.w);
+        float4 i2 = f4zero(), i1 = f4zero(), a2 = f4zero(), a1 = f4zero(), b2 = f4zero(), b1 = f4zero();
+        for (int Y = y0 - 3; Y < y1 + 3; ++Y) {                 // row Y arrives: a[Y-1], b[Y-2], c[Y-3] complete
+            const float4 vin = (Y >= 0 && Y < a.w) ? *reinterpret_cast<const float4*>(B + (Y - ty0 + 3) * d + 4 * q) : f4zero();
+            float4 an = f4add3(i2, i1, vin);
+            if (Y - 1 < 0 || Y - 1 >= a.w) an = f4zero();
+            float4 bn = f4add3(a2, a1, an);
+            if (Y - 2 < 0 || Y - 2 >= a.w) bn = f4zero();
+            const float4 cn = f4add3(b2, b1, bn);
+            if (Y - 3 >= y0) {
+                const int64_t off = plane_off + (int64_t)(Y - 3) * d + 4 * q;
+                float4 r = make_float4(cn.x * c729, cn.y * c729, cn.z * c729, cn.w * c729);
+                if (UPDATE) {
+                    float4 pp = *reinterpret_cast<const float4*>(a.p + off), mm = *reinterpret_cast<const float4*>(a.m + off),
+                           vv = *reinterpret_cast<const float4*>(a.v + off);
+                    adam_update1(pp.x, mm.x, vv.x, r.x, a.s); adam_update1(pp.y, mm.y, vv.y, r.y, a.s);
+                    adam_update1(pp.z, mm.z, vv.z, r.z, a.s); adam_update1(pp.w, mm.w, vv.w, r.w, a.s);
+                    *reinterpret_cast<float4*>(a.p + off) = pp;
+                    *reinterpret_cast<float4*>(a.m + off) = mm;
+                    *reinterpret_cast<float4*>(a.v + off) = vv;
+                    if (a.out) *reinterpret_cast<float4*>(a.out + off) = r;
+                } else {
+                    *reinterpret_cast<float4*>(a.out + off) = r;
+                }
+            }
+            i2 = i1; i1 = vin; a2 = a1; a1 = an; b2 = b1; b1 = bn;
+        }
     }
 }
 
@@ -299,29 +303,49 @@ static inline unsigned adam_grid(int64_t n, int block) {
     return (unsigned)(b < 1 ? 1 : b);
 }
 
-static int g_field_lx = 0;   // tuning knob (CA_FIELD_LX env, read once): planes per H segment of k_field_box
+#define CA_BOX3_LX 16
+#define CA_BOX3_SMEM (96 * 1024)
 
-// one B pass on a 3-channel field; with `upd` the result is consumed by the Adam step (and stored only if out != null)
-static int field_box(const float* in, float* out, int ha, int wa, int da, const float* zero_row, const FieldBoxArgs* upd,
-                     cudaStream_t st) {
-    FieldBoxArgs a;
+// rows per CTA of k_box3_p such that both shared-memory buffers fit; 0: the plane rows are too long
+static int box3_rows_per_tile(int wa, int da) {
+    const int maxrows = (int)(CA_BOX3_SMEM / ((size_t)2 * da * 4)) - 6;
+    if (maxrows < 1) return 0;
+    const int nt = (wa + maxrows - 1) / maxrows;
+    return (wa + nt - 1) / nt;
+}
+
+// out = B^3 in on a (3, h, w, d) field, through the scratch field tmp; with `upd` the result drives the Adam step
+// (and is stored only if out != null)
+static int box3_cubed(const float* in, float* tmp, float* out, int ha, int wa, int da, const Box3Args* upd, cudaStream_t st) {
+    Box3Args a;
     if (upd) a = *upd;
-    a.in = in; a.out = out; a.zero_row = zero_row;
     a.h = ha; a.w = wa; a.d = da; a.nq = da / 4;
-    if (g_field_lx == 0) {
-        const char* e = getenv("CA_FIELD_LX");
-        g_field_lx = e ? atoi(e) : 8;
-        if (g_field_lx < 1) g_field_lx = 8;
+    a.in = in; a.out = tmp;
+    {
+        const dim3 grid((unsigned)ca_divup((int64_t)wa * a.nq, 128), (unsigned)ca_divup(ha, CA_BOX3_LX), 3u);
+        auto k = k_box3_h<CA_BOX3_LX>;
+        CA_LAUNCH(k, grid, dim3(128), 0, st, a);
+        CA_CHECK_LAUNCH("box3_h");
     }
-    a.Lx = g_field_lx;
-    a.rpb = a.nq >= 128 ? 1 : 128 / a.nq;
-    const int rps = (wa + 1) / 2;
-    if (a.rpb > rps) a.rpb = rps;
-    const unsigned nthreads = (unsigned)((a.nq * a.rpb + 31) & ~31);
-    const dim3 grid((unsigned)((rps + a.rpb - 1) / a.rpb), (unsigned)((ha + a.Lx - 1) / a.Lx), 3u);
-    if (upd) { auto k = k_field_box<true>; CA_LAUNCH(k, grid, dim3(nthreads), 0, st, a); }
-    else { auto k = k_field_box<false>; CA_LAUNCH(k, grid, dim3(nthreads), 0, st, a); }
-    CA_CHECK_LAUNCH("field_box");
+    a.in = tmp; a.out = out;
+    a.Ty = box3_rows_per_tile(wa, da);
+    a.ntiles = (wa + a.Ty - 1) / a.Ty;
+    const int cols = 256 / a.nq > 0 ? 256 / a.nq : 1;       // row chunks that keep 256 threads busy
+    a.Ly = (a.Ty + cols - 1) / cols;
+    if (a.Ly < 4) a.Ly = ca_min(4, a.Ty);
+    const size_t smem = (size_t)2 * (a.Ty + 6) * da * 4;
+    const dim3 grid((unsigned)a.ntiles, (unsigned)ha, 3u);
+#ifndef CA_EMU
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_box3_p<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CA_BOX3_SMEM + 6 * 4096);
+        cudaFuncSetAttribute(k_box3_p<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CA_BOX3_SMEM + 6 * 4096);
+        attr_done = true;
+    }
+#endif
+    if (upd) { auto k = k_box3_p<true>; CA_LAUNCH(k, grid, dim3(256), smem, st, a); }
+    else { auto k = k_box3_p<false>; CA_LAUNCH(k, grid, dim3(256), smem, st, a); }
+    CA_CHECK_LAUNCH("box3_p");
     return CA_OK;
 }
 
@@ -355,16 +379,11 @@ extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int
     float4* fixcl = (float4*)(((uintptr_t)(gu + 3 * nw) + 255) & ~(uintptr_t)255);
     float4* movcl = fixcl + n * CG;
     float* zero_row = (float*)(((uintptr_t)(movcl + n * CG) + 255) & ~(uintptr_t)255);   // da + 16 zeros for k_field_box
-    // marching box passes need float4 rows; any other shape takes the generic avg_pool3d kernel
-    const bool fast = (da & 3) == 0 && da / 4 <= 256 && (((uintptr_t)p | (uintptr_t)m | (uintptr_t)v | (uintptr_t)u_out | (uintptr_t)g_out) & 15) == 0;
-    if (niter > 0 && fast && cudaMemsetAsync(zero_row, 0, ((size_t)da + 16) * 4, st) != cudaSuccess) {
-        ca_set_error("adam_run: memset failed");
-        return CA_ERR_LAUNCH;
-    }
-    auto box = [&](const float* in, float* out) -> int {
-        if (fast) return field_box(in, out, hl, wa, da, zero_row, nullptr, st);
-        return ca_launch_avgpool3d(in, 3, hl, wa, da, 3, 1, 1, out, st);
-    };
+    // the fused B^3 kernels need float4 rows that fit shared memory; any other shape takes three generic avg_pool3d passes
+    const bool fast = (da & 3) == 0 && box3_rows_per_tile(wa, da) > 0 &&
+                      (((uintptr_t)p | (uintptr_t)m | (uintptr_t)v | (uintptr_t)u_out | (uintptr_t)g_out) & 15) == 0;
+    (void)zero_row;
+    auto box = [&](const float* in, float* out) -> int { return ca_launch_avgpool3d(in, 3, hl, wa, da, 3, 1, 1, out, st); };
     if (niter > 0 && !features_ready) {
         const unsigned gb = adam_grid(n, 256);
         CA_LAUNCH(k_planar_to_cl, dim3(gb), dim3(256), 0, st, fix, C, CG, n, fixcl);
@@ -385,16 +404,22 @@ extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int
     for (int it = 0; it < niter; ++it) {
         const int step = first_step + it;
         int rc;
-        if ((rc = box(p, t0)) != CA_OK) return rc;
-        if ((rc = box(t0, t1)) != CA_OK) return rc;
-        if ((rc = box(t1, u_out)) != CA_OK) return rc;
+        if (fast) {
+            if ((rc = box3_cubed(p, t0, u_out, hl, wa, da, nullptr, st)) != CA_OK) return rc;
+        } else {
+            if ((rc = box(p, t0)) != CA_OK) return rc;
+            if ((rc = box(t0, t1)) != CA_OK) return rc;
+            if ((rc = box(t1, u_out)) != CA_OK) return rc;
+        }
         const int bx = da >= 128 ? 128 : (da >= 64 ? 64 : 32);
         CA_LAUNCH(k_adam_grad, dim3((unsigned)((da + bx - 1) / bx), (unsigned)wa, (unsigned)hl), dim3(bx), 0, st, u_out, fixcl, movcl, CG,
                   g, g0x, g0y, g0z, gu);
         CA_CHECK_LAUNCH("adam_grad");
-        if ((rc = box(gu, t0)) != CA_OK) return rc;
-        if ((rc = box(t0, t1)) != CA_OK) return rc;
-        FieldBoxArgs upd;
+        if (!fast) {
+            if ((rc = box(gu, t0)) != CA_OK) return rc;
+            if ((rc = box(t0, t1)) != CA_OK) return rc;
+        }
+        Box3Args upd;
         const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
         upd.p = p; upd.m = m; upd.v = v;
         upd.s.w_lerp = (float)(1.0 - b1);
@@ -404,8 +429,8 @@ extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int
         upd.s.eps = (float)eps;
         upd.s.neg_step_size = (float)(-(lr / bc1));
         if (fast) {
-            // third pass of B^3 g_u fused with the Adam step; dL/dp is stored only when the caller asks for it
-            if ((rc = field_box(t1, g_out, hl, wa, da, zero_row, &upd, st)) != CA_OK) return rc;
+            // B^3 g_u fused with the Adam step; dL/dp is stored only when the caller asks for it
+            if ((rc = box3_cubed(gu, t0, g_out, hl, wa, da, &upd, st)) != CA_OK) return rc;
         } else {
             float* gp = g_out ? g_out : t0;
             if ((rc = box(t1, gp)) != CA_OK) return rc;

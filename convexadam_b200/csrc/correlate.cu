@@ -76,7 +76,9 @@ static RawLayout make_raw_layout(int nx, int w, int dF) {
 }
 
 // raw[(g*S + kD), x, y, z] = sum_c (f_c(x,y,z) - mpad_c(x+kH, y+kW, z+kD))^2 for the pair (kH,kW) = chunk_start+g
-template <int HW, int MINB>
+// FAST: the channel sum is an FMA chain (14 roundings per value instead of the reference's 36 separate ops); see the
+// "certified" mode below for how its results are used.
+template <int HW, int MINB, bool FAST>
 __global__ void __launch_bounds__(128, MINB) k_raw_ssd(const float* __restrict__ fixp, const float* __restrict__ movp,
                                                        int C, int h, int w, int d, int dF, int dP, int chunk_start,
                                                        int zq, int nzb, RawLayout rl, int r0, float* __restrict__ raw) {
@@ -103,23 +105,30 @@ __global__ void __launch_bounds__(128, MINB) k_raw_ssd(const float* __restrict__
     const float* fp = fixp + ((int64_t)x * w + y) * dF + z0;
     const float* mp = movp + ((int64_t)(x + kH) * wp + (y + kW)) * dP + z0;
     const int64_t fstride = (int64_t)h * w * dF, mstride = (int64_t)hp * wp * dP;
+    // software pipeline: the loads of channel c+1 are in flight while channel c is reduced (the kernel is bound by
+    // the latency of these L2 hits, not by issue slots)
+    float4 f4 = __ldg(reinterpret_cast<const float4*>(fp));
+    float4 m4[NM / 4];
+#pragma unroll
+    for (int j = 0; j < NM / 4; ++j) m4[j] = __ldg(reinterpret_cast<const float4*>(mp) + j);
     for (int c = 0; c < C; ++c) {
-        const float4 f4 = __ldg(reinterpret_cast<const float4*>(fp));
         const float f[4] = {f4.x, f4.y, f4.z, f4.w};
         float m[NM];
 #pragma unroll
-        for (int j = 0; j < NM / 4; ++j) {
-            const float4 m4 = __ldg(reinterpret_cast<const float4*>(mp) + j);
-            m[4 * j + 0] = m4.x; m[4 * j + 1] = m4.y; m[4 * j + 2] = m4.z; m[4 * j + 3] = m4.w;
+        for (int j = 0; j < NM / 4; ++j) { m[4 * j + 0] = m4[j].x; m[4 * j + 1] = m4[j].y; m[4 * j + 2] = m4[j].z; m[4 * j + 3] = m4[j].w; }
+        if (c + 1 < C) {
+            fp += fstride;
+            mp += mstride;
+            f4 = __ldg(reinterpret_cast<const float4*>(fp));
+#pragma unroll
+            for (int j = 0; j < NM / 4; ++j) m4[j] = __ldg(reinterpret_cast<const float4*>(mp) + j);
         }
-        fp += fstride;
-        mp += mstride;
 #pragma unroll
         for (int k = 0; k < S; ++k)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float df = __fsub_rn(f[i], m[i + k]);
-                acc[k][i] = __fadd_rn(acc[k][i], __fmul_rn(df, df));
+                acc[k][i] = FAST ? __fmaf_rn(df, df, acc[k][i]) : __fadd_rn(acc[k][i], __fmul_rn(df, df));
             }
     }
     float* rp = raw + (int64_t)blockIdx.x * S * rl.plane + (int64_t)blockIdx.z * rl.xPitch + (int64_t)(y + 2) * rl.rowPitch + 4 + z0;
@@ -227,9 +236,116 @@ static __device__ __forceinline__ void box12_step(int X, const Box12Args& a, Box
     }
 }
 
+
+// ---- FAST variant of the same march: separable sums ------------------------------------------------------------------
+// box3 o box3 with the truncation of the intermediate to the volume is separable per axis, so each box is a 3-tap sum
+// along D (registers + the shuffled halo), along W (the 4 rows a thread holds) and along H (the in-plane sums of the two
+// previous planes): 8 additions and one multiplication by RN(1/27) per value and box instead of 26 + an exact division.
+// The result differs from the reference's ordered sum by a few ulp (<= 30 roundings against <= 68, see coupled.cu:
+// "certified selection"), which is why this mode never decides an argmin on its own.
+static __device__ __forceinline__ void box_inplane(const float4 (&v)[4], const float (&hl)[4], const float (&hr)[4], float (&out)[2][4]) {
+    float ds[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        ds[j][0] = (hl[j] + v[j].x) + v[j].y;
+        ds[j][1] = (v[j].x + v[j].y) + v[j].z;
+        ds[j][2] = (v[j].y + v[j].z) + v[j].w;
+        ds[j][3] = (v[j].z + v[j].w) + hr[j];
+    }
+#pragma unroll
+    for (int o = 0; o < 2; ++o)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out[o][k] = (ds[o][k] + ds[o + 1][k]) + ds[o + 2][k];
+}
+
+// hs[0] = in-plane sums of the previous plane, hs[1] = of the one before
+template <bool DALIGNED>
+static __device__ __forceinline__ void box12_fast_step(int X, const Box12Args& a, BoxThread& t, float (&h1)[2][2][4],
+                                                       float (&h2)[2][2][4], float4 (&cur)[4]) {
+    const float c27 = 1.0f / 27.0f;
+    const int boff = (X & 1) * t.p1buf;
+    float in[2][4];
+    // ---- first box: raw plane X in, box1 plane X-1 out (shared memory) ----
+    if (X < a.r1) {
+        float hl[4], hr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) box_halo(cur[j], t.rawp[j], t.bl, hl[j], hr[j]);
+        box_inplane(cur, hl, hr, in);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t.rawp[j] += t.xPitch;
+    } else {
+#pragma unroll
+        for (int o = 0; o < 2; ++o)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) in[o][k] = 0.f;
+    }
+    const bool p1ok = X - 1 >= a.b0 && X - 1 < a.b1;
+    if (p1ok) {
+#pragma unroll
+        for (int o = 0; o < 2; ++o)
+            if (t.p1w[o]) {
+                float4 r;
+                r.x = ((h1[1][o][0] + h1[0][o][0]) + in[o][0]) * c27;
+                r.y = ((h1[1][o][1] + h1[0][o][1]) + in[o][1]) * c27;
+                r.z = ((h1[1][o][2] + h1[0][o][2]) + in[o][2]) * c27;
+                r.w = ((h1[1][o][3] + h1[0][o][3]) + in[o][3]) * c27;
+                if (!DALIGNED) { r.y = t.zok[1] ? r.y : 0.f; r.z = t.zok[2] ? r.z : 0.f; r.w = t.zok[3] ? r.w : 0.f; }
+                *reinterpret_cast<float4*>(t.p1w[o] + boff) = r;
+            }
+    }
+#pragma unroll
+    for (int o = 0; o < 2; ++o)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { h1[1][o][k] = h1[0][o][k]; h1[0][o][k] = in[o][k]; }
+    __syncthreads();
+    // ---- next raw plane: issued now, consumed at the next step ----
+    if (X + 1 < a.r1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cur[j] = __ldg(reinterpret_cast<const float4*>(t.rawp[j]));
+    }
+    // ---- second box: box1 plane P = X-1 in, cost-volume plane P-1 out ----
+    if (p1ok) {
+        float4 v[4];
+        float hl[4], hr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float* quad = t.p1r[j] + boff;
+            v[j] = *reinterpret_cast<const float4*>(quad);
+            box_halo(v[j], quad, t.bl, hl[j], hr[j]);
+        }
+        box_inplane(v, hl, hr, in);
+    } else {
+#pragma unroll
+        for (int o = 0; o < 2; ++o)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) in[o][k] = 0.f;     // a plane outside the volume
+    }
+    if (X - 2 >= a.xb) {
+#pragma unroll
+        for (int o = 0; o < 2; ++o)
+            if (t.out[o]) {
+                const float r0 = ((h2[1][o][0] + h2[0][o][0]) + in[o][0]) * c27, r1 = ((h2[1][o][1] + h2[0][o][1]) + in[o][1]) * c27,
+                            r2 = ((h2[1][o][2] + h2[0][o][2]) + in[o][2]) * c27, r3 = ((h2[1][o][3] + h2[0][o][3]) + in[o][3]) * c27;
+                if (DALIGNED) {
+                    ca_st_stream4(reinterpret_cast<float4*>(t.out[o]), make_float4(r0, r1, r2, r3));
+                } else {
+                    if (t.zok[0]) t.out[o][0] = r0;
+                    if (t.zok[1]) t.out[o][1] = r1;
+                    if (t.zok[2]) t.out[o][2] = r2;
+                    if (t.zok[3]) t.out[o][3] = r3;
+                }
+                t.out[o] += t.outPitch;
+            }
+    }
+#pragma unroll
+    for (int o = 0; o < 2; ++o)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { h2[1][o][k] = h2[0][o][k]; h2[0][o][k] = in[o][k]; }
+}
+
 // grid = (row tiles, planes of the chunk); block = nq*RP threads rounded up to whole warps, z-fastest.
 // Shared memory: two plane buffers of (2*RP rows + one all-zero row) x 4*nq floats.
-template <bool DALIGNED>
+template <bool DALIGNED, bool FAST>
 __global__ void __launch_bounds__(512, 1) k_box12(Box12Args a) {
     CA_DYN_SMEM(float, p1);
     const int tid = (int)threadIdx.x;
@@ -277,22 +393,33 @@ __global__ void __launch_bounds__(512, 1) k_box12(Box12Args a) {
         const bool in2 = rp < a.RP - 1 && y2 < a.w;
         t.out[o] = in2 ? a.ssd + (label * (a.xe - a.xb) * a.w + y2) * a.d + z0 : nullptr;
     }
-    float s1[3][2][4], s2[3][2][4];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int o = 0; o < 2; ++o)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) s1[i][o][k] = s2[i][o][k] = 0.f;
     float4 cur[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) cur[j] = __ldg(reinterpret_cast<const float4*>(t.rawp[j]));
     __syncthreads();
     // march over the global planes r0 .. xe+1 (the second box lags one plane behind the first)
-    for (int X = a.r0; X <= a.xe + 1; X += 3) {
-        box12_step<0, DALIGNED>(X, a, t, s1, s2, cur);
-        box12_step<1, DALIGNED>(X + 1, a, t, s1, s2, cur);
-        box12_step<2, DALIGNED>(X + 2, a, t, s1, s2, cur);
+    if (FAST) {
+        float h1[2][2][4], h2[2][2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int o = 0; o < 2; ++o)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) h1[i][o][k] = h2[i][o][k] = 0.f;
+        for (int X = a.r0; X <= a.xe + 1; ++X) box12_fast_step<DALIGNED>(X, a, t, h1, h2, cur);
+    } else {
+        float s1[3][2][4], s2[3][2][4];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int o = 0; o < 2; ++o)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s1[i][o][k] = s2[i][o][k] = 0.f;
+        for (int X = a.r0; X <= a.xe + 1; X += 3) {
+            box12_step<0, DALIGNED>(X, a, t, s1, s2, cur);
+            box12_step<1, DALIGNED>(X + 1, a, t, s1, s2, cur);
+            box12_step<2, DALIGNED>(X + 2, a, t, s1, s2, cur);
+        }
     }
 }
 
@@ -319,7 +446,10 @@ CorrPlan make_plan(int C, int h, int w, int d, int hw, int xb, int xe, int G) {
     p.rl = make_raw_layout(p.r1 - p.r0, w, p.dF);
     // box12 tiling: whole rows per CTA (nq quads), RP row pairs of the first box -> Ty = 2*(RP-1) output rows
     p.nq = p.dF / 4;
-    int rp_max = 512 / p.nq;
+    static int env_bt = -1;      // tuning knob: CA_BOX_THREADS = largest CTA of the box kernel (default 512)
+    if (env_bt < 0) { const char* e = getenv("CA_BOX_THREADS"); env_bt = e ? atoi(e) : 0; }
+    const int bt = (env_bt >= 64 && env_bt <= 512) ? env_bt : 512;
+    int rp_max = bt / p.nq;
     if (rp_max > (w + 3) / 2 + 1) rp_max = (w + 3) / 2 + 1;     // one tile covers all rows
     if (rp_max < 2) rp_max = 2;
     const int ty_max = 2 * (rp_max - 1);
@@ -350,19 +480,26 @@ CorrPlan make_plan(int C, int h, int w, int d, int hw, int xb, int xe, int G) {
 
 static int g_raw_minb = 0;   // tuning knob (CA_RAW_MINB env, read once): min resident blocks per SM of k_raw_ssd
 
-template <int HW>
-void launch_raw(const float* fixp, const float* movp, int C, int h, int w, int d, int chunk_start, int g, const CorrPlan& p,
-                float* raw, cudaStream_t st) {
+template <int HW, bool FAST>
+void launch_raw_t(const float* fixp, const float* movp, int C, int h, int w, int d, int chunk_start, int g, const CorrPlan& p,
+                  float* raw, cudaStream_t st) {
     const TileGeom t = make_tile(p.dF, 128);
     const dim3 grid((unsigned)g, (unsigned)(t.nzb * ((w + t.by - 1) / t.by)), (unsigned)(p.r1 - p.r0)), block(t.bx, t.by);
     if (g_raw_minb == 0) {
         const char* e = getenv("CA_RAW_MINB");
         g_raw_minb = e ? atoi(e) : 6;
-        if (g_raw_minb != 4 && g_raw_minb != 8) g_raw_minb = 6;
+        if (g_raw_minb != 4 && g_raw_minb != 5 && g_raw_minb != 8) g_raw_minb = 6;
     }
-    if (g_raw_minb == 4) { auto k = k_raw_ssd<HW, 4>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, p.dF, p.dP, chunk_start, t.zq, t.nzb, p.rl, p.r0, raw); }
-    else if (g_raw_minb == 8) { auto k = k_raw_ssd<HW, 8>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, p.dF, p.dP, chunk_start, t.zq, t.nzb, p.rl, p.r0, raw); }
-    else { auto k = k_raw_ssd<HW, 6>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, p.dF, p.dP, chunk_start, t.zq, t.nzb, p.rl, p.r0, raw); }
+    if (g_raw_minb == 5) { auto k = k_raw_ssd<HW, 5, FAST>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, p.dF, p.dP, chunk_start, t.zq, t.nzb, p.rl, p.r0, raw); }
+    else if (g_raw_minb == 4) { auto k = k_raw_ssd<HW, 4, FAST>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, p.dF, p.dP, chunk_start, t.zq, t.nzb, p.rl, p.r0, raw); }
+    else if (g_raw_minb == 8) { auto k = k_raw_ssd<HW, 8, FAST>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, p.dF, p.dP, chunk_start, t.zq, t.nzb, p.rl, p.r0, raw); }
+    else { auto k = k_raw_ssd<HW, 6, FAST>; CA_LAUNCH(k, grid, block, 0, st, fixp, movp, C, h, w, d, p.dF, p.dP, chunk_start, t.zq, t.nzb, p.rl, p.r0, raw); }
+}
+template <int HW>
+void launch_raw(bool fast, const float* fixp, const float* movp, int C, int h, int w, int d, int chunk_start, int g, const CorrPlan& p,
+                float* raw, cudaStream_t st) {
+    if (fast) launch_raw_t<HW, true>(fixp, movp, C, h, w, d, chunk_start, g, p, raw, st);
+    else launch_raw_t<HW, false>(fixp, movp, C, h, w, d, chunk_start, g, p, raw, st);
 }
 }  // namespace
 
@@ -378,10 +515,10 @@ extern "C" size_t ca_correlate_min_workspace_bytes(int C, int h, int w, int d, i
     return make_plan(C, h, w, d, disp_hw, 0, h, 1).total;
 }
 
-extern "C" int ca_correlate_slab(const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, int x_begin,
-                                 int x_end, float* ssd, int64_t* argmin, void* workspace, size_t workspace_bytes,
-                                 ca_stream_t stream) {
+static int correlate_impl(bool fast, const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, int x_begin,
+                          int x_end, float* ssd, int64_t* argmin, void* workspace, size_t workspace_bytes, ca_stream_t stream) {
     CA_CHECK_ARG(fix && mov && ssd && workspace, "correlate: null pointer");
+    CA_CHECK_ARG(!(fast && argmin), "correlate (fast): the argmin of approximate costs is not the reference's; use ca_coupled_convex_certified");
     CA_CHECK_ARG(C > 0 && h > 0 && w > 0 && d > 0, "correlate: bad dims");
     CA_CHECK_ARG(x_begin >= 0 && x_end <= h && x_begin < x_end, "correlate: bad slab [%d, %d) of %d planes", x_begin, x_end, h);
     if (disp_hw < 1 || disp_hw > 8) {
@@ -427,8 +564,10 @@ extern "C" int ca_correlate_slab(const float* fix, const float* mov, int C, int 
     {
         static bool attr_done = false;   // opt in to > 48 KB of dynamic shared memory once
         if (!attr_done) {
-            cudaFuncSetAttribute(k_box12<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-            cudaFuncSetAttribute(k_box12<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaFuncSetAttribute(k_box12<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaFuncSetAttribute(k_box12<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaFuncSetAttribute(k_box12<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaFuncSetAttribute(k_box12<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
             attr_done = true;
         }
     }
@@ -440,14 +579,14 @@ extern "C" int ca_correlate_slab(const float* fix, const float* mov, int C, int 
     for (int cs = 0; cs < npairs; cs += p.G) {
         const int g = ca_min(p.G, npairs - cs);
         switch (disp_hw) {
-            case 1: launch_raw<1>(fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
-            case 2: launch_raw<2>(fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
-            case 3: launch_raw<3>(fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
-            case 4: launch_raw<4>(fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
-            case 5: launch_raw<5>(fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
-            case 6: launch_raw<6>(fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
-            case 7: launch_raw<7>(fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
-            default: launch_raw<8>(fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
+            case 1: launch_raw<1>(fast, fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
+            case 2: launch_raw<2>(fast, fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
+            case 3: launch_raw<3>(fast, fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
+            case 4: launch_raw<4>(fast, fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
+            case 5: launch_raw<5>(fast, fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
+            case 6: launch_raw<6>(fast, fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
+            case 7: launch_raw<7>(fast, fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
+            default: launch_raw<8>(fast, fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
         }
         CA_CHECK_LAUNCH("correlate/raw");
         Box12Args a;
@@ -456,8 +595,13 @@ extern "C" int ca_correlate_slab(const float* fix, const float* mov, int C, int 
         a.r0 = p.r0; a.r1 = p.r1; a.b0 = p.b0; a.b1 = p.b1; a.xb = x_begin; a.xe = x_end;
         a.nq = p.nq; a.RP = p.RP; a.Ty = p.Ty;
         const dim3 bgrid((unsigned)p.ntiles, (unsigned)(g * S)), bblock((unsigned)p.nthreads);
-        if ((d & 3) == 0) { auto k = k_box12<true>; CA_LAUNCH(k, bgrid, bblock, p.box_smem, st, a); }
-        else { auto k = k_box12<false>; CA_LAUNCH(k, bgrid, bblock, p.box_smem, st, a); }
+        if (fast) {
+            if ((d & 3) == 0) { auto k = k_box12<true, true>; CA_LAUNCH(k, bgrid, bblock, p.box_smem, st, a); }
+            else { auto k = k_box12<false, true>; CA_LAUNCH(k, bgrid, bblock, p.box_smem, st, a); }
+        } else {
+            if ((d & 3) == 0) { auto k = k_box12<true, false>; CA_LAUNCH(k, bgrid, bblock, p.box_smem, st, a); }
+            else { auto k = k_box12<false, false>; CA_LAUNCH(k, bgrid, bblock, p.box_smem, st, a); }
+        }
         CA_CHECK_LAUNCH("correlate/box12");
     }
     if (argmin) {
@@ -471,7 +615,20 @@ extern "C" int ca_correlate_slab(const float* fix, const float* mov, int C, int 
     return CA_OK;
 }
 
+extern "C" int ca_correlate_slab(const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, int x_begin,
+                                 int x_end, float* ssd, int64_t* argmin, void* workspace, size_t workspace_bytes,
+                                 ca_stream_t stream) {
+    return correlate_impl(false, fix, mov, C, h, w, d, disp_hw, x_begin, x_end, ssd, argmin, workspace, workspace_bytes, stream);
+}
+
 extern "C" int ca_correlate(const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, float* ssd,
                             int64_t* argmin, void* workspace, size_t workspace_bytes, ca_stream_t stream) {
-    return ca_correlate_slab(fix, mov, C, h, w, d, disp_hw, 0, h, ssd, argmin, workspace, workspace_bytes, stream);
+    return correlate_impl(false, fix, mov, C, h, w, d, disp_hw, 0, h, ssd, argmin, workspace, workspace_bytes, stream);
+}
+
+// The cost volume to a few ulp (relative error <= CA_FAST_SSD_REL_ERR of each entry, see coupled.cu): the input of
+// ca_coupled_convex_certified, which still returns the reference's selections bit for bit.
+extern "C" int ca_correlate_fast(const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, float* ssd,
+                                 void* workspace, size_t workspace_bytes, ca_stream_t stream) {
+    return correlate_impl(true, fix, mov, C, h, w, d, disp_hw, 0, h, ssd, nullptr, workspace, workspace_bytes, stream);
 }

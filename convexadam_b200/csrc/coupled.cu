@@ -107,6 +107,134 @@ __global__ void __launch_bounds__(256) k_i64_to_keys(const int64_t* __restrict__
         keys[o] = (unsigned long long)in[o] & 0xffffffffull;
 }
 
+// ---- certified selection from an approximate cost volume -------------------------------------------------------------
+// ca_correlate_fast produces ssd' with |ssd' - ssd| <= 98 u * ssd (u = 2^-24): both are sums of the same non-negative
+// terms, the reference's ordered arithmetic rounds at most 68 times per entry (14 for the channel sum, 27 per box
+// filter), the fast one at most 30.  Adding the regulariser (computed identically) and the final rounding, every
+// coupled cost satisfies |c' - c| <= eps * max(c, c') with eps = 100 u = 5.96e-6.  If l* is the reference's selection
+// and l' the approximate one, c'(l*) <= c'(l') (1+eps)/(1-eps) = c'(l') (1 + 1.2e-5) < c'(l') * (1 + 2^-16): the reference's
+// selection always lies in the band.  A voxel with a single label in the band is therefore decided; the others (a few
+// hundred per million) are re-decided by k_cc_fixup, which evaluates the candidates' costs in the reference's exact
+// operation order straight from the feature volumes.  The selections -- and with them disp_soft -- are the
+// reference's bit for bit; only the cost volume itself is approximate.
+static __device__ __forceinline__ float ca_band_hi(float c) { return __fmul_ru(c, 1.0f + 0x1p-16f); }
+
+struct FixupArgs {
+    const float* ssd;           // (L, n) approximate cost volume
+    const float* mesh;          // (3, L)
+    const float* soft;          // (3, n)
+    const float* fix;           // (C, h, w, d) features the volume was built from
+    const float* mov;
+    const int* flagged;
+    const int* nflagged;
+    unsigned long long* keys;
+    int64_t n;
+    float coeff;
+    int C, h, w, d, hw;
+};
+
+// One CTA per flagged voxel: (1) the minimum approximate cost over ALL labels, (2) the labels within the band of it,
+// (3) one warp per candidate evaluates the exact cost: raw SSD on the 5x5x5 neighbourhood (utils.py:84: (f-m) rounded,
+// squared rounded, channels summed sequentially; the moving features zero-padded, utils.py:76), the first box filter at
+// the 27 neighbours (ascending (dH,dW,dD) sum of the in-volume taps, /27; zero outside the volume), the second one at
+// the voxel (utils.py:85), then + coeff * |mesh - soft|^2 as in utils.py:104.  The minimum of the (cost, label) keys is
+// the first minimum in label order, whatever order the candidates were evaluated in.
+static __device__ __forceinline__ float cc_cost(const FixupArgs& a, int L, int l, int v, float s0, float s1, float s2) {
+    const float d0 = __fsub_rn(__ldg(a.mesh + l), s0), d1 = __fsub_rn(__ldg(a.mesh + L + l), s1), d2 = __fsub_rn(__ldg(a.mesh + 2 * L + l), s2);
+    const float dist = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+    return __fadd_rn(ca_ld_stream1(a.ssd + (int64_t)l * a.n + v), __fmul_rn(a.coeff, dist));
+}
+
+#define CA_FIXUP_MAXL 4913   // (2*8+1)^3
+__global__ void __launch_bounds__(128) k_cc_fixup(FixupArgs a) {
+    __shared__ float s_raw[4][128];
+    __shared__ float s_box[4][32];
+    __shared__ float s_min[4];
+    __shared__ unsigned long long s_key[4];
+    __shared__ int s_ncand;
+    __shared__ int s_cand[CA_FIXUP_MAXL];
+    const int tid = (int)threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const int S = 2 * a.hw + 1, L = S * S * S;
+    const int count = *a.nflagged;
+    float* raw = s_raw[wib];
+    float* box = s_box[wib];
+    const int64_t cs = (int64_t)a.h * a.w * a.d;
+    for (int idx = (int)blockIdx.x; idx < count; idx += (int)gridDim.x) {
+        const int v = a.flagged[idx];
+        const int z = v % a.d, y = (v / a.d) % a.w, x = v / (a.d * a.w);
+        const float s0 = a.soft[v], s1 = a.soft[a.n + v], s2 = a.soft[2 * a.n + v];
+        if (tid == 0) s_ncand = 0;
+        float mn = INFINITY;
+#pragma unroll 6
+        for (int l = tid; l < L; l += 128) mn = fminf(mn, cc_cost(a, L, l, v, s0, s1, s2));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        if (lane == 0) s_min[wib] = mn;
+        __syncthreads();
+        const float thr = ca_band_hi(fminf(fminf(s_min[0], s_min[1]), fminf(s_min[2], s_min[3])));
+#pragma unroll 6
+        for (int l = tid; l < L; l += 128)
+            if (cc_cost(a, L, l, v, s0, s1, s2) <= thr) s_cand[atomicAdd(&s_ncand, 1)] = l;
+        __syncthreads();
+        const int ncand = s_ncand;
+        unsigned long long best = ~0ull;
+        for (int ci = wib; ci < ncand; ci += 4) {
+            const int lc = s_cand[ci];
+            const int kH = lc % S - a.hw, kW = (lc / S) % S - a.hw, kD = lc / (S * S) - a.hw;
+            // raw SSD at x + [-2,2]^3 (0 outside the volume: a +0 tap leaves an fp32 sum unchanged)
+            for (int t = lane; t < 125; t += 32) {
+                const int px = x + t / 25 - 2, py = y + (t / 5) % 5 - 2, pz = z + t % 5 - 2;
+                float acc = 0.f;
+                if (px >= 0 && px < a.h && py >= 0 && py < a.w && pz >= 0 && pz < a.d) {
+                    const int mx = px + kH, my = py + kW, mz = pz + kD;
+                    const bool min_vol = mx >= 0 && mx < a.h && my >= 0 && my < a.w && mz >= 0 && mz < a.d;
+                    const float* fp = a.fix + ((int64_t)px * a.w + py) * a.d + pz;
+                    const float* mp = a.mov + (min_vol ? ((int64_t)mx * a.w + my) * a.d + mz : 0);
+#pragma unroll 4
+                    for (int c = 0; c < a.C; ++c) {
+                        const float df = __fsub_rn(__ldg(fp + c * cs), min_vol ? __ldg(mp + c * cs) : 0.f);
+                        acc = __fadd_rn(acc, __fmul_rn(df, df));
+                    }
+                }
+                raw[t] = acc;
+            }
+            __syncwarp();
+            if (lane < 27) {
+                const int qx = lane / 9 - 1, qy = (lane / 3) % 3 - 1, qz = lane % 3 - 1;
+                float b = 0.f;
+                if (x + qx >= 0 && x + qx < a.h && y + qy >= 0 && y + qy < a.w && z + qz >= 0 && z + qz < a.d) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 27; ++e) {
+                        const int ex = qx + e / 9 - 1, ey = qy + (e / 3) % 3 - 1, ez = qz + e % 3 - 1;
+                        acc = __fadd_rn(acc, raw[(ex + 2) * 25 + (ey + 2) * 5 + (ez + 2)]);
+                    }
+                    b = ca_div27(acc);
+                }
+                box[lane] = b;
+            }
+            __syncwarp();
+            float acc = 0.f;
+#pragma unroll
+            for (int e = 0; e < 27; ++e) acc = __fadd_rn(acc, box[e]);
+            const float ssd_exact = ca_div27(acc);
+            __syncwarp();
+            const float d0 = __fsub_rn(a.mesh[lc], s0), d1 = __fsub_rn(a.mesh[L + lc], s1), d2 = __fsub_rn(a.mesh[2 * L + lc], s2);
+            const float dist = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+            const unsigned long long k = pack_key(__fadd_rn(ssd_exact, __fmul_rn(a.coeff, dist)), lc);
+            best = k < best ? k : best;
+        }
+        if (lane == 0) s_key[wib] = best;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long k = s_key[0];
+            for (int i = 1; i < 4; ++i) k = s_key[i] < k ? s_key[i] : k;
+            a.keys[v] = k;
+        }
+        __syncthreads();
+    }
+}
+
 // ---- exact pruning of the six passes -----------------------------------------------------------------------------------
 // Labels come in blocks of S consecutive ones (same kD and kW, all kH): mesh[1] and mesh[2] are constant inside a block.
 // With bmin_b(x) = min of ssd over block b, every label l of the block satisfies, in the reference's own rounded
@@ -203,13 +331,17 @@ __global__ void __launch_bounds__(256) k_mesh_boxes(const float* __restrict__ me
 
 // one coupled-convex pass that reads the slab minima (S*n floats), the block minima of the slabs that survive, and the
 // labels of the blocks that survive.  The label index is uniform across a warp, so mesh[l] is a broadcast load.
-template <int VEC, int S>
+// CERT (certified mode, see below): the costs are approximate, so a block is only skipped when its bound exceeds
+// U * (1 + 2^-16), the runner-up cost is tracked next to the best one, and a voxel whose runner-up lies within the band of
+// its best cost is appended to `flagged` for k_cc_fixup.
+template <int VEC, int S, bool CERT>
 __global__ void __launch_bounds__(128, 4) k_cost_argmin_pruned(const float* __restrict__ ssd, const float* __restrict__ bmin,
                                                             const float* __restrict__ smin, int64_t n, int L,
                                                             const float* __restrict__ mesh, const float4* __restrict__ boxes,
                                                             const float* __restrict__ soft, float coeff, int row_len,
                                                             const unsigned long long* __restrict__ prev,
-                                                            unsigned long long* __restrict__ keys) {
+                                                            unsigned long long* __restrict__ keys, int* __restrict__ flagged,
+                                                            int* __restrict__ nflagged) {
     CA_DYN_SMEM(float4, sbox);
     const int B = S * S;
     for (int i = threadIdx.x; i < 2 * B + 2 * S; i += blockDim.x) sbox[i] = boxes[i];
@@ -229,11 +361,12 @@ __global__ void __launch_bounds__(128, 4) k_cost_argmin_pruned(const float* __re
         v0 = ((warp / tpr) * 4 + (lane >> 3)) * row_len + (warp % tpr) * 32 + (lane & 7) * 4;
     }
     if (v0 >= n) return;
-    float s0[VEC], s1[VEC], s2[VEC], best[VEC], U[VEC];
+    float s0[VEC], s1[VEC], s2[VEC], best[VEC], U[VEC], second[VEC];
     int bl[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
         best[i] = INFINITY;
+        second[i] = INFINITY;
         bl[i] = 0;
         s0[i] = soft[v0 + i]; s1[i] = soft[n + v0 + i]; s2[i] = soft[2 * n + v0 + i];
     }
@@ -271,6 +404,7 @@ __global__ void __launch_bounds__(128, 4) k_cost_argmin_pruned(const float* __re
             const float dist = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
             U[i] = fminf(U[i], __fadd_rn(__ldg(ssd + (int64_t)r * n + v0 + i), __fmul_rn(coeff, dist)));
         }
+        if (CERT) U[i] = ca_band_hi(U[i]);
     }
     // level 1: which slabs can hold the argmin (S independent loads, no branches)
     unsigned slab_mask = 0;
@@ -336,6 +470,7 @@ __global__ void __launch_bounds__(128, 4) k_cost_argmin_pruned(const float* __re
                         const float d0 = __fsub_rn(m0, s0[i]), d1 = __fsub_rn(m1, s1[i]), d2 = __fsub_rn(m2, s2[i]);
                         const float dist = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
                         const float cost = __fadd_rn(c[i], __fmul_rn(coeff, dist));
+                        if (CERT) second[i] = fminf(second[i], fmaxf(cost, best[i]));
                         if (cost < best[i]) { best[i] = cost; bl[i] = l; }
                     }
                 }
@@ -343,7 +478,11 @@ __global__ void __launch_bounds__(128, 4) k_cost_argmin_pruned(const float* __re
         }
     }
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) keys[v0 + i] = pack_key(best[i], bl[i]);
+    for (int i = 0; i < VEC; ++i) {
+        keys[v0 + i] = pack_key(best[i], bl[i]);
+        // an exactly zero cost is exact in both arithmetics (every term of the sums is zero), ties included
+        if (CERT && best[i] > 0.f && second[i] <= ca_band_hi(best[i])) flagged[atomicAdd(nflagged, 1)] = (int)(v0 + i);
+    }
 }
 
 static inline unsigned small_grid(int64_t n) {
@@ -421,25 +560,31 @@ int ca_launch_mesh_boxes(const float* mesh, int S, float4* boxes, cudaStream_t s
 }
 
 // one pruned pass; keys holds the previous selection on entry and the new one on exit (each thread reads its own
-// entries before it writes them)
+// entries before it writes them).  flagged != nullptr: certified mode (approximate costs, see ca_band_hi).
 int ca_launch_cost_argmin_pruned(const float* ssd, const float* bmin, int64_t n, int S, const float* mesh, const float4* boxes,
-                                 const float* soft, float coeff, int row_len, unsigned long long* keys, cudaStream_t st) {
+                                 const float* soft, float coeff, int row_len, unsigned long long* keys, cudaStream_t st,
+                                 int* flagged = nullptr, int* nflagged = nullptr) {
     if (row_len <= 0 || row_len % 32 != 0 || (n / row_len) % 4 != 0 || n % row_len != 0) row_len = 0;   // 4x32 warp tiles need whole tiles
     const int L = S * S * S, B = S * S;
     const float* smin = bmin + (int64_t)B * n;
     const int vec = (n % 4 == 0 && ((((uintptr_t)ssd) | ((uintptr_t)bmin)) & 15) == 0) ? 4 : 1;
     const unsigned gx = (unsigned)ca_divup(ca_divup(n, vec), 128);
     const size_t smem = ((size_t)2 * B + 2 * S) * sizeof(float4);
-#define CA_PRUNED(SS)                                                                                                                   \
-    case SS:                                                                                                                            \
-        if (vec == 4) { auto k = k_cost_argmin_pruned<4, SS>; CA_LAUNCH(k, dim3(gx), dim3(128), smem, st, ssd, bmin, smin, n, L, mesh, boxes, soft, coeff, row_len, keys, keys); } \
-        else { auto k = k_cost_argmin_pruned<1, SS>; CA_LAUNCH(k, dim3(gx), dim3(128), smem, st, ssd, bmin, smin, n, L, mesh, boxes, soft, coeff, row_len, keys, keys); }        \
+    const bool cert = flagged != nullptr;
+#define CA_PRUNED_K(SS, VV, CC) { auto k = k_cost_argmin_pruned<VV, SS, CC>; CA_LAUNCH(k, dim3(gx), dim3(128), smem, st, ssd, bmin, smin, n, L, mesh, boxes, soft, coeff, row_len, keys, keys, flagged, nflagged); }
+#define CA_PRUNED(SS)                                           \
+    case SS:                                                    \
+        if (vec == 4 && cert) CA_PRUNED_K(SS, 4, true)          \
+        else if (vec == 4) CA_PRUNED_K(SS, 4, false)            \
+        else if (cert) CA_PRUNED_K(SS, 1, true)                 \
+        else CA_PRUNED_K(SS, 1, false)                          \
         break;
     switch (S) {
         CA_PRUNED(3) CA_PRUNED(5) CA_PRUNED(7) CA_PRUNED(9) CA_PRUNED(11) CA_PRUNED(13) CA_PRUNED(15) CA_PRUNED(17)
         default: ca_set_error("cost_argmin_pruned: disp_hw out of range"); return CA_ERR_UNSUPPORTED;
     }
 #undef CA_PRUNED
+#undef CA_PRUNED_K
     CA_CHECK_LAUNCH("cost_argmin_pruned");
     return CA_OK;
 }
@@ -487,6 +632,65 @@ extern "C" int ca_coupled_convex(const float* ssd, const int64_t* argmin, const 
         }
         CA_LAUNCH(k_soft_from_keys, dim3(small_grid(n)), dim3(256), 0, st, keys, mesh, h, w, d, L, disp_soft);
         CA_CHECK_LAUNCH("coupled_convex/soft");
+    }
+    return CA_OK;
+}
+
+// ---- coupled_convex on the approximate volume of ca_correlate_fast, selections certified exact -------------------------
+// workspace: [keys n u64 | bmin,smin,boxes | flagged n i32 | counters 8 i32]
+extern "C" size_t ca_coupled_convex_certified_workspace_bytes(int h, int w, int d, int disp_hw) {
+    const size_t n = (size_t)h * w * d;
+    return ca_coupled_convex_workspace_bytes(h, w, d, disp_hw) + n * 4 + 256 + 64 + 256;
+}
+
+extern "C" int ca_coupled_convex_certified(const float* ssd, const float* fix, const float* mov, int C, const float* mesh, int h,
+                                           int w, int d, int disp_hw, float* disp_soft, int64_t* sel_out, int32_t* flagged_out,
+                                           void* workspace, size_t workspace_bytes, ca_stream_t stream) {
+    CA_CHECK_ARG(ssd && fix && mov && mesh && disp_soft && workspace, "coupled_convex_certified: null pointer");
+    CA_CHECK_ARG(C > 0 && h > 0 && w > 0 && d > 0 && disp_hw >= 1 && disp_hw <= 8, "coupled_convex_certified: bad dims");
+    CA_CHECK_ARG((int64_t)h * w * d < (1ll << 31), "coupled_convex_certified: coarse grid too large");
+    if (workspace_bytes < ca_coupled_convex_certified_workspace_bytes(h, w, d, disp_hw)) {
+        ca_set_error("coupled_convex_certified: workspace too small");
+        return CA_ERR_WORKSPACE;
+    }
+    static const float coeffs[6] = {0.003f, 0.01f, 0.03f, 0.1f, 0.3f, 1.f};   // utils.py:98
+    cudaStream_t st = (cudaStream_t)stream;
+    const int S = 2 * disp_hw + 1, L = S * S * S;
+    const int64_t n = (int64_t)h * w * d;
+    unsigned long long* keys = (unsigned long long*)workspace;
+    float* bmin = (float*)(((uintptr_t)(keys + n) + 255) & ~(uintptr_t)255);
+    float4* boxes = cc_boxes_of(bmin, n, S);
+    int* flagged = (int*)(((uintptr_t)((char*)workspace + ca_coupled_convex_workspace_bytes(h, w, d, disp_hw)) + 255) & ~(uintptr_t)255);
+    int* counters = (int*)(((uintptr_t)(flagged + n) + 63) & ~(uintptr_t)63);
+    int rc;
+    if (cudaMemsetAsync(counters, 0, 8 * sizeof(int), st) != cudaSuccess || cudaMemsetAsync(disp_soft, 0, (size_t)3 * n * 4, st) != cudaSuccess) {
+        ca_set_error("coupled_convex_certified: memset failed");
+        return CA_ERR_LAUNCH;
+    }
+    // approximate argmin + block minima in one streaming pass, then the same pruned kernel with coeff = 0 (soft = 0:
+    // the regulariser term is exactly +0) certifies it: it re-reads only the blocks within the band of the minimum
+    if ((rc = ca_launch_blockmin_argmin(ssd, n, S, bmin, keys, st)) != CA_OK) return rc;
+    if ((rc = ca_launch_mesh_boxes(mesh, S, boxes, st)) != CA_OK) return rc;
+    FixupArgs fa;
+    fa.ssd = ssd; fa.mesh = mesh; fa.soft = disp_soft; fa.fix = fix; fa.mov = mov; fa.flagged = flagged; fa.keys = keys;
+    fa.n = n; fa.C = C; fa.h = h; fa.w = w; fa.d = d; fa.hw = disp_hw;
+    for (int j = -1; j < 6; ++j) {
+        const float coeff = j < 0 ? 0.f : coeffs[j];
+        int* cnt = counters + (j + 1);
+        if ((rc = ca_launch_cost_argmin_pruned(ssd, bmin, n, S, mesh, boxes, disp_soft, coeff, d, keys, st, flagged, cnt)) != CA_OK) return rc;
+        fa.coeff = coeff; fa.nflagged = cnt;
+        CA_LAUNCH(k_cc_fixup, dim3(148 * 8), dim3(128), 0, st, fa);
+        CA_CHECK_LAUNCH("coupled_convex_certified/fixup");
+        if (sel_out) {
+            rc = ca_launch_keys_to_i64(keys, n, sel_out + (int64_t)(j + 1) * n, st);
+            if (rc != CA_OK) return rc;
+        }
+        CA_LAUNCH(k_soft_from_keys, dim3(small_grid(n)), dim3(256), 0, st, keys, mesh, h, w, d, L, disp_soft);
+        CA_CHECK_LAUNCH("coupled_convex_certified/soft");
+    }
+    if (flagged_out && cudaMemcpyAsync(flagged_out, counters, 7 * sizeof(int), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+        ca_set_error("coupled_convex_certified: copy failed");
+        return CA_ERR_LAUNCH;
     }
     return CA_OK;
 }

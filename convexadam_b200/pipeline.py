@@ -5,6 +5,7 @@ Everything between the host images and the dense field stays on the GPU, on the 
 no host synchronisation (the reference syncs at utils.py:61 and round-trips the field through the CPU at
 MIND.py:156).  The cost volume (L,h,w,d) is allocated once and reused for the backward direction.
 """
+import os
 from dataclasses import dataclass
 
 import torch
@@ -31,6 +32,16 @@ class Params:
     selected_smooth: int = 0
     grid_sp_adam: int = 2
     ic: bool = True
+    # "certified": approximate cost volume (ca_correlate_fast) + selections proven equal to the exact path's
+    # (ca_coupled_convex_certified); "exact": the bit-exact cost volume (ca_correlate + ca_coupled_convex).  Both
+    # give bit-identical argmin / selections / disp_soft; CONVEXADAM_B200_MODE overrides the default.
+    mode: str = ""
+
+    def resolved_mode(self):
+        m = self.mode or os.environ.get("CONVEXADAM_B200_MODE", "certified")
+        if m not in ("certified", "exact"):
+            raise ValueError(f"unknown mode {m!r} (certified | exact)")
+        return m
 
 
 def convex_stage(lib: Lib, fix_s, mov_s, shape, prm: Params, ssd_buf=None):
@@ -44,17 +55,20 @@ def convex_stage(lib: Lib, fix_s, mov_s, shape, prm: Params, ssd_buf=None):
     L = (2 * prm.disp_hw + 1) ** 3
     if ssd_buf is None or ssd_buf.shape != (L, h, w, d):
         ssd_buf = torch.empty((L, h, w, d), dtype=torch.float32, device=dev)
-    # the argmin of utils.py:87 is taken inside coupled_convex, in the pass that builds its block minima
-    ssd, _ = lib.correlate(fix_s, mov_s, prm.disp_hw, want_argmin=False, out=ssd_buf)
-    _mark("correlate")
-    soft = lib.coupled_convex(ssd, None, mesh, prm.disp_hw)
-    _mark("coupled_convex")
+    certified = prm.resolved_mode() == "certified"
+
+    def one_direction(a, b):
+        # the argmin of utils.py:87 is taken inside coupled_convex, in the pass that builds its block minima
+        ssd, _ = lib.correlate(a, b, prm.disp_hw, want_argmin=False, out=ssd_buf, fast=certified)
+        _mark("correlate")
+        soft = lib.coupled_convex_certified(ssd, a, b, mesh, prm.disp_hw) if certified else lib.coupled_convex(ssd, None, mesh, prm.disp_hw)
+        _mark("coupled_convex")
+        return soft
+
+    soft = one_direction(fix_s, mov_s)
     if not prm.ic:
         return soft
-    ssd, _ = lib.correlate(mov_s, fix_s, prm.disp_hw, want_argmin=False, out=ssd_buf)
-    _mark("correlate")
-    soft_ = lib.coupled_convex(ssd, None, mesh, prm.disp_hw)
-    _mark("coupled_convex")
+    soft_ = one_direction(mov_s, fix_s)
     return ic_and_upsample(lib, soft, soft_, shape, prm)
 
 

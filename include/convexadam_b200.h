@@ -9,6 +9,7 @@
  *   ca_onehot_pooled       weighted one-hot + avg_pool3d     convex_adam_nnUNet.py:19-38,66-67,98-99
  *   ca_correlate           correlate                         convex_adam_utils.py:72-89
  *   ca_coupled_convex      coupled_convex                    convex_adam_utils.py:93-109
+ *   ca_correlate_fast + ca_coupled_convex_certified   the same two, fused use  convex_adam_MIND.py:124-138
  *   ca_inverse_consistency inverse_consistency               convex_adam_utils.py:114-129
  *   ca_field_affine        (x/scale).flip(1), x*scale*gs     convex_adam_MIND.py:134,139,141
  *   ca_trilinear           F.interpolate(mode='trilinear')   convex_adam_MIND.py:141,153,182
@@ -105,6 +106,25 @@ CA_API size_t ca_coupled_convex_workspace_bytes(int h, int w, int d, int disp_hw
 CA_API int ca_coupled_convex(const float* ssd, const int64_t* argmin, const float* mesh, int h, int w, int d, int disp_hw,
                       float* disp_soft, int64_t* sel_out, void* workspace, size_t workspace_bytes,
                       ca_stream_t stream);
+
+/* ---- correlate + coupled_convex, "certified" mode: the fused path convex_adam_pt uses (MIND.py:124-138) ----------
+ * Inside convex_adam_pt the cost volume never escapes: it is only ever consumed through argmin (utils.py:87) and the six
+ * selections of coupled_convex (utils.py:104-105).  ca_correlate_fast builds it with separable running sums and FMAs
+ * (about 38 instead of 94 fp32 operations per entry); every entry is within a relative 98 * 2^-24 of the reference's
+ * value (both are sums of the same non-negative terms; at most 68 roundings there, 30 here).
+ * ca_coupled_convex_certified then takes argmin and the six selections from it and proves each one: a voxel whose
+ * runner-up cost lies outside the band [best, best * (1 + 2^-16)] cannot have another selection in the reference's
+ * arithmetic; the few voxels inside the band are re-decided from exact costs, recomputed in the reference's operation
+ * order from the feature volumes (fix, mov: the same (C,h,w,d) arrays given to ca_correlate_fast).  The selections and
+ * disp_soft are therefore bit-identical to ca_correlate + ca_coupled_convex; only the volume is approximate.
+ * sel_out: optional (7,h,w,d) int64 -- plane 0 the argmin of utils.py:87, planes 1..6 the six passes.
+ * flagged_out: optional 7 int32 on the device, the number of voxels that needed the exact re-decision in each. */
+CA_API int ca_correlate_fast(const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, float* ssd,
+                      void* workspace, size_t workspace_bytes, ca_stream_t stream);
+CA_API size_t ca_coupled_convex_certified_workspace_bytes(int h, int w, int d, int disp_hw);
+CA_API int ca_coupled_convex_certified(const float* ssd, const float* fix, const float* mov, int C, const float* mesh, int h,
+                                int w, int d, int disp_hw, float* disp_soft, int64_t* sel_out, int32_t* flagged_out,
+                                void* workspace, size_t workspace_bytes, ca_stream_t stream);
 
 /* coupled_convex in pieces (the loop of utils.py:98-107 run by the host, for H slabs with a halo exchange in between):
  * ca_cc_blockmin: bmin (S*S + S, n): per-voxel minima over the S*S blocks of S consecutive labels, followed by the minima

@@ -124,3 +124,19 @@ template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { retur
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) { return emu_shfl(v, emu::lane_id() + d); }
 template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) { return emu_shfl(v, emu::lane_id() - d); }
 template <class T> static inline T __shfl_sync(unsigned, T v, int l) { return emu_shfl(v, l); }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l) {
+        const int p = emu_shfl(pred, l);
+        if (emu::warp_alive_mask_has(l) && p) r |= 1u << l;
+    }
+    return r;
+}
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+// product rounded towards +inf (the double product of two floats is exact)
+static inline float __fmul_ru(float a, float b) {
+    const double p = (double)a * (double)b;
+    float r = (float)p;
+    if ((double)r < p) r = nextafterf(r, INFINITY);
+    return r;
+}

@@ -93,6 +93,40 @@ def check_coupled(lib, device, C=12, h=6, w=7, d=8, hw=2):
     assert_bits_equal(N(soft), soft_o, "coupled_convex soft (ragged)")
 
 
+def check_certified(lib, device, cases=((12, 6, 5, 8, 2), (5, 7, 6, 12, 3), (3, 4, 5, 7, 1)), tie_case=True):
+    """correlate(fast) + coupled_convex_certified: argmin, the six selections and disp_soft bit-equal to the oracle's
+    (i.e. to the exact path); the approximate volume within the stated relative bound of the exact one."""
+    bound = 98 * 2.0 ** -24
+    cases = tuple(cases) + ((("tie",) + tuple(cases[0]), ("zero",) + tuple(cases[0])) if tie_case else ())
+    for i, case in enumerate(cases):
+        kind = case[0] if isinstance(case[0], str) else ""
+        C, h, w, d, hw = case[-5:]
+        r = rng(80 + i)
+        fix = r.rand(C, h, w, d).astype(np.float32)
+        mov = r.rand(C, h, w, d).astype(np.float32)
+        if kind:
+            # moving features constant along D: labels that differ only in kD have bit-identical costs wherever the
+            # shifted neighbourhood stays inside the volume -> exact ties, decided by the first-minimum rule
+            mov[:] = mov[..., :1]
+        if kind == "zero":
+            fix[:] = mov      # ... and all of them exactly zero along the zero-displacement line
+        ssd_o, am_o = orc.correlate(fix, mov, hw, tail=0)
+        mesh = orc.disp_mesh(hw)
+        soft_o, sel_o = orc.coupled_convex(ssd_o, am_o, mesh, want_sel=True)
+        f, m = T(fix, device), T(mov, device)
+        ssd_f, _ = lib.correlate(f, m, hw, fast=True)
+        err = np.abs(N(ssd_f).astype(np.float64) - ssd_o.astype(np.float64))
+        assert (err <= bound * ssd_o.astype(np.float64) + 1e-38).all(), f"fast ssd outside its bound: {(err / np.maximum(ssd_o, 1e-30)).max():.3e}"
+        soft, sel, flagged = lib.coupled_convex_certified(ssd_f, f, m, T(mesh, device), hw, want_sel=True, want_flagged=True)
+        assert (N(sel[0]) == am_o).all(), f"certified argmin {(C, h, w, d, hw)}"
+        assert (N(sel[1:]) == sel_o[1:]).all(), f"certified selections {(C, h, w, d, hw)}"
+        assert_bits_equal(N(soft), soft_o, f"certified disp_soft {(C, h, w, d, hw)}")
+        fl = N(flagged)
+        assert (fl >= 0).all() and (fl <= h * w * d).all()
+        if kind == "tie":
+            assert fl.sum() > 0, "the tie case must exercise the exact re-decision"
+
+
 def check_correlate_slab(lib, device, C=4, h=9, w=6, d=8, hw=2, slabs=((0, 3), (3, 4), (4, 9), (0, 1), (8, 9), (2, 7))):
     """ca_correlate_slab == the same planes of the full call, bit for bit (slab edges inside and at the faces)."""
     r = rng(70)
@@ -238,7 +272,8 @@ def check_adam(lib, device, C=12, shape=(10, 12, 14), lam=1.25, steps=(1, 2, 7))
             continue
         p, m, v = T(p0, device), T(m0, device), T(v0, device)
         u, g = lib.adam_run(T(fix, device), T(mov, device), lam, p, m, v, k + 1, 1, want_grad=True)
-        assert_bits_equal(N(u), u_o, f"adam u step {k + 1}")
+        # u = B^3 p: the fused separable kernels associate the 27x27x27 taps differently from torch's ordered sums
+        assert np.abs(N(u) - u_o).max() <= 2e-6 * max(1.0, np.abs(u_o).max()), f"adam u step {k + 1}: {np.abs(N(u) - u_o).max():.2e}"
         gmax = np.abs(g_o).max()
         assert np.abs(N(g) - g_o).max() <= 5e-6 * gmax, f"adam grad step {k + 1}: {np.abs(N(g) - g_o).max() / gmax:.2e}"
         # |dp| <= |dg| / eps (eps = 1e-8, lr = 1): the first step (v = 0) amplifies fp32 gradient noise

@@ -25,6 +25,7 @@ def test_avgpool(lib): kc.check_avgpool(lib, DEV)
 def test_mind(lib): kc.check_mind(lib, DEV, shape=(14, 12, 18))
 def test_correlate(lib): kc.check_correlate(lib, DEV, cases=((12, 4, 5, 7, 2), (16, 3, 4, 8, 1), (3, 4, 4, 5, 3)))
 def test_coupled(lib): kc.check_coupled(lib, DEV, h=4, w=5, d=8)
+def test_certified(lib): kc.check_certified(lib, DEV, cases=((12, 4, 5, 8, 2), (3, 4, 5, 7, 1)))
 def test_mesh_and_axes(lib): kc.check_mesh_and_axes(lib, DEV)
 def test_inverse_consistency(lib): kc.check_inverse_consistency(lib, DEV, shape=(6, 7, 9))
 def test_trilinear_affine_pack(lib): kc.check_trilinear_affine_pack(lib, DEV)

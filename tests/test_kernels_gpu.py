@@ -50,6 +50,10 @@ def test_coupled(lib, dev):
     kc.check_coupled(lib, dev, h=6, w=7, d=9, hw=6)
 
 
+def test_certified(lib, dev):
+    kc.check_certified(lib, dev, cases=((12, 10, 9, 16, 3), (16, 6, 7, 8, 1), (3, 5, 6, 9, 4), (12, 8, 6, 12, 6), (12, 7, 9, 10, 2)))
+
+
 def test_correlate_rejects_bad_arguments(lib, dev):
     from convexadam_b200._native import NativeError
     f = torch.zeros(12, 4, 4, 4, device=dev)
@@ -154,3 +158,29 @@ def test_full_size_identity_pair(lib, dev):
     assert bool((am == centre).all())
     soft = lib.coupled_convex(ssd, am, lib.disp_mesh(hw, dev), hw)
     assert float(soft.abs().max()) <= 1e-6
+
+
+def test_full_size_certified_equals_exact(lib, full_volume):
+    """BASELINE config 2 size: the approximate volume stays inside its stated bound (every one of the 2.16e9 entries), and
+    argmin, the six selections and disp_soft of the certified path are those of the exact path, bit for bit."""
+    fix, mov, ssd, am, orc = full_volume
+    hw = FULL["hw"]
+    dev = ssd.device
+    mesh = lib.disp_mesh(hw, dev)
+    soft_e, sel_e = lib.coupled_convex(ssd, am, mesh, hw, want_sel=True)
+    f, m = fix.to(dev), mov.to(dev)
+    ssd_f, _ = lib.correlate(f, m, hw, fast=True)
+    bound = 98 * 2.0 ** -24
+    worst = 0.0
+    for l0 in range(0, ssd.shape[0], 169):
+        a, b = ssd[l0:l0 + 169].double(), ssd_f[l0:l0 + 169].double()
+        worst = max(worst, float(((b - a).abs() / a.clamp_min(1e-30)).max()))
+    assert worst <= bound, f"fast cost volume: max relative deviation {worst:.3e} > {bound:.3e}"
+    soft_c, sel_c, flagged = lib.coupled_convex_certified(ssd_f, f, m, mesh, hw, want_sel=True, want_flagged=True)
+    assert bool((sel_c[0] == am).all()), "certified argmin"
+    for j in range(6):
+        assert bool((sel_c[j + 1] == sel_e[j]).all()), f"certified selection of pass {j}"
+    assert bool((soft_c.view(torch.int32) == soft_e.view(torch.int32)).all())
+    fl = flagged.cpu().numpy()
+    print(f"full size: max relative deviation of the fast volume {worst:.3e}; voxels re-decided exactly per selection {fl.tolist()} of {am.numel()}")
+    assert fl.sum() > 0 and fl.max() < am.numel() // 50

@@ -111,3 +111,16 @@ def test_full_size_translation_and_determinism():
     core = a[32:-32, 32:-32, 32:-32].reshape(-1, 3)
     # warped(x) = moving(x + disp): moving(x) = fixed(x - s) => disp = +s
     assert np.abs(np.median(core, 0) - np.array([2.0, -2.0, 2.0])).max() <= 0.35, np.median(core, 0)
+
+
+def test_full_size_certified_mode_equals_exact_mode():
+    """BASELINE config 2 shape with MIND features: the convex stage (both directions, inverse consistency, upsampling,
+    B^3) through the certified path == through the exact cost volume, bit for bit."""
+    from convexadam_b200 import pipeline
+    from convexadam_b200.synth import make_pair
+    dev = torch.device("cuda:0")
+    fixed, moving = make_pair((192, 160, 256), seed=3)
+    kw = dict(mind_r=1, mind_d=2, lambda_weight=1.25, grid_sp=2, disp_hw=6, selected_niter=1, selected_smooth=0, grid_sp_adam=2, ic=True)
+    a = pipeline.register_mind(fixed.to(dev), moving.to(dev), pipeline.Params(mode="exact", **kw))
+    b = pipeline.register_mind(fixed.to(dev), moving.to(dev), pipeline.Params(mode="certified", **kw))
+    assert bool((a.view(torch.int32) == b.view(torch.int32)).all())

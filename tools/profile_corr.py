@@ -13,8 +13,13 @@ dev = torch.device("cuda:0")
 f, m = make_pair((192, 160, 256), seed=0)
 fs, _ = lib.mindssc_pooled(f.to(dev), 1, 2, 2)
 ms, _ = lib.mindssc_pooled(m.to(dev), 1, 2, 2)
-ssd, am = lib.correlate(fs, ms, 6)
-if "--cc" in sys.argv:
-    soft = lib.coupled_convex(ssd, am, lib.disp_mesh(6, dev), 6)
+if "--fast" in sys.argv:       # the certified path: approximate volume + certified selections
+    ssd, _ = lib.correlate(fs, ms, 6, fast=True)
+    if "--cc" in sys.argv:
+        soft = lib.coupled_convex_certified(ssd, fs, ms, lib.disp_mesh(6, dev), 6)
+else:
+    ssd, am = lib.correlate(fs, ms, 6)
+    if "--cc" in sys.argv:
+        soft = lib.coupled_convex(ssd, am, lib.disp_mesh(6, dev), 6)
 torch.cuda.synchronize()
 print("done", lib.launch_count())
