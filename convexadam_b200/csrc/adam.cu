@@ -269,7 +269,11 @@ __global__ void __launch_bounds__(256) k_box3_p(Box3Args a) {
         const int ch = i / nq, q = i - ch * nq;
         const int y0 = ty0 + ch * a.Ly, y1 = ca_min(ca_min(y0 + a.Ly, ty0 + a.Ty), a.w);
         float4 i2 = f4zero(), i1 = f4zero(), a2 = f4zero(), a1 = f4zero(), b2 = f4zero(), b1 = f4zero();
-        for (int Y = y0 - 3; Y < y1 + 3; ++Y) {                 // row Y arrives: a[Y-1], b[Y-2], c[Y-3] complete
+        // UPDATE: the (p, m, v) rows are requested three rows ahead of their use (a queue of three register sets,
+        // statically indexed: the row loop is unrolled by three)
+        float4 pq[3], mq[3], vq[3];
+        const int64_t col = plane_off + 4 * q;
+        auto step = [&](int Y, int slot) {                      // row Y arrives: a[Y-1], b[Y-2], c[Y-3] complete
             const float4 vin = (Y >= 0 && Y < a.w) ? *reinterpret_cast<const float4*>(B + (Y - ty0 + 3) * d + 4 * q) : f4zero();
             float4 an = f4add3(i2, i1, vin);
             if (Y - 1 < 0 || Y - 1 >= a.w) an = f4zero();
@@ -277,11 +281,10 @@ __global__ void __launch_bounds__(256) k_box3_p(Box3Args a) {
             if (Y - 2 < 0 || Y - 2 >= a.w) bn = f4zero();
             const float4 cn = f4add3(b2, b1, bn);
             if (Y - 3 >= y0) {
-                const int64_t off = plane_off + (int64_t)(Y - 3) * d + 4 * q;
+                const int64_t off = col + (int64_t)(Y - 3) * d;
                 float4 r = make_float4(cn.x * c729, cn.y * c729, cn.z * c729, cn.w * c729);
                 if (UPDATE) {
-                    float4 pp = *reinterpret_cast<const float4*>(a.p + off), mm = *reinterpret_cast<const float4*>(a.m + off),
-                           vv = *reinterpret_cast<const float4*>(a.v + off);
+                    float4 pp = pq[slot], mm = mq[slot], vv = vq[slot];
                     adam_update1(pp.x, mm.x, vv.x, r.x, a.s); adam_update1(pp.y, mm.y, vv.y, r.y, a.s);
                     adam_update1(pp.z, mm.z, vv.z, r.z, a.s); adam_update1(pp.w, mm.w, vv.w, r.w, a.s);
                     *reinterpret_cast<float4*>(a.p + off) = pp;
@@ -292,7 +295,18 @@ __global__ void __launch_bounds__(256) k_box3_p(Box3Args a) {
                     *reinterpret_cast<float4*>(a.out + off) = r;
                 }
             }
+            if (UPDATE && Y >= y0 && Y < y1) {                  // consumed at step Y + 3, same slot
+                const int64_t off = col + (int64_t)Y * d;
+                pq[slot] = *reinterpret_cast<const float4*>(a.p + off);
+                mq[slot] = *reinterpret_cast<const float4*>(a.m + off);
+                vq[slot] = *reinterpret_cast<const float4*>(a.v + off);
+            }
             i2 = i1; i1 = vin; a2 = a1; a1 = an; b2 = b1; b1 = bn;
+        };
+        for (int Y = y0 - 3; Y < y1 + 3; Y += 3) {
+            step(Y, 0);
+            if (Y + 1 < y1 + 3) step(Y + 1, 1);
+            if (Y + 2 < y1 + 3) step(Y + 2, 2);
         }
     }
 }
@@ -361,7 +375,7 @@ extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int
                                   const float* g0y, const float* g0z, float* u_out, float* g_out, void* workspace,
                                   size_t workspace_bytes, int features_ready, ca_stream_t stream) {
     CA_CHECK_ARG(fix && mov && p && m && v && g0x && g0y && g0z && u_out && workspace, "adam_run: null pointer");
-    CA_CHECK_ARG(C > 0 && ha > 1 && wa > 1 && da > 1, "adam_run: bad dims (each Adam-grid axis must be >= 2)");
+    CA_CHECK_ARG(C > 0 && C <= 128 && ha > 1 && wa > 1 && da > 1, "adam_run: bad dims (1..128 channels, each Adam-grid axis >= 2)");
     CA_CHECK_ARG(lo >= 0 && hi <= ha && lo < hi, "adam_run: bad window [%d, %d) of %d planes", lo, hi, ha);
     CA_CHECK_ARG(first_step >= 1 && niter >= 0, "adam_run: bad step range");
     CA_CHECK_ARG((int64_t)ha * wa * da * ((C + 3) / 4) < (1ll << 31) && wa < 65536 && ha < 65536, "adam_run: grid too large");

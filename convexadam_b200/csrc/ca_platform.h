@@ -89,3 +89,41 @@ static __device__ __forceinline__ void ca_st_stream4(float4* p, const float4& v)
     *p = v;
 #endif
 }
+
+// ---- bulk asynchronous copies global -> shared memory (TMA engine, no tensor map: contiguous runs) --------------------
+// One mbarrier per CTA phase: thread 0 arms it with the total byte count, any thread issues copies that complete on it,
+// every thread waits for the phase.  Under CA_EMU the copy is a memcpy and the wait is a block barrier.
+#if defined(CA_EMU)
+static inline void ca_mbar_init(unsigned long long* bar, int count) { (void)bar; (void)count; }
+static inline void ca_mbar_expect_tx(unsigned long long* bar, unsigned bytes) { (void)bar; (void)bytes; }
+static inline void ca_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) { (void)bar; memcpy(dst, src, bytes); }
+static inline void ca_mbar_wait(unsigned long long* bar, unsigned parity) { (void)bar; (void)parity; emu::sync_block(); }
+#else
+static __device__ __forceinline__ unsigned ca_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+static __device__ __forceinline__ void ca_mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ca_smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+static __device__ __forceinline__ void ca_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ca_smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bytes: a multiple of 16; dst and src 16-byte aligned
+static __device__ __forceinline__ void ca_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ca_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(ca_smem_u32(bar))
+                 : "memory");
+}
+static __device__ __forceinline__ void ca_mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "CA_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra CA_MBAR_DONE;\n"
+        "bra CA_MBAR_WAIT;\n"
+        "CA_MBAR_DONE:\n"
+        "}\n" ::"r"(ca_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+#endif

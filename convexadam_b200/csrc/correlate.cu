@@ -143,6 +143,93 @@ __global__ void __launch_bounds__(128, MINB) k_raw_ssd(const float* __restrict__
     }
 }
 
+// ---- raw SSD, staged: the kernel the full-size path runs -------------------------------------------------------------
+// k_raw_ssd above reads every feature value straight from L2 and is bound by the latency of those loads (ncu: 63 % of
+// the stall samples sit on the first use of a loaded value, the L1 miss queues are full).  Here a CTA owns TY whole rows
+// of one plane x and one H-shift kH, and produces ALL S values of kD for NW consecutive values of kW from shared
+// memory: per channel the fixed rows (TY x dF, contiguous in memory) and the moving rows with their displacement
+// neighbourhood ((TY+NW-1) x dP, contiguous too: the features are stored zero-padded) arrive as ONE bulk asynchronous
+// copy each (cp.async.bulk -> UBLKCP, completion on an mbarrier): 2*C copies per CTA, the SM's load/store units and L1
+// are out of the picture, and each feature value is fetched from L2 once per CTA instead of once per (kW, thread).
+// The arithmetic per thread is that of k_raw_ssd.
+#define CA_RAW_TY 4
+struct RawStagedArgs {
+    const float* fixp;
+    const float* movp;
+    float* raw;
+    RawLayout rl;
+    int C, h, w, d, dF, dP, r0, kW0, NW;
+};
+
+template <int HW, bool FAST>
+__global__ void __launch_bounds__(256, 2) k_raw_ssd_staged(RawStagedArgs a) {
+    constexpr int S = 2 * HW + 1;
+    constexpr int NM = (4 + 2 * HW + 3) & ~3;
+    CA_DYN_SMEM(float, sm);
+    __shared__ unsigned long long bar;
+    const int nthr = (int)(blockDim.x * blockDim.y);
+    const int tid = (int)threadIdx.y * (int)blockDim.x + (int)threadIdx.x;
+    const int kH = (int)blockIdx.x;
+    const int x = a.r0 + (int)blockIdx.z;
+    const int y0t = (int)blockIdx.y * CA_RAW_TY;
+    const int hp = a.h + 2 * HW, wp = a.w + 2 * HW;
+    const int nfr = ca_min(CA_RAW_TY, a.w - y0t);                    // fixed rows of this tile
+    const int nmr = nfr + a.NW - 1;                                  // moving rows: y + kW
+    const int mrows = CA_RAW_TY + a.NW - 1;
+    const int fch = CA_RAW_TY * a.dF, mch = mrows * a.dP;            // floats per channel in shared memory
+    float* sfix = sm;                                                // [C][TY][dF]
+    float* smov = sm + (size_t)a.C * fch;                            // [C][TY+NW-1][dP]
+    if (tid == 0) ca_mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) ca_mbar_expect_tx(&bar, (unsigned)(a.C * (nfr * a.dF + nmr * a.dP) * 4));
+    for (int i = tid; i < 2 * a.C; i += nthr) {
+        const int c = i >> 1;
+        if (i & 1) ca_bulk_g2s(smov + (size_t)c * mch, a.movp + (((int64_t)c * hp + x + kH) * wp + y0t + a.kW0) * a.dP, (unsigned)(nmr * a.dP) * 4, &bar);
+        else ca_bulk_g2s(sfix + (size_t)c * fch, a.fixp + (((int64_t)c * a.h + x) * a.w + y0t) * a.dF, (unsigned)(nfr * a.dF) * 4, &bar);
+    }
+    ca_mbar_wait(&bar, 0);
+    const int ty = (int)threadIdx.y, z0 = 4 * (int)threadIdx.x;
+    const int y = y0t + ty;
+    if (y >= a.w) return;
+    const float* fs = sfix + ty * a.dF + z0;
+    float* rp0 = a.raw + (int64_t)blockIdx.z * a.rl.xPitch + (int64_t)(y + 2) * a.rl.rowPitch + 4 + z0;
+    for (int kWl = 0; kWl < a.NW; ++kWl) {
+        float acc[S][4];
+#pragma unroll
+        for (int k = 0; k < S; ++k)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[k][i] = 0.f;
+        const float* ms = smov + (ty + kWl) * a.dP + z0;
+        for (int c = 0; c < a.C; ++c) {
+            const float4 f4 = *reinterpret_cast<const float4*>(fs + c * fch);
+            const float f[4] = {f4.x, f4.y, f4.z, f4.w};
+            float m[NM];
+#pragma unroll
+            for (int j = 0; j < NM / 4; ++j) {
+                const float4 m4 = *reinterpret_cast<const float4*>(ms + c * mch + 4 * j);
+                m[4 * j + 0] = m4.x; m[4 * j + 1] = m4.y; m[4 * j + 2] = m4.z; m[4 * j + 3] = m4.w;
+            }
+#pragma unroll
+            for (int k = 0; k < S; ++k)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float df = __fsub_rn(f[i], m[i + k]);
+                    acc[k][i] = FAST ? __fmaf_rn(df, df, acc[k][i]) : __fadd_rn(acc[k][i], __fmul_rn(df, df));
+                }
+        }
+        float* rp = rp0 + (int64_t)(kWl * S + kH) * S * a.rl.plane;
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+            float4 o;
+            o.x = (z0 + 0 < a.d) ? acc[k][0] : 0.f;
+            o.y = (z0 + 1 < a.d) ? acc[k][1] : 0.f;
+            o.z = (z0 + 2 < a.d) ? acc[k][2] : 0.f;
+            o.w = (z0 + 3 < a.d) ? acc[k][3] : 0.f;
+            ca_st_stream4(reinterpret_cast<float4*>(rp + k * a.rl.plane), o);
+        }
+    }
+}
+
 // ---- the two box filters, fused ------------------------------------------------------------------------------------
 struct Box12Args {
     const float* raw;
@@ -465,6 +552,7 @@ CorrPlan make_plan(int C, int h, int w, int d, int hw, int xb, int xe, int G) {
         if (env_g < 0) { const char* e = getenv("CA_CORR_CHUNK"); env_g = e ? atoi(e) : 0; }
         G = env_g > 0 ? env_g : (int)(((size_t)3 << 30) / pair_bytes);
         if (G < 1) G = 1;
+        if (G > p.S) G -= G % p.S;      // whole kW groups: the staged raw kernel shares one moving tile among them
     }
     if (G > p.S * p.S) G = p.S * p.S;
     p.G = G;
@@ -478,6 +566,11 @@ CorrPlan make_plan(int C, int h, int w, int d, int hw, int xb, int xe, int G) {
     return p;
 }
 
+static bool use_staged() {       // CA_RAW_STAGED=0: A/B switch back to the direct-from-L2 raw kernel
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("CA_RAW_STAGED"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v == 1;
+}
 static int g_raw_minb = 0;   // tuning knob (CA_RAW_MINB env, read once): min resident blocks per SM of k_raw_ssd
 
 template <int HW, bool FAST>
@@ -500,6 +593,32 @@ void launch_raw(bool fast, const float* fixp, const float* movp, int C, int h, i
                 float* raw, cudaStream_t st) {
     if (fast) launch_raw_t<HW, true>(fixp, movp, C, h, w, d, chunk_start, g, p, raw, st);
     else launch_raw_t<HW, false>(fixp, movp, C, h, w, d, chunk_start, g, p, raw, st);
+}
+
+// staged raw kernel for a chunk of whole kW groups (chunk_start = kW0 * S, g = NW * S); false: shape not supported
+template <int HW>
+bool launch_raw_staged(bool fast, const float* fixp, const float* movp, int C, int h, int w, int d, int kW0, int NW, const CorrPlan& p,
+                       float* raw, cudaStream_t st, int* rc) {
+    constexpr int S = 2 * HW + 1;
+    const size_t smem = ((size_t)C * CA_RAW_TY * p.dF + (size_t)C * (CA_RAW_TY + NW - 1) * p.dP) * sizeof(float);
+    const int nq = p.dF / 4;
+    if (smem > 110 * 1024 || nq * CA_RAW_TY > 256) return false;     // >= two CTAs per SM, <= 256 threads
+    RawStagedArgs a;
+    a.fixp = fixp; a.movp = movp; a.raw = raw; a.rl = p.rl;
+    a.C = C; a.h = h; a.w = w; a.d = d; a.dF = p.dF; a.dP = p.dP; a.r0 = p.r0; a.kW0 = kW0; a.NW = NW;
+    const dim3 grid((unsigned)S, (unsigned)((w + CA_RAW_TY - 1) / CA_RAW_TY), (unsigned)(p.r1 - p.r0)), block((unsigned)nq, CA_RAW_TY);
+#ifndef CA_EMU
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_raw_ssd_staged<HW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        cudaFuncSetAttribute(k_raw_ssd_staged<HW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        attr_done = true;
+    }
+#endif
+    if (fast) { auto k = k_raw_ssd_staged<HW, true>; CA_LAUNCH(k, grid, block, smem, st, a); }
+    else { auto k = k_raw_ssd_staged<HW, false>; CA_LAUNCH(k, grid, block, smem, st, a); }
+    *rc = CA_OK;
+    return true;
 }
 }  // namespace
 
@@ -578,6 +697,21 @@ static int correlate_impl(bool fast, const float* fix, const float* mov, int C, 
     }
     for (int cs = 0; cs < npairs; cs += p.G) {
         const int g = ca_min(p.G, npairs - cs);
+        bool staged = false;
+        int src = CA_OK;
+        if (use_staged() && cs % S == 0 && g % S == 0) {
+            switch (disp_hw) {
+                case 1: staged = launch_raw_staged<1>(fast, fixp, movp, C, h, w, d, cs / S, g / S, p, raw, st, &src); break;
+                case 2: staged = launch_raw_staged<2>(fast, fixp, movp, C, h, w, d, cs / S, g / S, p, raw, st, &src); break;
+                case 3: staged = launch_raw_staged<3>(fast, fixp, movp, C, h, w, d, cs / S, g / S, p, raw, st, &src); break;
+                case 4: staged = launch_raw_staged<4>(fast, fixp, movp, C, h, w, d, cs / S, g / S, p, raw, st, &src); break;
+                case 5: staged = launch_raw_staged<5>(fast, fixp, movp, C, h, w, d, cs / S, g / S, p, raw, st, &src); break;
+                case 6: staged = launch_raw_staged<6>(fast, fixp, movp, C, h, w, d, cs / S, g / S, p, raw, st, &src); break;
+                case 7: staged = launch_raw_staged<7>(fast, fixp, movp, C, h, w, d, cs / S, g / S, p, raw, st, &src); break;
+                default: staged = launch_raw_staged<8>(fast, fixp, movp, C, h, w, d, cs / S, g / S, p, raw, st, &src); break;
+            }
+        }
+        if (!staged)
         switch (disp_hw) {
             case 1: launch_raw<1>(fast, fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
             case 2: launch_raw<2>(fast, fixp, movp, C, h, w, d, cs, g, p, raw, st); break;

@@ -235,6 +235,23 @@ __global__ void __launch_bounds__(128) k_cc_fixup(FixupArgs a) {
     }
 }
 
+// certification of the plain argmin (utils.py:87) from the slab minima and runner-ups: the global runner-up is the
+// winner slab's own runner-up or another slab's minimum, whichever is smaller
+__global__ void __launch_bounds__(256) k_certify_argmin(const float* __restrict__ smin, const float* __restrict__ ssec, int64_t n, int S,
+                                                        int* __restrict__ flagged, int* __restrict__ nflagged) {
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+        float best = INFINITY, second = INFINITY;
+        int bs = 0;
+        for (int sl = 0; sl < S; ++sl) {
+            const float m = ca_ld_stream1(smin + (int64_t)sl * n + v);
+            second = fminf(second, fmaxf(m, best));
+            if (m < best) { best = m; bs = sl; }
+        }
+        second = fminf(second, ca_ld_stream1(ssec + (int64_t)bs * n + v));
+        if (best > 0.f && second <= ca_band_hi(best)) flagged[atomicAdd(nflagged, 1)] = (int)v;
+    }
+}
+
 // ---- exact pruning of the six passes -----------------------------------------------------------------------------------
 // Labels come in blocks of S consecutive ones (same kD and kW, all kH): mesh[1] and mesh[2] are constant inside a block.
 // With bmin_b(x) = min of ssd over block b, every label l of the block satisfies, in the reference's own rounded
@@ -247,16 +264,18 @@ __global__ void __launch_bounds__(128) k_cc_fixup(FixupArgs a) {
 
 // one streaming pass over the volume: bmin (S*S, n) block minima, smin (S, n) minima over the S blocks that share kD
 // ("slabs" of S*S labels), and the plain argmin (utils.py:87) merged into keys.  blockIdx.y = slab.
+// ssec != nullptr (certified mode): also the runner-up cost of every slab, (S, n)
 template <int VEC>
 __global__ void __launch_bounds__(256) k_blockmin_argmin(const float* __restrict__ ssd, int64_t n, int S, float* __restrict__ bmin,
-                                                         float* __restrict__ smin, unsigned long long* __restrict__ keys) {
+                                                         float* __restrict__ smin, float* __restrict__ ssec,
+                                                         unsigned long long* __restrict__ keys) {
     const int slab = (int)blockIdx.y;
     const int64_t v0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (v0 >= n) return;
-    float best[VEC], sm[VEC];
+    float best[VEC], sm[VEC], sec[VEC];
     int bl[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { best[i] = INFINITY; sm[i] = INFINITY; bl[i] = slab * S * S; }
+    for (int i = 0; i < VEC; ++i) { best[i] = INFINITY; sm[i] = INFINITY; sec[i] = INFINITY; bl[i] = slab * S * S; }
     const float* sp = ssd + v0;
     for (int b = slab * S; b < (slab + 1) * S; ++b) {
         float bm[VEC];
@@ -275,6 +294,7 @@ __global__ void __launch_bounds__(256) k_blockmin_argmin(const float* __restrict
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
                 bm[i] = fminf(bm[i], c[i]);
+                sec[i] = fminf(sec[i], fmaxf(c[i], best[i]));
                 if (c[i] < best[i]) { best[i] = c[i]; bl[i] = l; }
             }
         }
@@ -285,6 +305,10 @@ __global__ void __launch_bounds__(256) k_blockmin_argmin(const float* __restrict
     }
     if (VEC == 4) *reinterpret_cast<float4*>(smin + (int64_t)slab * n + v0) = make_float4(sm[0], sm[1 % VEC], sm[2 % VEC], sm[3 % VEC]);
     else smin[(int64_t)slab * n + v0] = sm[0];
+    if (ssec) {
+        if (VEC == 4) *reinterpret_cast<float4*>(ssec + (int64_t)slab * n + v0) = make_float4(sec[0], sec[1 % VEC], sec[2 % VEC], sec[3 % VEC]);
+        else ssec[(int64_t)slab * n + v0] = sec[0];
+    }
     if (keys) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) atomicMin(keys + v0 + i, pack_key(best[i], bl[i]));
@@ -532,17 +556,18 @@ static bool cc_prune_enabled() {
 }
 
 // bmin (S*S,n) followed by smin (S,n) in one buffer, and, when keys != nullptr, the plain argmin as keys
-int ca_launch_blockmin_argmin(const float* ssd, int64_t n, int S, float* bmin, unsigned long long* keys, cudaStream_t st) {
+int ca_launch_blockmin_argmin(const float* ssd, int64_t n, int S, float* bmin, unsigned long long* keys, cudaStream_t st,
+                              float* ssec = nullptr) {
     float* smin = bmin + (int64_t)S * S * n;
-    const int vec = (n % 4 == 0 && ((((uintptr_t)ssd) | ((uintptr_t)bmin)) & 15) == 0) ? 4 : 1;
+    const int vec = (n % 4 == 0 && ((((uintptr_t)ssd) | ((uintptr_t)bmin) | ((uintptr_t)ssec)) & 15) == 0) ? 4 : 1;
     const unsigned gx = (unsigned)ca_divup(ca_divup(n, vec), 256);
     if (keys && cudaMemsetAsync(keys, 0xff, (size_t)n * 8, st) != cudaSuccess) {
         ca_set_error("blockmin_argmin: memset failed");
         return CA_ERR_LAUNCH;
     }
     const dim3 grid(gx, (unsigned)S), block(256);
-    if (vec == 4) { auto k = k_blockmin_argmin<4>; CA_LAUNCH(k, grid, block, 0, st, ssd, n, S, bmin, smin, keys); }
-    else { auto k = k_blockmin_argmin<1>; CA_LAUNCH(k, grid, block, 0, st, ssd, n, S, bmin, smin, keys); }
+    if (vec == 4) { auto k = k_blockmin_argmin<4>; CA_LAUNCH(k, grid, block, 0, st, ssd, n, S, bmin, smin, ssec, keys); }
+    else { auto k = k_blockmin_argmin<1>; CA_LAUNCH(k, grid, block, 0, st, ssd, n, S, bmin, smin, ssec, keys); }
     CA_CHECK_LAUNCH("blockmin_argmin");
     return CA_OK;
 }
@@ -640,7 +665,8 @@ extern "C" int ca_coupled_convex(const float* ssd, const int64_t* argmin, const 
 // workspace: [keys n u64 | bmin,smin,boxes | flagged n i32 | counters 8 i32]
 extern "C" size_t ca_coupled_convex_certified_workspace_bytes(int h, int w, int d, int disp_hw) {
     const size_t n = (size_t)h * w * d;
-    return ca_coupled_convex_workspace_bytes(h, w, d, disp_hw) + n * 4 + 256 + 64 + 256;
+    const size_t S = 2 * (size_t)disp_hw + 1;
+    return ca_coupled_convex_workspace_bytes(h, w, d, disp_hw) + n * 4 + 256 + 64 + 256 + S * n * 4 + 256;
 }
 
 extern "C" int ca_coupled_convex_certified(const float* ssd, const float* fix, const float* mov, int C, const float* mesh, int h,
@@ -662,14 +688,15 @@ extern "C" int ca_coupled_convex_certified(const float* ssd, const float* fix, c
     float4* boxes = cc_boxes_of(bmin, n, S);
     int* flagged = (int*)(((uintptr_t)((char*)workspace + ca_coupled_convex_workspace_bytes(h, w, d, disp_hw)) + 255) & ~(uintptr_t)255);
     int* counters = (int*)(((uintptr_t)(flagged + n) + 63) & ~(uintptr_t)63);
+    float* ssec = (float*)(((uintptr_t)(counters + 16) + 255) & ~(uintptr_t)255);
     int rc;
     if (cudaMemsetAsync(counters, 0, 8 * sizeof(int), st) != cudaSuccess || cudaMemsetAsync(disp_soft, 0, (size_t)3 * n * 4, st) != cudaSuccess) {
         ca_set_error("coupled_convex_certified: memset failed");
         return CA_ERR_LAUNCH;
     }
-    // approximate argmin + block minima in one streaming pass, then the same pruned kernel with coeff = 0 (soft = 0:
-    // the regulariser term is exactly +0) certifies it: it re-reads only the blocks within the band of the minimum
-    if ((rc = ca_launch_blockmin_argmin(ssd, n, S, bmin, keys, st)) != CA_OK) return rc;
+    // approximate argmin, block/slab minima and slab runner-ups in one streaming pass; k_certify_argmin then flags the
+    // voxels whose runner-up lies within the band (the fix-up runs with coeff = 0, soft = 0: regulariser exactly +0)
+    if ((rc = ca_launch_blockmin_argmin(ssd, n, S, bmin, keys, st, ssec)) != CA_OK) return rc;
     if ((rc = ca_launch_mesh_boxes(mesh, S, boxes, st)) != CA_OK) return rc;
     FixupArgs fa;
     fa.ssd = ssd; fa.mesh = mesh; fa.soft = disp_soft; fa.fix = fix; fa.mov = mov; fa.flagged = flagged; fa.keys = keys;
@@ -677,7 +704,12 @@ extern "C" int ca_coupled_convex_certified(const float* ssd, const float* fix, c
     for (int j = -1; j < 6; ++j) {
         const float coeff = j < 0 ? 0.f : coeffs[j];
         int* cnt = counters + (j + 1);
-        if ((rc = ca_launch_cost_argmin_pruned(ssd, bmin, n, S, mesh, boxes, disp_soft, coeff, d, keys, st, flagged, cnt)) != CA_OK) return rc;
+        if (j < 0) {
+            CA_LAUNCH(k_certify_argmin, dim3(small_grid(n)), dim3(256), 0, st, bmin + (int64_t)S * S * n, ssec, n, S, flagged, cnt);
+            CA_CHECK_LAUNCH("coupled_convex_certified/certify_argmin");
+        } else if ((rc = ca_launch_cost_argmin_pruned(ssd, bmin, n, S, mesh, boxes, disp_soft, coeff, d, keys, st, flagged, cnt)) != CA_OK) {
+            return rc;
+        }
         fa.coeff = coeff; fa.nflagged = cnt;
         CA_LAUNCH(k_cc_fixup, dim3(148 * 8), dim3(128), 0, st, fa);
         CA_CHECK_LAUNCH("coupled_convex_certified/fixup");
