@@ -20,6 +20,8 @@ _SIGS = {
     "ca_last_error": (C.c_char_p, []),
     "ca_is_cuda_build": (C.c_int, []),
     "ca_launch_count": (C.c_ulonglong, []),
+    "ca_kernel_timing": (None, [_i]),
+    "ca_kernel_times": (_i, [C.POINTER(C.c_double), C.POINTER(_i), _i]),
     "ca_mindssc_workspace_bytes": (_sz, [_i, _i, _i]),
     "ca_mindssc_pooled": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "ca_avgpool3d": (_i, [_vp, _i64, _i, _i, _i, _i, _i, _i, _vp, _vp]),
@@ -98,6 +100,24 @@ class Lib:
 
     def launch_count(self) -> int:
         return int(self.dll.ca_launch_count())
+
+    KERNEL_SLOTS = ("raw_ssd", "box_filters", "blockmin_argmin", "select_pass", "exact_redecision", "adam_grad", "adam_box3")
+
+    def kernel_timing(self, slots=()):
+        """Bracket the launches of the named kernels (KERNEL_SLOTS) with CUDA events on the launch stream; () = off."""
+        mask = 0
+        for name in slots:
+            mask |= 1 << self.KERNEL_SLOTS.index(name)
+        self.dll.ca_kernel_timing(mask)
+
+    def kernel_times(self):
+        """{slot: (total ms, launches)} of everything recorded since kernel_timing(); synchronise first."""
+        n = 8
+        ms, cnt = (C.c_double * n)(), (_i * n)()
+        rc = self.dll.ca_kernel_times(ms, cnt, n)
+        if rc < 0:
+            self._chk(rc)
+        return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(self.KERNEL_SLOTS) if cnt[i]}
 
     # -- helpers -----------------------------------------------------------------------------------------
     def _chk(self, rc):

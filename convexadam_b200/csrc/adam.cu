@@ -426,8 +426,10 @@ extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int
             if ((rc = box(t1, u_out)) != CA_OK) return rc;
         }
         const int bx = da >= 128 ? 128 : (da >= 64 ? 64 : 32);
+        void* tmg = ca_timing_begin(CA_T_ADAM_GRAD, st);
         CA_LAUNCH(k_adam_grad, dim3((unsigned)((da + bx - 1) / bx), (unsigned)wa, (unsigned)hl), dim3(bx), 0, st, u_out, fixcl, movcl, CG,
                   g, g0x, g0y, g0z, gu);
+        ca_timing_end(tmg, st);
         CA_CHECK_LAUNCH("adam_grad");
         if (!fast) {
             if ((rc = box(gu, t0)) != CA_OK) return rc;

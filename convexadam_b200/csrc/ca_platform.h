@@ -22,6 +22,10 @@
 #include "../../include/convexadam_b200.h"
 
 void ca_note_launch();   // counts kernel launches (ca_launch_count) -- the bench reports it
+// optional per-kernel timing with CUDA events on the launch stream (common.cu); slots:
+enum { CA_T_RAW = 0, CA_T_BOX = 1, CA_T_BLOCKMIN = 2, CA_T_SELECT = 3, CA_T_FIXUP = 4, CA_T_ADAM_GRAD = 5, CA_T_BOX3 = 6, CA_T_NSLOTS = 8 };
+void* ca_timing_begin(int slot, cudaStream_t st);
+void ca_timing_end(void* h, cudaStream_t st);
 
 // ---- error plumbing (no exceptions across the C ABI) -------------------------------------------------
 void ca_set_error(const char* fmt, ...);

@@ -324,115 +324,9 @@ static __device__ __forceinline__ void box12_step(int X, const Box12Args& a, Box
 }
 
 
-// ---- FAST variant of the same march: separable sums ------------------------------------------------------------------
-// box3 o box3 with the truncation of the intermediate to the volume is separable per axis, so each box is a 3-tap sum
-// along D (registers + the shuffled halo), along W (the 4 rows a thread holds) and along H (the in-plane sums of the two
-// previous planes): 8 additions and one multiplication by RN(1/27) per value and box instead of 26 + an exact division.
-// The result differs from the reference's ordered sum by a few ulp (<= 30 roundings against <= 68, see coupled.cu:
-// "certified selection"), which is why this mode never decides an argmin on its own.
-static __device__ __forceinline__ void box_inplane(const float4 (&v)[4], const float (&hl)[4], const float (&hr)[4], float (&out)[2][4]) {
-    float ds[4][4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        ds[j][0] = (hl[j] + v[j].x) + v[j].y;
-        ds[j][1] = (v[j].x + v[j].y) + v[j].z;
-        ds[j][2] = (v[j].y + v[j].z) + v[j].w;
-        ds[j][3] = (v[j].z + v[j].w) + hr[j];
-    }
-#pragma unroll
-    for (int o = 0; o < 2; ++o)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) out[o][k] = (ds[o][k] + ds[o + 1][k]) + ds[o + 2][k];
-}
-
-// hs[0] = in-plane sums of the previous plane, hs[1] = of the one before
-template <bool DALIGNED>
-static __device__ __forceinline__ void box12_fast_step(int X, const Box12Args& a, BoxThread& t, float (&h1)[2][2][4],
-                                                       float (&h2)[2][2][4], float4 (&cur)[4]) {
-    const float c27 = 1.0f / 27.0f;
-    const int boff = (X & 1) * t.p1buf;
-    float in[2][4];
-    // ---- first box: raw plane X in, box1 plane X-1 out (shared memory) ----
-    if (X < a.r1) {
-        float hl[4], hr[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) box_halo(cur[j], t.rawp[j], t.bl, hl[j], hr[j]);
-        box_inplane(cur, hl, hr, in);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) t.rawp[j] += t.xPitch;
-    } else {
-#pragma unroll
-        for (int o = 0; o < 2; ++o)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) in[o][k] = 0.f;
-    }
-    const bool p1ok = X - 1 >= a.b0 && X - 1 < a.b1;
-    if (p1ok) {
-#pragma unroll
-        for (int o = 0; o < 2; ++o)
-            if (t.p1w[o]) {
-                float4 r;
-                r.x = ((h1[1][o][0] + h1[0][o][0]) + in[o][0]) * c27;
-                r.y = ((h1[1][o][1] + h1[0][o][1]) + in[o][1]) * c27;
-                r.z = ((h1[1][o][2] + h1[0][o][2]) + in[o][2]) * c27;
-                r.w = ((h1[1][o][3] + h1[0][o][3]) + in[o][3]) * c27;
-                if (!DALIGNED) { r.y = t.zok[1] ? r.y : 0.f; r.z = t.zok[2] ? r.z : 0.f; r.w = t.zok[3] ? r.w : 0.f; }
-                *reinterpret_cast<float4*>(t.p1w[o] + boff) = r;
-            }
-    }
-#pragma unroll
-    for (int o = 0; o < 2; ++o)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { h1[1][o][k] = h1[0][o][k]; h1[0][o][k] = in[o][k]; }
-    __syncthreads();
-    // ---- next raw plane: issued now, consumed at the next step ----
-    if (X + 1 < a.r1) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) cur[j] = __ldg(reinterpret_cast<const float4*>(t.rawp[j]));
-    }
-    // ---- second box: box1 plane P = X-1 in, cost-volume plane P-1 out ----
-    if (p1ok) {
-        float4 v[4];
-        float hl[4], hr[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float* quad = t.p1r[j] + boff;
-            v[j] = *reinterpret_cast<const float4*>(quad);
-            box_halo(v[j], quad, t.bl, hl[j], hr[j]);
-        }
-        box_inplane(v, hl, hr, in);
-    } else {
-#pragma unroll
-        for (int o = 0; o < 2; ++o)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) in[o][k] = 0.f;     // a plane outside the volume
-    }
-    if (X - 2 >= a.xb) {
-#pragma unroll
-        for (int o = 0; o < 2; ++o)
-            if (t.out[o]) {
-                const float r0 = ((h2[1][o][0] + h2[0][o][0]) + in[o][0]) * c27, r1 = ((h2[1][o][1] + h2[0][o][1]) + in[o][1]) * c27,
-                            r2 = ((h2[1][o][2] + h2[0][o][2]) + in[o][2]) * c27, r3 = ((h2[1][o][3] + h2[0][o][3]) + in[o][3]) * c27;
-                if (DALIGNED) {
-                    ca_st_stream4(reinterpret_cast<float4*>(t.out[o]), make_float4(r0, r1, r2, r3));
-                } else {
-                    if (t.zok[0]) t.out[o][0] = r0;
-                    if (t.zok[1]) t.out[o][1] = r1;
-                    if (t.zok[2]) t.out[o][2] = r2;
-                    if (t.zok[3]) t.out[o][3] = r3;
-                }
-                t.out[o] += t.outPitch;
-            }
-    }
-#pragma unroll
-    for (int o = 0; o < 2; ++o)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { h2[1][o][k] = h2[0][o][k]; h2[0][o][k] = in[o][k]; }
-}
-
 // grid = (row tiles, planes of the chunk); block = nq*RP threads rounded up to whole warps, z-fastest.
 // Shared memory: two plane buffers of (2*RP rows + one all-zero row) x 4*nq floats.
-template <bool DALIGNED, bool FAST>
+template <bool DALIGNED>
 __global__ void __launch_bounds__(512, 1) k_box12(Box12Args a) {
     CA_DYN_SMEM(float, p1);
     const int tid = (int)threadIdx.x;
@@ -485,28 +379,181 @@ __global__ void __launch_bounds__(512, 1) k_box12(Box12Args a) {
     for (int j = 0; j < 4; ++j) cur[j] = __ldg(reinterpret_cast<const float4*>(t.rawp[j]));
     __syncthreads();
     // march over the global planes r0 .. xe+1 (the second box lags one plane behind the first)
-    if (FAST) {
-        float h1[2][2][4], h2[2][2][4];
+    float s1[3][2][4], s2[3][2][4];
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int o = 0; o < 2; ++o)
+        for (int o = 0; o < 2; ++o)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) h1[i][o][k] = h2[i][o][k] = 0.f;
-        for (int X = a.r0; X <= a.xe + 1; ++X) box12_fast_step<DALIGNED>(X, a, t, h1, h2, cur);
-    } else {
-        float s1[3][2][4], s2[3][2][4];
+            for (int k = 0; k < 4; ++k) s1[i][o][k] = s2[i][o][k] = 0.f;
+    for (int X = a.r0; X <= a.xe + 1; X += 3) {
+        box12_step<0, DALIGNED>(X, a, t, s1, s2, cur);
+        box12_step<1, DALIGNED>(X + 1, a, t, s1, s2, cur);
+        box12_step<2, DALIGNED>(X + 2, a, t, s1, s2, cur);
+    }
+}
+
+// ---- the two box filters, FAST variant: separable sums, raw planes staged by the TMA engine ---------------------------
+// box3 o box3 with the truncation of the intermediate to the volume is separable per axis, so each box is a 3-tap sum
+// along D, along W and along H (the in-plane sums of the two previous planes): 8 additions and one multiplication by
+// RN(1/27) per value and box instead of 26 additions and an exact division.  The result differs from the reference's
+// ordered sum by a few ulp (<= 30 roundings against <= 68, see coupled.cu "certified selection"), which is why this mode
+// never decides an argmin on its own.
+// Same tiling and march as k_box12, but the kernel is bound by memory latency, not by issue slots, so the raw planes do
+// not go through registers: the tile's rows of plane X+NST (one contiguous run of the chunk buffer, zero halo rows and
+// pad columns included) are requested with ONE bulk asynchronous copy (cp.async.bulk + mbarrier) into a ring of NST
+// shared-memory stages while plane X is being filtered, and every tap -- the +-1 neighbours along D included -- is a
+// shared-memory read of a zero-padded row: no shuffles, no boundary selects, no address arithmetic per row.
+#define CA_BOXF_NST 4
+struct BoxFastArgs {
+    const float* raw;
+    float* ssd;
+    RawLayout rl;
+    int w, d, S, chunk_start;
+    int r0, r1, b0, b1, xb, xe;
+    int nq, RP, Ty;
+};
+
+// sums of a 3x3 window (rows j..j+2, columns -1..+1) for the thread's two output rows x 4 columns; p = the thread's
+// first row at column z0, pitch in floats, columns z0-1 and z0+4 readable (zero pads)
+static __device__ __forceinline__ void boxf_inplane(const float* p, int pitch, float (&out)[2][4]) {
+    float ds[4][4];
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 4; ++j) {
+        const float* r = p + j * pitch;
+        const float4 v = *reinterpret_cast<const float4*>(r);
+        const float hl = r[-1], hr = r[4];
+        ds[j][0] = (hl + v.x) + v.y;
+        ds[j][1] = (v.x + v.y) + v.z;
+        ds[j][2] = (v.y + v.z) + v.w;
+        ds[j][3] = (v.z + v.w) + hr;
+    }
 #pragma unroll
-            for (int o = 0; o < 2; ++o)
+    for (int o = 0; o < 2; ++o)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) s1[i][o][k] = s2[i][o][k] = 0.f;
-        for (int X = a.r0; X <= a.xe + 1; X += 3) {
-            box12_step<0, DALIGNED>(X, a, t, s1, s2, cur);
-            box12_step<1, DALIGNED>(X + 1, a, t, s1, s2, cur);
-            box12_step<2, DALIGNED>(X + 2, a, t, s1, s2, cur);
+        for (int k = 0; k < 4; ++k) out[o][k] = (ds[o][k] + ds[o + 1][k]) + ds[o + 2][k];
+}
+
+// grid = (row tiles, planes of the chunk); block = nq*RP threads rounded up to whole warps.
+// shared memory: NST raw stages of (2*RP+2) rows, then two first-box planes of 2*RP (+2 zero) rows; row pitch dF+8, data at column 4
+template <bool DALIGNED>
+__global__ void __launch_bounds__(512, 1) k_box12_fast(BoxFastArgs a) {
+    CA_DYN_SMEM(float, sm);
+    __shared__ unsigned long long full[CA_BOXF_NST];
+    const int tid = (int)threadIdx.x, nthr = (int)blockDim.x;
+    const int q = tid % a.nq, rp = tid / a.nq;
+    const int z0 = 4 * q;
+    const int pitch = a.rl.rowPitch;
+    const int RT = 2 * a.RP + 2;                         // raw rows of the tile
+    const int stage_f = RT * pitch, p1_f = RT * pitch;       // (the last row pair's threads read two rows past the 2*RP first-box rows: zeros)
+    float* sraw = sm;
+    float* sp1 = sm + CA_BOXF_NST * stage_f;
+    const int ty0 = (int)blockIdx.x * a.Ty;
+    const int pl = (int)blockIdx.y;
+    const int g = pl / a.S, kD = pl - g * a.S;
+    const int64_t label = (int64_t)kD * a.S * a.S + a.chunk_start + g;
+    const int nrows = ca_min(RT, a.w + 4 - ty0);         // rows of the tile present in the chunk buffer
+    const unsigned copy_bytes = (unsigned)(nrows * pitch) * 4;
+    const float* src0 = a.raw + (int64_t)pl * a.rl.plane + (int64_t)ty0 * pitch;
+    // everything that is never copied or written stays zero: missing raw rows, first-box rows outside the volume, pads
+    for (int i = tid; i < CA_BOXF_NST * stage_f + 2 * p1_f; i += nthr) sm[i] = 0.f;
+    if (tid == 0)
+        for (int s = 0; s < CA_BOXF_NST; ++s) ca_mbar_init(&full[s], 1);
+    __syncthreads();
+    if (tid == 0)
+        for (int s = 0; s < CA_BOXF_NST && a.r0 + s < a.r1; ++s) {
+            ca_mbar_expect_tx(&full[s], copy_bytes);
+            ca_bulk_g2s(sraw + s * stage_f, src0 + (int64_t)s * a.rl.xPitch, copy_bytes, &full[s]);
         }
+    const bool active1 = rp < a.RP;
+    bool w1[2], w2[2];                                   // the thread's first-box rows / output rows exist
+    float* out[2];
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+        const int y1 = ty0 - 1 + 2 * rp + o, y2 = ty0 + 2 * rp + o;
+        w1[o] = active1 && y1 >= 0 && y1 < a.w;
+        w2[o] = rp < a.RP - 1 && y2 < a.w;
+        out[o] = a.ssd + (label * (a.xe - a.xb) * a.w + (w2[o] ? y2 : 0)) * a.d + z0;
+    }
+    const int roff = (active1 ? 2 * rp : 0) * pitch + 4 + z0;      // the thread's first row in a stage / first-box plane
+    const int64_t outPitch = (int64_t)a.w * a.d;
+    const float c27 = 1.0f / 27.0f;
+    float h1[2][2][4], h2[2][2][4];                      // in-plane sums of the previous plane [0] and the one before [1]
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int o = 0; o < 2; ++o)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h1[i][o][k] = h2[i][o][k] = 0.f;
+    for (int X = a.r0; X <= a.xe + 1; ++X) {
+        const int it = X - a.r0, st = it % CA_BOXF_NST;
+        float in[2][4];
+        // ---- first box: raw plane X in, box1 plane X-1 out ----
+        if (X < a.r1) {
+            ca_mbar_wait(&full[st], (unsigned)(it / CA_BOXF_NST) & 1u);
+            boxf_inplane(sraw + st * stage_f + roff, pitch, in);
+        } else {
+#pragma unroll
+            for (int o = 0; o < 2; ++o)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) in[o][k] = 0.f;
+        }
+        const bool p1ok = X - 1 >= a.b0 && X - 1 < a.b1;
+        float* p1 = sp1 + (X & 1) * p1_f;
+        if (p1ok) {
+#pragma unroll
+            for (int o = 0; o < 2; ++o)
+                if (w1[o]) {
+                    float4 r;
+                    r.x = ((h1[1][o][0] + h1[0][o][0]) + in[o][0]) * c27;
+                    r.y = ((h1[1][o][1] + h1[0][o][1]) + in[o][1]) * c27;
+                    r.z = ((h1[1][o][2] + h1[0][o][2]) + in[o][2]) * c27;
+                    r.w = ((h1[1][o][3] + h1[0][o][3]) + in[o][3]) * c27;
+                    if (!DALIGNED) { r.y = z0 + 1 < a.d ? r.y : 0.f; r.z = z0 + 2 < a.d ? r.z : 0.f; r.w = z0 + 3 < a.d ? r.w : 0.f; }
+                    *reinterpret_cast<float4*>(p1 + roff + o * pitch) = r;
+                }
+        }
+#pragma unroll
+        for (int o = 0; o < 2; ++o)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { h1[1][o][k] = h1[0][o][k]; h1[0][o][k] = in[o][k]; }
+        __syncthreads();
+        // every thread is done with stage st: refill it with plane X + NST
+        if (tid == 0 && X + CA_BOXF_NST < a.r1) {
+            ca_mbar_expect_tx(&full[st], copy_bytes);
+            ca_bulk_g2s(sraw + st * stage_f, src0 + (int64_t)(it + CA_BOXF_NST) * a.rl.xPitch, copy_bytes, &full[st]);
+        }
+        // ---- second box: box1 plane X-1 in, cost-volume plane X-2 out ----
+        if (p1ok) {
+            boxf_inplane(p1 + roff, pitch, in);
+        } else {
+#pragma unroll
+            for (int o = 0; o < 2; ++o)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) in[o][k] = 0.f;     // a plane outside the volume
+        }
+        if (X - 2 >= a.xb) {
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+                if (w2[o]) {
+                    const float r0 = ((h2[1][o][0] + h2[0][o][0]) + in[o][0]) * c27, r1 = ((h2[1][o][1] + h2[0][o][1]) + in[o][1]) * c27,
+                                r2 = ((h2[1][o][2] + h2[0][o][2]) + in[o][2]) * c27, r3 = ((h2[1][o][3] + h2[0][o][3]) + in[o][3]) * c27;
+                    if (DALIGNED) {
+                        ca_st_stream4(reinterpret_cast<float4*>(out[o]), make_float4(r0, r1, r2, r3));
+                    } else {
+                        if (z0 + 0 < a.d) out[o][0] = r0;
+                        if (z0 + 1 < a.d) out[o][1] = r1;
+                        if (z0 + 2 < a.d) out[o][2] = r2;
+                        if (z0 + 3 < a.d) out[o][3] = r3;
+                    }
+                }
+                out[o] += outPitch;
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < 2; ++o)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { h2[1][o][k] = h2[0][o][k]; h2[0][o][k] = in[o][k]; }
     }
 }
 
@@ -516,14 +563,14 @@ struct CorrPlan {
     int nq, RP, Ty, ntiles, nthreads;
     int r0, r1, b0, b1;
     RawLayout rl;
-    size_t off_fix, off_mov, off_raw, off_keys, total, chunk_bytes, box_smem;
+    size_t off_fix, off_mov, off_raw, off_keys, total, chunk_bytes, box_smem, boxf_smem;
 };
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // G = number of (kH,kW) pairs per chunk; G<=0 -> default (raw chunk buffer of up to ~3 GB: a handful of launches).
 // [xb, xe) = the H planes of the cost volume to produce (a slab of a spatially split pair; the whole volume: 0, h).
-CorrPlan make_plan(int C, int h, int w, int d, int hw, int xb, int xe, int G) {
+CorrPlan make_plan(int C, int h, int w, int d, int hw, int xb, int xe, int G, bool fast = false) {
     CorrPlan p;
     p.S = 2 * hw + 1;
     p.dF = ca_roundup4(d);
@@ -535,7 +582,9 @@ CorrPlan make_plan(int C, int h, int w, int d, int hw, int xb, int xe, int G) {
     p.nq = p.dF / 4;
     static int env_bt = -1;      // tuning knob: CA_BOX_THREADS = largest CTA of the box kernel (default 512)
     if (env_bt < 0) { const char* e = getenv("CA_BOX_THREADS"); env_bt = e ? atoi(e) : 0; }
-    const int bt = (env_bt >= 64 && env_bt <= 512) ? env_bt : 512;
+    // the fast kernel is bound by shared-memory latency and the per-plane barrier: two or three smaller CTAs per SM
+    // overlap better than one of 480 threads (measured at config 2: 8.0 vs 8.7 ms per direction)
+    const int bt = (env_bt >= 64 && env_bt <= 512) ? env_bt : (fast ? 320 : 512);
     int rp_max = bt / p.nq;
     if (rp_max > (w + 3) / 2 + 1) rp_max = (w + 3) / 2 + 1;     // one tile covers all rows
     if (rp_max < 2) rp_max = 2;
@@ -545,6 +594,7 @@ CorrPlan make_plan(int C, int h, int w, int d, int hw, int xb, int xe, int G) {
     p.RP = p.Ty / 2 + 1;
     p.nthreads = (p.nq * p.RP + 31) & ~31;
     p.box_smem = (size_t)2 * (2 * p.RP + 1) * (4 * p.nq) * sizeof(float);
+    p.boxf_smem = (size_t)(CA_BOXF_NST + 2) * (2 * p.RP + 2) * (p.dF + 8) * sizeof(float);
     const size_t plane = (size_t)h * w * p.dF * 4;
     const size_t pair_bytes = (size_t)p.S * p.rl.plane * 4;
     if (G <= 0) {
@@ -650,7 +700,7 @@ static int correlate_impl(bool fast, const float* fix, const float* mov, int C, 
     }
     CA_CHECK_ARG((int64_t)h * (w + 4) * (ca_roundup4(d) + 8) < (1ll << 31) && h < 65536, "correlate: coarse grid too large");
     // largest chunk that fits the caller's workspace (>= 1 pair), capped at the default plan
-    CorrPlan p = make_plan(C, h, w, d, disp_hw, x_begin, x_end, 0);
+    CorrPlan p = make_plan(C, h, w, d, disp_hw, x_begin, x_end, 0, fast);
     if (p.total > workspace_bytes) {
         const CorrPlan p1 = make_plan(C, h, w, d, disp_hw, x_begin, x_end, 1);
         if (p1.total > workspace_bytes) {
@@ -659,8 +709,8 @@ static int correlate_impl(bool fast, const float* fix, const float* mov, int C, 
         }
         const size_t pair_bytes = p1.chunk_bytes;
         int G = 1 + (int)((workspace_bytes - p1.total) / pair_bytes);
-        p = make_plan(C, h, w, d, disp_hw, x_begin, x_end, G);
-        while (p.total > workspace_bytes && p.G > 1) p = make_plan(C, h, w, d, disp_hw, x_begin, x_end, p.G - 1);
+        p = make_plan(C, h, w, d, disp_hw, x_begin, x_end, G, fast);
+        while (p.total > workspace_bytes && p.G > 1) p = make_plan(C, h, w, d, disp_hw, x_begin, x_end, p.G - 1, fast);
     }
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
@@ -683,20 +733,21 @@ static int correlate_impl(bool fast, const float* fix, const float* mov, int C, 
     {
         static bool attr_done = false;   // opt in to > 48 KB of dynamic shared memory once
         if (!attr_done) {
-            cudaFuncSetAttribute(k_box12<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-            cudaFuncSetAttribute(k_box12<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-            cudaFuncSetAttribute(k_box12<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-            cudaFuncSetAttribute(k_box12<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaFuncSetAttribute(k_box12<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaFuncSetAttribute(k_box12<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaFuncSetAttribute(k_box12_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_box12_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             attr_done = true;
         }
     }
 #endif
-    if (p.box_smem > 160 * 1024) {
+    if (p.box_smem > 160 * 1024 || (fast && p.boxf_smem > 200 * 1024)) {
         ca_set_error("correlate: row tile needs %zu bytes of shared memory", p.box_smem);
         return CA_ERR_UNSUPPORTED;
     }
     for (int cs = 0; cs < npairs; cs += p.G) {
         const int g = ca_min(p.G, npairs - cs);
+        void* tm = ca_timing_begin(CA_T_RAW, st);
         bool staged = false;
         int src = CA_OK;
         if (use_staged() && cs % S == 0 && g % S == 0) {
@@ -722,7 +773,9 @@ static int correlate_impl(bool fast, const float* fix, const float* mov, int C, 
             case 7: launch_raw<7>(fast, fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
             default: launch_raw<8>(fast, fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
         }
+        ca_timing_end(tm, st);
         CA_CHECK_LAUNCH("correlate/raw");
+        tm = ca_timing_begin(CA_T_BOX, st);
         Box12Args a;
         a.raw = raw; a.ssd = ssd; a.rl = p.rl;
         a.w = w; a.d = d; a.S = S; a.chunk_start = cs;
@@ -730,12 +783,18 @@ static int correlate_impl(bool fast, const float* fix, const float* mov, int C, 
         a.nq = p.nq; a.RP = p.RP; a.Ty = p.Ty;
         const dim3 bgrid((unsigned)p.ntiles, (unsigned)(g * S)), bblock((unsigned)p.nthreads);
         if (fast) {
-            if ((d & 3) == 0) { auto k = k_box12<true, true>; CA_LAUNCH(k, bgrid, bblock, p.box_smem, st, a); }
-            else { auto k = k_box12<false, true>; CA_LAUNCH(k, bgrid, bblock, p.box_smem, st, a); }
+            BoxFastArgs f;
+            f.raw = raw; f.ssd = ssd; f.rl = p.rl;
+            f.w = w; f.d = d; f.S = S; f.chunk_start = cs;
+            f.r0 = p.r0; f.r1 = p.r1; f.b0 = p.b0; f.b1 = p.b1; f.xb = x_begin; f.xe = x_end;
+            f.nq = p.nq; f.RP = p.RP; f.Ty = p.Ty;
+            if ((d & 3) == 0) { auto k = k_box12_fast<true>; CA_LAUNCH(k, bgrid, bblock, p.boxf_smem, st, f); }
+            else { auto k = k_box12_fast<false>; CA_LAUNCH(k, bgrid, bblock, p.boxf_smem, st, f); }
         } else {
-            if ((d & 3) == 0) { auto k = k_box12<true, false>; CA_LAUNCH(k, bgrid, bblock, p.box_smem, st, a); }
-            else { auto k = k_box12<false, false>; CA_LAUNCH(k, bgrid, bblock, p.box_smem, st, a); }
+            if ((d & 3) == 0) { auto k = k_box12<true>; CA_LAUNCH(k, bgrid, bblock, p.box_smem, st, a); }
+            else { auto k = k_box12<false>; CA_LAUNCH(k, bgrid, bblock, p.box_smem, st, a); }
         }
+        ca_timing_end(tm, st);
         CA_CHECK_LAUNCH("correlate/box12");
     }
     if (argmin) {

@@ -566,8 +566,10 @@ int ca_launch_blockmin_argmin(const float* ssd, int64_t n, int S, float* bmin, u
         return CA_ERR_LAUNCH;
     }
     const dim3 grid(gx, (unsigned)S), block(256);
+    void* tm = ca_timing_begin(CA_T_BLOCKMIN, st);
     if (vec == 4) { auto k = k_blockmin_argmin<4>; CA_LAUNCH(k, grid, block, 0, st, ssd, n, S, bmin, smin, ssec, keys); }
     else { auto k = k_blockmin_argmin<1>; CA_LAUNCH(k, grid, block, 0, st, ssd, n, S, bmin, smin, ssec, keys); }
+    ca_timing_end(tm, st);
     CA_CHECK_LAUNCH("blockmin_argmin");
     return CA_OK;
 }
@@ -596,6 +598,7 @@ int ca_launch_cost_argmin_pruned(const float* ssd, const float* bmin, int64_t n,
     const unsigned gx = (unsigned)ca_divup(ca_divup(n, vec), 128);
     const size_t smem = ((size_t)2 * B + 2 * S) * sizeof(float4);
     const bool cert = flagged != nullptr;
+    void* tm = ca_timing_begin(CA_T_SELECT, st);
 #define CA_PRUNED_K(SS, VV, CC) { auto k = k_cost_argmin_pruned<VV, SS, CC>; CA_LAUNCH(k, dim3(gx), dim3(128), smem, st, ssd, bmin, smin, n, L, mesh, boxes, soft, coeff, row_len, keys, keys, flagged, nflagged); }
 #define CA_PRUNED(SS)                                           \
     case SS:                                                    \
@@ -610,6 +613,7 @@ int ca_launch_cost_argmin_pruned(const float* ssd, const float* bmin, int64_t n,
     }
 #undef CA_PRUNED
 #undef CA_PRUNED_K
+    ca_timing_end(tm, st);
     CA_CHECK_LAUNCH("cost_argmin_pruned");
     return CA_OK;
 }
@@ -711,7 +715,9 @@ extern "C" int ca_coupled_convex_certified(const float* ssd, const float* fix, c
             return rc;
         }
         fa.coeff = coeff; fa.nflagged = cnt;
+        void* tmf = ca_timing_begin(CA_T_FIXUP, st);
         CA_LAUNCH(k_cc_fixup, dim3(148 * 8), dim3(128), 0, st, fa);
+        ca_timing_end(tmf, st);
         CA_CHECK_LAUNCH("coupled_convex_certified/fixup");
         if (sel_out) {
             rc = ca_launch_keys_to_i64(keys, n, sel_out + (int64_t)(j + 1) * n, st);

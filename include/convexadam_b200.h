@@ -54,6 +54,13 @@ CA_API const char* ca_last_error(void);
 CA_API int ca_is_cuda_build(void);
 /* Number of kernels this library has launched in this process so far (bench.py reports the per-step count). */
 CA_API unsigned long long ca_launch_count(void);
+/* Measurement aid (bench.py): ca_kernel_timing(mask) makes the library bracket the launches of the kernels whose slot
+ * bit is set in mask with CUDA
+ * events on the launch stream (no synchronisation); after the caller has synchronised, ca_kernel_times sums them per
+ * slot (0 raw SSD, 1 box filters, 2 block minima + argmin, 3 coupled-convex selection pass, 4 exact re-decision,
+ * 5 Adam gradient, 6 Adam B^3) and returns the number of recorded launches.  ca_kernel_timing(0) switches it off. */
+CA_API void ca_kernel_timing(int slot_mask);
+CA_API int ca_kernel_times(double* ms, int* count, int nslots);
 
 /* ---- MIND-SSC descriptor fused with block-mean pooling (utils.py:24-68 + MIND.py:118-119) -------------------
  * img (H,W,D) f32.  Up to two pooled outputs (pool factor gs_a / gs_b, 0 = absent; 1 = full resolution, i.e. the
