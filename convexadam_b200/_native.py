@@ -142,8 +142,13 @@ class Lib:
     def _p(t):
         return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
+    poison_workspaces = False   # tests: fill every workspace with 0xFF (NaN patterns) so that any read of unwritten scratch shows
+
     def _ws(self, nbytes, ref):
-        return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=ref.device)
+        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=ref.device)
+        if self.poison_workspaces:
+            ws.fill_(255)
+        return ws
 
     def const(self, key, maker, device):
         k = (key, str(device))

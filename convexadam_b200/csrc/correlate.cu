@@ -43,6 +43,28 @@ __global__ void __launch_bounds__(256) k_pad_features(const float* __restrict__ 
     }
 }
 
+// zero halo of the chunk buffer (rows -2,-1,w,w+1 of every plane slice and the 4+4 pad columns of the others): the
+// raw kernels only ever write interiors, the box kernels read rows/columns around a tile without bounds checks
+__global__ void __launch_bounds__(256) k_zero_raw_halo(float* __restrict__ raw, int64_t nslices, int w, int rowPitch) {
+    const int per_slice = 4 * (rowPitch / 4) + 2 * w;          // float4 items: 4 whole rows + 2 pad quads per interior row
+    const int64_t total = nslices * per_slice;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t sl = i / per_slice;
+        const int k = (int)(i - sl * per_slice);
+        float* base = raw + sl * (int64_t)(w + 4) * rowPitch;
+        const int rq = rowPitch / 4;
+        if (k < 4 * rq) {
+            const int r = k / rq, q = k - r * rq;
+            const int row = r < 2 ? r : w + r;                 // rows 0, 1, w+2, w+3
+            *reinterpret_cast<float4*>(base + (int64_t)row * rowPitch + 4 * q) = z;
+        } else {
+            const int j = k - 4 * rq, row = 2 + (j >> 1);
+            *reinterpret_cast<float4*>(base + (int64_t)row * rowPitch + ((j & 1) ? rowPitch - 4 : 0)) = z;
+        }
+    }
+}
+
 // ---- tile geometry of the raw-SSD kernel ---------------------------------------------------------------------------
 // A block is (bx, by) threads: bx consecutive z-quads (4 voxels each) x by consecutive y rows; grid = (tiles, h, planes)
 // so that no thread ever needs a 64-bit div/mod (the kernels are issue-bound, index maths must be free).
@@ -723,11 +745,11 @@ static int correlate_impl(bool fast, const float* fix, const float* mov, int C, 
         CA_LAUNCH(k_pad_features, dim3((unsigned)ca_min((int)ca_divup(tf, 256), 148 * 16)), dim3(256), 0, st, fix, C, h, w, d, 0, p.dF, fixp);
         CA_LAUNCH(k_pad_features, dim3((unsigned)ca_min((int)ca_divup(tm, 256), 148 * 16)), dim3(256), 0, st, mov, C, h, w, d, disp_hw, p.dP, movp);
         CA_CHECK_LAUNCH("correlate/pad");
-        // zero the halo rows / pad columns of the chunk buffer once; the raw kernel only ever writes interiors
-        if (cudaMemsetAsync(raw, 0, p.chunk_bytes, st) != cudaSuccess) {
-            ca_set_error("correlate: memset failed");
-            return CA_ERR_LAUNCH;
-        }
+        // zero the halo rows / pad columns of the chunk buffer once; the raw kernels only ever write interiors
+        const int64_t nslices = (int64_t)p.G * p.S * (p.r1 - p.r0);
+        CA_LAUNCH(k_zero_raw_halo, dim3((unsigned)ca_min((int)ca_divup(nslices * (4 * (p.rl.rowPitch / 4) + 2 * w), 256), 148 * 16)), dim3(256), 0, st,
+                  raw, nslices, w, p.rl.rowPitch);
+        CA_CHECK_LAUNCH("correlate/zero_halo");
     }
 #ifndef CA_EMU
     {

@@ -36,6 +36,14 @@ class Params:
     # (ca_coupled_convex_certified); "exact": the bit-exact cost volume (ca_correlate + ca_coupled_convex).  Both
     # give bit-identical argmin / selections / disp_soft; CONVEXADAM_B200_MODE overrides the default.
     mode: str = ""
+    # "1": run the forward and the backward direction of the convex stage on two CUDA streams (needs a second cost
+    # volume).  Measured at config 2: 24.1 instead of 25.9 ms for the stage (+4 % pairs/s); off by default because the
+    # kernels of the two directions then time-share the SMs and per-kernel timings stop being meaningful.
+    # "" = CONVEXADAM_B200_OVERLAP, default off
+    overlap: str = ""
+
+    def resolved_overlap(self):
+        return (self.overlap or os.environ.get("CONVEXADAM_B200_OVERLAP", "0")) in ("1", "on", "true", "True")
 
     def resolved_mode(self):
         m = self.mode or os.environ.get("CONVEXADAM_B200_MODE", "certified")
@@ -57,19 +65,64 @@ def convex_stage(lib: Lib, fix_s, mov_s, shape, prm: Params, ssd_buf=None):
         ssd_buf = torch.empty((L, h, w, d), dtype=torch.float32, device=dev)
     certified = prm.resolved_mode() == "certified"
 
-    def one_direction(a, b):
+    def one_direction(a, b, buf, mark=True):
         # the argmin of utils.py:87 is taken inside coupled_convex, in the pass that builds its block minima
-        ssd, _ = lib.correlate(a, b, prm.disp_hw, want_argmin=False, out=ssd_buf, fast=certified)
-        _mark("correlate")
+        ssd, _ = lib.correlate(a, b, prm.disp_hw, want_argmin=False, out=buf, fast=certified)
+        if mark:
+            _mark("correlate")
         soft = lib.coupled_convex_certified(ssd, a, b, mesh, prm.disp_hw) if certified else lib.coupled_convex(ssd, None, mesh, prm.disp_hw)
-        _mark("coupled_convex")
+        if mark:
+            _mark("coupled_convex")
         return soft
 
-    soft = one_direction(fix_s, mov_s)
     if not prm.ic:
-        return soft
-    soft_ = one_direction(mov_s, fix_s)
-    return ic_and_upsample(lib, soft, soft_, shape, prm)
+        return one_direction(fix_s, mov_s, ssd_buf)
+    if not (prm.resolved_overlap() and lib.is_cuda):
+        soft = one_direction(fix_s, mov_s, ssd_buf)
+        soft_ = one_direction(mov_s, fix_s, ssd_buf)
+        return ic_and_upsample(lib, soft, soft_, shape, prm)
+    # The two directions are independent until inverse consistency: issue them on two streams so that the latency-bound
+    # kernels of one (selection passes, exact re-decisions, box filters) share the SMs with the issue-bound raw SSD
+    # kernel of the other.  Each direction owns a cost volume; both streams start after, and are joined by, the
+    # caller's stream.
+    main = torch.cuda.current_stream(dev)
+    side = _side_streams(dev)
+    ssd_buf2 = _second_volume(ssd_buf)
+    start = torch.cuda.Event()
+    start.record(main)
+    outs = []
+    for st, (a, b, buf) in zip(side, ((fix_s, mov_s, ssd_buf), (mov_s, fix_s, ssd_buf2))):
+        st.wait_event(start)
+        with torch.cuda.stream(st):
+            outs.append(one_direction(a, b, buf, mark=False))
+        done = torch.cuda.Event()
+        done.record(st)
+        main.wait_event(done)
+    for t in (fix_s, mov_s, ssd_buf, ssd_buf2) + tuple(outs):
+        for st in side:
+            t.record_stream(st)
+    _mark("correlate+coupled_convex (two directions on two streams)")
+    return ic_and_upsample(lib, outs[0], outs[1], shape, prm)
+
+
+_SIDE = {}
+_VOL2 = {}
+
+
+def _side_streams(dev):
+    key = str(dev)
+    if key not in _SIDE:
+        _SIDE[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+    return _SIDE[key]
+
+
+def _second_volume(buf):
+    """The backward direction's cost volume (cached per device and shape: 8.6 GB at config 2)."""
+    key = (str(buf.device), tuple(buf.shape))
+    if key not in _VOL2:
+        _VOL2.clear()
+        _VOL2[key] = torch.empty_like(buf)
+    return _VOL2[key]
 
 
 def ic_and_upsample(lib: Lib, soft, soft_, shape, prm: Params):

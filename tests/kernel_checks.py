@@ -53,6 +53,14 @@ def check_mind(lib, device, shape=(22, 18, 26)):
 
 
 def check_correlate(lib, device, cases=((12, 6, 5, 7, 2), (16, 4, 6, 8, 1), (3, 5, 4, 9, 3), (12, 7, 6, 12, 2))):
+    lib.poison_workspaces = True        # scratch starts as NaN patterns: nothing may depend on its previous content
+    try:
+        _check_correlate(lib, device, cases)
+    finally:
+        lib.poison_workspaces = False
+
+
+def _check_correlate(lib, device, cases):
     for i, (C, h, w, d, hw) in enumerate(cases):
         r = rng(10 + i)
         fix = r.rand(C, h, w, d).astype(np.float32)
@@ -96,6 +104,14 @@ def check_coupled(lib, device, C=12, h=6, w=7, d=8, hw=2):
 def check_certified(lib, device, cases=((12, 6, 5, 8, 2), (5, 7, 6, 12, 3), (3, 4, 5, 7, 1)), tie_case=True):
     """correlate(fast) + coupled_convex_certified: argmin, the six selections and disp_soft bit-equal to the oracle's
     (i.e. to the exact path); the approximate volume within the stated relative bound of the exact one."""
+    lib.poison_workspaces = True
+    try:
+        _check_certified(lib, device, cases, tie_case)
+    finally:
+        lib.poison_workspaces = False
+
+
+def _check_certified(lib, device, cases, tie_case):
     bound = 98 * 2.0 ** -24
     cases = tuple(cases) + ((("tie",) + tuple(cases[0]), ("zero",) + tuple(cases[0])) if tie_case else ())
     for i, case in enumerate(cases):
