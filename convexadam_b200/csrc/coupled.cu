@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(256) k_mesh_boxes(const float* __restrict__ me
 // U * (1 + 2^-16), the runner-up cost is tracked next to the best one, and a voxel whose runner-up lies within the band of
 // its best cost is appended to `flagged` for k_cc_fixup.
 template <int VEC, int S, bool CERT>
-__global__ void __launch_bounds__(128, 4) k_cost_argmin_pruned(const float* __restrict__ ssd, const float* __restrict__ bmin,
+__global__ void __launch_bounds__(128, 5) k_cost_argmin_pruned(const float* __restrict__ ssd, const float* __restrict__ bmin,
                                                             const float* __restrict__ smin, int64_t n, int L,
                                                             const float* __restrict__ mesh, const float4* __restrict__ boxes,
                                                             const float* __restrict__ soft, float coeff, int row_len,
@@ -394,31 +394,18 @@ __global__ void __launch_bounds__(128, 4) k_cost_argmin_pruned(const float* __re
         bl[i] = 0;
         s0[i] = soft[v0 + i]; s1[i] = soft[n + v0 + i]; s2[i] = soft[2 * n + v0 + i];
     }
-    // The bound U: the exact cost, under the new soft field and coefficient, of (a) the previous selection and (b) a label
-    // close to soft(x) found by descending the boxes (slab -> block -> label).  Any label gives a valid bound.
+    // The bound U: the exact cost, under the new soft field and coefficient, of (a) the previous selection and (b) the
+    // label next to soft(x).  Any label gives a valid bound.
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
         int cand[2];
         cand[0] = (int)(unsigned)(prev[v0 + i] & 0xffffffffull);
-        int bs = 0;
-        float bd = INFINITY;
-        for (int sl = 0; sl < S; ++sl) {
-            const float dd = box_dist(slo[sl], shi[sl], s0[i], s1[i], s2[i]);
-            if (dd < bd) { bd = dd; bs = sl; }
-        }
-        int bb = bs * S;
-        bd = INFINITY;
-        for (int k = 0; k < S; ++k) {
-            const float dd = box_dist(blo[bs * S + k], bhi[bs * S + k], s0[i], s1[i], s2[i]);
-            if (dd < bd) { bd = dd; bb = bs * S + k; }
-        }
-        cand[1] = bb * S;
-        bd = INFINITY;
-        for (int k = 0; k < S; ++k) {
-            const int l = bb * S + k;
-            const float d0 = __ldg(mesh + l) - s0[i], d1 = __ldg(mesh + L + l) - s1[i], d2 = __ldg(mesh + 2 * L + l) - s2[i];
-            const float dd = d0 * d0 + d1 * d1 + d2 * d2;
-            if (dd < bd) { bd = dd; cand[1] = l; }
+        // the label next to soft(x) on the regular displacement grid (mesh[c, l] ~ k_c - hw): one more upper bound
+        {
+            const float hwf = 0.5f * (float)(S - 1);
+            const int kH = ca_clamp((int)rintf(s0[i] + hwf), 0, S - 1), kW = ca_clamp((int)rintf(s1[i] + hwf), 0, S - 1),
+                      kD = ca_clamp((int)rintf(s2[i] + hwf), 0, S - 1);
+            cand[1] = (kD * S + kW) * S + kH;
         }
         U[i] = INFINITY;
 #pragma unroll

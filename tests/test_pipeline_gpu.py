@@ -124,3 +124,7 @@ def test_full_size_certified_mode_equals_exact_mode():
     a = pipeline.register_mind(fixed.to(dev), moving.to(dev), pipeline.Params(mode="exact", **kw))
     b = pipeline.register_mind(fixed.to(dev), moving.to(dev), pipeline.Params(mode="certified", **kw))
     assert bool((a.view(torch.int32) == b.view(torch.int32)).all())
+    # ... and with the two directions issued on two streams
+    c = pipeline.register_mind(fixed.to(dev), moving.to(dev), pipeline.Params(mode="certified", overlap="1", **kw))
+    torch.cuda.synchronize()
+    assert bool((a.view(torch.int32) == c.view(torch.int32)).all())
