@@ -125,10 +125,17 @@ def cpu_reference_sample(shape, prm, niter, scale_div):
     return 1.0 / (dt * ratio), dt, desc, os.cpu_count()
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use every host core (set before the
+    OpenMP runtime of the oracle / torch initialises)."""
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
+
+
 def run_reference(args, shape, prm):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     from oracle import ca_oracle as orc
     orc.build()
     total = args.steps + args.warmup
@@ -145,7 +152,7 @@ def run_reference(args, shape, prm):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t * ratio, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "192x160x256 pair, MIND-SSC r1 d2, disp_hw=6, grid_sp=2, grid_sp_adam=2, %d Adam it., ic=True" % args.niter,
+        "config": {"workload": "%dx%dx%d pair, MIND-SSC r1 d2, disp_hw=6, grid_sp=2, grid_sp_adam=2, %d Adam it., ic=True, fp32 cost volume" % (tuple(shape) + (args.niter,)),
                    "note": "CPU arm: the reference is pure Python over torch and absent on the GPU box; this is its C restatement "
                            "(oracle/ca_oracle.c, pinned bit-exact to reference golden vectors) on all host threads"},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": desc},
@@ -310,6 +317,11 @@ def main():
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
     }
     if not args.no_cpu_baseline and world == 1:
+        import ctypes
+        try:    # torch's OpenMP runtime is already up: raise its thread count directly (the oracle shares libgomp)
+            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(os.cpu_count())
+        except OSError:
+            pass
         from oracle import ca_oracle as orc
         orc.build()
         v, dt, desc, cores = cpu_reference_sample(shape, prm, args.niter, 2)
