@@ -285,7 +285,7 @@ def main():
     roof = kernel_line("box_filters", box_name, ndir * ab["box_per_direction"], "hbm",
                        "dominant kernel of the step; reads the raw SSD planes once, writes the cost volume once")
     # DRAM bytes per launch of the dominant kernel from the committed ncu capture of the same kernel at this shape
-    # (profiles/r1_ncu_box12_fast.txt: dram__bytes_read.sum + dram__bytes_write.sum, 52-pair launch)
+    # (profiles/r1_ncu_k_box12_fast.txt: dram__bytes_read.sum + dram__bytes_write.sum, 52-pair launch)
     if roof is not None:
         roof["traffic"] = 5.576e9 if (mode == "certified" and tuple(shape) == (192, 160, 256)) else None
     others = [kernel_line("raw_ssd", "k_raw_ssd_staged (SSD over 13 kD x 4 kW per CTA from TMA-staged tiles)",

@@ -45,22 +45,21 @@ __global__ void __launch_bounds__(256) k_pad_features(const float* __restrict__ 
 
 // zero halo of the chunk buffer (rows -2,-1,w,w+1 of every plane slice and the 4+4 pad columns of the others): the
 // raw kernels only ever write interiors, the box kernels read rows/columns around a tile without bounds checks
-__global__ void __launch_bounds__(256) k_zero_raw_halo(float* __restrict__ raw, int64_t nslices, int w, int rowPitch) {
-    const int per_slice = 4 * (rowPitch / 4) + 2 * w;          // float4 items: 4 whole rows + 2 pad quads per interior row
-    const int64_t total = nslices * per_slice;
+__global__ void __launch_bounds__(128) k_zero_raw_halo(float* __restrict__ raw, int64_t nslices, int w, int rowPitch) {
+    const int rq = rowPitch / 4;
+    const int per_slice = 4 * rq + 2 * w;                      // float4 items: 4 whole rows + 2 pad quads per interior row
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t sl = i / per_slice;
-        const int k = (int)(i - sl * per_slice);
+    for (int64_t sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
         float* base = raw + sl * (int64_t)(w + 4) * rowPitch;
-        const int rq = rowPitch / 4;
-        if (k < 4 * rq) {
-            const int r = k / rq, q = k - r * rq;
-            const int row = r < 2 ? r : w + r;                 // rows 0, 1, w+2, w+3
-            *reinterpret_cast<float4*>(base + (int64_t)row * rowPitch + 4 * q) = z;
-        } else {
-            const int j = k - 4 * rq, row = 2 + (j >> 1);
-            *reinterpret_cast<float4*>(base + (int64_t)row * rowPitch + ((j & 1) ? rowPitch - 4 : 0)) = z;
+        for (int k = (int)threadIdx.x; k < per_slice; k += (int)blockDim.x) {
+            if (k < 4 * rq) {
+                const int r = k / rq, q = k - r * rq;
+                const int row = r < 2 ? r : w + r;             // rows 0, 1, w+2, w+3
+                *reinterpret_cast<float4*>(base + row * rowPitch + 4 * q) = z;
+            } else {
+                const int j = k - 4 * rq, row = 2 + (j >> 1);
+                *reinterpret_cast<float4*>(base + row * rowPitch + ((j & 1) ? rowPitch - 4 : 0)) = z;
+            }
         }
     }
 }
@@ -747,8 +746,7 @@ static int correlate_impl(bool fast, const float* fix, const float* mov, int C, 
         CA_CHECK_LAUNCH("correlate/pad");
         // zero the halo rows / pad columns of the chunk buffer once; the raw kernels only ever write interiors
         const int64_t nslices = (int64_t)p.G * p.S * (p.r1 - p.r0);
-        CA_LAUNCH(k_zero_raw_halo, dim3((unsigned)ca_min((int)ca_divup(nslices * (4 * (p.rl.rowPitch / 4) + 2 * w), 256), 148 * 16)), dim3(256), 0, st,
-                  raw, nslices, w, p.rl.rowPitch);
+        CA_LAUNCH(k_zero_raw_halo, dim3((unsigned)(nslices < 148 * 32 ? nslices : 148 * 32)), dim3(128), 0, st, raw, nslices, w, p.rl.rowPitch);
         CA_CHECK_LAUNCH("correlate/zero_halo");
     }
 #ifndef CA_EMU
