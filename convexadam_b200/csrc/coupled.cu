@@ -325,13 +325,27 @@ static __device__ __forceinline__ float box_dist(const float4& lo, const float4&
 }
 
 // bounding boxes of the displacement vectors of every block of S labels and every slab of S blocks:
-// boxes = [blo (B) | bhi (B) | slo (S) | shi (S)] float4.  One CTA; the mesh is a per-call constant.
+// boxes = [blo (B) | bhi (B) | slo (S) | shi (S) | axis (S) | range lo, hi | flag] float4.  One CTA; the mesh is a per-call constant.
+// axis[k] = (mesh[0, kH=k], mesh[1, kW=k], mesh[2, kD=k]); flag.x = 1.0 when the mesh is the separable grid those
+// tables describe (mesh[c, l] depends only on the c-th index of l, bit for bit) -- disp_mesh_t of MIND.py:127 is.
 __global__ void __launch_bounds__(256) k_mesh_boxes(const float* __restrict__ mesh, int L, int S, float4* __restrict__ boxes) {
     const int B = S * S;
     float4* blo = boxes;
     float4* bhi = blo + B;
     float4* slo = bhi + B;
     float4* shi = slo + S;
+    float4* axis = shi + S;
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    int bad = 0;
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        const int kH = l % S, kW = (l / S) % S, kD = l / B;
+        bad |= __float_as_uint(mesh[l]) != __float_as_uint(mesh[kH]);
+        bad |= __float_as_uint(mesh[L + l]) != __float_as_uint(mesh[L + kW * S]);
+        bad |= __float_as_uint(mesh[2 * L + l]) != __float_as_uint(mesh[2 * L + kD * B]);
+    }
+    if (bad) s_bad = 1;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         float4 lo = make_float4(mesh[b * S], mesh[L + b * S], mesh[2 * L + b * S], 0.f), hi = lo;
         for (int k = 1; k < S; ++k) {
@@ -351,6 +365,17 @@ __global__ void __launch_bounds__(256) k_mesh_boxes(const float* __restrict__ me
         }
         slo[sl] = lo; shi[sl] = hi;
     }
+    for (int k = threadIdx.x; k < S; k += blockDim.x) axis[k] = make_float4(mesh[k], mesh[L + k * S], mesh[2 * L + k * B], 0.f);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float4 lo = axis[0], hi = axis[0];
+        for (int k = 1; k < S; ++k) {
+            lo.x = fminf(lo.x, axis[k].x); lo.y = fminf(lo.y, axis[k].y); lo.z = fminf(lo.z, axis[k].z);
+            hi.x = fmaxf(hi.x, axis[k].x); hi.y = fmaxf(hi.y, axis[k].y); hi.z = fmaxf(hi.z, axis[k].z);
+        }
+        axis[S] = lo; axis[S + 1] = hi;
+        axis[S + 2] = make_float4(s_bad ? 0.f : 1.f, 0.f, 0.f, 0.f);
+    }
 }
 
 // one coupled-convex pass that reads the slab minima (S*n floats), the block minima of the slabs that survive, and the
@@ -368,6 +393,7 @@ __global__ void __launch_bounds__(128, 5) k_cost_argmin_pruned(const float* __re
                                                             int* __restrict__ nflagged) {
     CA_DYN_SMEM(float4, sbox);
     const int B = S * S;
+    if (boxes[2 * B + 3 * S + 2].x != 0.f) return;       // separable mesh: k_cost_argmin_sep does this pass
     for (int i = threadIdx.x; i < 2 * B + 2 * S; i += blockDim.x) sbox[i] = boxes[i];
     __syncthreads();
     const float4* blo = sbox;
@@ -496,6 +522,160 @@ __global__ void __launch_bounds__(128, 5) k_cost_argmin_pruned(const float* __re
     }
 }
 
+// The same pass for the separable displacement grid (the mesh of MIND.py:127): mesh[0,l], mesh[1,l], mesh[2,l] depend
+// only on kH, kW, kD, so the squared distances split into per-axis terms that are computed once per slab (kD), once per
+// block (kW) and once per label (kH) -- in the reference's rounded operations, so every cost and every bound is the
+// value the generic kernel computes, bit for bit, at less than half the instructions.
+template <int VEC, int S, bool CERT>
+__global__ void __launch_bounds__(128, 5) k_cost_argmin_sep(const float* __restrict__ ssd, const float* __restrict__ bmin,
+                                                            const float* __restrict__ smin, int64_t n, const float4* __restrict__ boxes,
+                                                            const float* __restrict__ soft, float coeff, int row_len,
+                                                            const unsigned long long* __restrict__ prev,
+                                                            unsigned long long* __restrict__ keys, int* __restrict__ flagged,
+                                                            int* __restrict__ nflagged) {
+    __shared__ float4 sax[S + 2];
+    const int B = S * S;
+    const float4* tab = boxes + 2 * B + 2 * S;
+    if (tab[S + 2].x == 0.f) return;                       // not separable: k_cost_argmin_pruned does this pass
+    for (int i = threadIdx.x; i < S + 2; i += blockDim.x) sax[i] = tab[i];
+    __syncthreads();
+    int64_t v0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (VEC == 4 && row_len > 0) {
+        const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const int64_t warp = gt >> 5;
+        const int lane = (int)(gt & 31);
+        const int tpr = row_len / 32;
+        v0 = ((warp / tpr) * 4 + (lane >> 3)) * row_len + (warp % tpr) * 32 + (lane & 7) * 4;
+    }
+    if (v0 >= n) return;
+    float s0[VEC], s1[VEC], s2[VEC], best[VEC], U[VEC], second[VEC], r01[VEC];
+    int bl[VEC];
+    const float4 rlo = sax[S], rhi = sax[S + 1];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        best[i] = INFINITY;
+        second[i] = INFINITY;
+        bl[i] = 0;
+        s0[i] = soft[v0 + i]; s1[i] = soft[n + v0 + i]; s2[i] = soft[2 * n + v0 + i];
+        // squared distance to the H and W ranges of the grid: the first two terms of every slab's bound
+        const float e0 = fmaxf(fmaxf(__fsub_rn(rlo.x, s0[i]), __fsub_rn(s0[i], rhi.x)), 0.f);
+        const float e1 = fmaxf(fmaxf(__fsub_rn(rlo.y, s1[i]), __fsub_rn(s1[i], rhi.y)), 0.f);
+        r01[i] = __fadd_rn(__fmul_rn(e0, e0), __fmul_rn(e1, e1));
+    }
+    // The bound U: the exact cost, under the new soft field and coefficient, of (a) the previous selection and (b) the
+    // label next to soft(x).  Any label gives a valid bound.
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        int cand[2];
+        cand[0] = (int)(unsigned)(prev[v0 + i] & 0xffffffffull);
+        {
+            const float hwf = 0.5f * (float)(S - 1);
+            const int kH = ca_clamp((int)rintf(s0[i] + hwf), 0, S - 1), kW = ca_clamp((int)rintf(s1[i] + hwf), 0, S - 1),
+                      kD = ca_clamp((int)rintf(s2[i] + hwf), 0, S - 1);
+            cand[1] = (kD * S + kW) * S + kH;
+        }
+        U[i] = INFINITY;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int r = cand[t];
+            const float d0 = __fsub_rn(sax[r % S].x, s0[i]), d1 = __fsub_rn(sax[(r / S) % S].y, s1[i]), d2 = __fsub_rn(sax[r / B].z, s2[i]);
+            const float dist = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+            U[i] = fminf(U[i], __fadd_rn(__ldg(ssd + (int64_t)r * n + v0 + i), __fmul_rn(coeff, dist)));
+        }
+        if (CERT) U[i] = ca_band_hi(U[i]);
+    }
+    // level 1: which slabs can hold the argmin (S independent loads, no branches)
+    unsigned slab_mask = 0;
+#pragma unroll
+    for (int sl = 0; sl < S; ++sl) {
+        float sm[VEC];
+        if (VEC == 4) {
+            const float4 b4 = ca_ld_stream4(reinterpret_cast<const float4*>(smin + (int64_t)sl * n + v0));
+            sm[0] = b4.x; sm[1 % VEC] = b4.y; sm[2 % VEC] = b4.z; sm[3 % VEC] = b4.w;
+        } else {
+            sm[0] = ca_ld_stream1(smin + (int64_t)sl * n + v0);
+        }
+        const float a2 = sax[sl].z;
+        bool need = false;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float d2 = __fsub_rn(a2, s2[i]);
+            need = need || !(__fadd_rn(sm[i], __fmul_rn(coeff, __fadd_rn(r01[i], __fmul_rn(d2, d2)))) > U[i]);
+        }
+        slab_mask |= need ? (1u << sl) : 0u;
+    }
+    const float* sp = ssd + v0;
+    for (int sl = 0; sl < S; ++sl) {
+        if (!((slab_mask >> sl) & 1u)) continue;
+        float q2[VEC], e0q[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float d2 = __fsub_rn(sax[sl].z, s2[i]);
+            q2[i] = __fmul_rn(d2, d2);
+            const float e0 = fmaxf(fmaxf(__fsub_rn(rlo.x, s0[i]), __fsub_rn(s0[i], rhi.x)), 0.f);
+            e0q[i] = __fmul_rn(e0, e0);
+        }
+        // level 2: the blocks of this slab
+        for (int bb = 0; bb < S; bb += 4) {
+            float bmv[4][VEC];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int b = sl * S + ca_min(bb + u, S - 1);
+                if (VEC == 4) {
+                    const float4 b4 = ca_ld_stream4(reinterpret_cast<const float4*>(bmin + (int64_t)b * n + v0));
+                    bmv[u][0] = b4.x; bmv[u][1 % VEC] = b4.y; bmv[u][2 % VEC] = b4.z; bmv[u][3 % VEC] = b4.w;
+                } else {
+                    bmv[u][0] = ca_ld_stream1(bmin + (int64_t)b * n + v0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (bb + u >= S) break;
+                const int b = sl * S + bb + u;
+                const float a1 = sax[bb + u].y;
+                float q1[VEC];
+                bool need = false;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const float d1 = __fsub_rn(a1, s1[i]);
+                    q1[i] = __fmul_rn(d1, d1);
+                    need = need || !(__fadd_rn(bmv[u][i], __fmul_rn(coeff, __fadd_rn(__fadd_rn(e0q[i], q1[i]), q2[i]))) > U[i]);
+                }
+                if (!need) continue;
+                float cv[S][VEC];                 // the S rows of the block: independent loads, all in flight together
+#pragma unroll
+                for (int k = 0; k < S; ++k) {
+                    const int l = b * S + k;
+                    if (VEC == 4) {
+                        const float4 c4 = ca_ld_stream4(reinterpret_cast<const float4*>(sp + (int64_t)l * n));
+                        cv[k][0] = c4.x; cv[k][1 % VEC] = c4.y; cv[k][2 % VEC] = c4.z; cv[k][3 % VEC] = c4.w;
+                    } else {
+                        cv[k][0] = ca_ld_stream1(sp + (int64_t)l * n);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < S; ++k) {
+                    const int l = b * S + k;
+                    const float a0 = sax[k].x;
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        const float d0 = __fsub_rn(a0, s0[i]);
+                        const float dist = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), q1[i]), q2[i]);
+                        const float cost = __fadd_rn(cv[k][i], __fmul_rn(coeff, dist));
+                        if (CERT) second[i] = fminf(second[i], fmaxf(cost, best[i]));
+                        if (cost < best[i]) { best[i] = cost; bl[i] = l; }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        keys[v0 + i] = pack_key(best[i], bl[i]);
+        if (CERT && best[i] > 0.f && second[i] <= ca_band_hi(best[i])) flagged[atomicAdd(nflagged, 1)] = (int)(v0 + i);
+    }
+}
+
 static inline unsigned small_grid(int64_t n) {
     int64_t b = ca_divup(n, 256);
     if (b > 148 * 16) b = 148 * 16;
@@ -565,7 +745,7 @@ int ca_launch_blockmin_argmin(const float* ssd, int64_t n, int S, float* bmin, u
 static float4* cc_boxes_of(float* bmin, int64_t n, int S) {
     return (float4*)(((uintptr_t)(bmin + (int64_t)(S * S + S) * n) + 255) & ~(uintptr_t)255);
 }
-static size_t cc_bmin_bytes(int64_t n, int S) { return ((size_t)S * S + S) * n * 4 + 256 + (size_t)(2 * S * S + 2 * S) * 16; }
+static size_t cc_bmin_bytes(int64_t n, int S) { return ((size_t)S * S + S) * n * 4 + 256 + (size_t)(2 * S * S + 3 * S + 3) * 16; }
 
 int ca_launch_mesh_boxes(const float* mesh, int S, float4* boxes, cudaStream_t st) {
     CA_LAUNCH(k_mesh_boxes, dim3(1), dim3(256), 0, st, mesh, S * S * S, S, boxes);
@@ -600,6 +780,20 @@ int ca_launch_cost_argmin_pruned(const float* ssd, const float* bmin, int64_t n,
     }
 #undef CA_PRUNED
 #undef CA_PRUNED_K
+#define CA_SEP_K(SS, VV, CC) { auto k = k_cost_argmin_sep<VV, SS, CC>; CA_LAUNCH(k, dim3(gx), dim3(128), 0, st, ssd, bmin, smin, n, boxes, soft, coeff, row_len, keys, keys, flagged, nflagged); }
+#define CA_SEP(SS)                                              \
+    case SS:                                                    \
+        if (vec == 4 && cert) CA_SEP_K(SS, 4, true)             \
+        else if (vec == 4) CA_SEP_K(SS, 4, false)               \
+        else if (cert) CA_SEP_K(SS, 1, true)                    \
+        else CA_SEP_K(SS, 1, false)                             \
+        break;
+    switch (S) {      // the kernel for a separable mesh; exactly one of the two does the work (flag written by k_mesh_boxes)
+        CA_SEP(3) CA_SEP(5) CA_SEP(7) CA_SEP(9) CA_SEP(11) CA_SEP(13) CA_SEP(15) CA_SEP(17)
+        default: break;
+    }
+#undef CA_SEP
+#undef CA_SEP_K
     ca_timing_end(tm, st);
     CA_CHECK_LAUNCH("cost_argmin_pruned");
     return CA_OK;
@@ -747,7 +941,7 @@ __global__ void __launch_bounds__(256) k_soft_from_label_window(const int64_t* _
     }
 }
 
-extern "C" size_t ca_cc_select_workspace_bytes(int64_t n) { return (size_t)n * 8 + 256 + (2 * 17 * 17 + 2 * 17) * 16 + 256; }
+extern "C" size_t ca_cc_select_workspace_bytes(int64_t n) { return (size_t)n * 8 + 256 + (2 * 17 * 17 + 3 * 17 + 3) * 16 + 256; }
 
 // block minima (S*S, n) of a slab's cost volume and, when argmin != NULL, its plain argmin (utils.py:87) in the same pass
 extern "C" int ca_cc_blockmin(const float* ssd, int64_t n, int disp_hw, float* bmin, int64_t* argmin, void* workspace,

@@ -91,6 +91,12 @@ def check_coupled(lib, device, C=12, h=6, w=7, d=8, hw=2):
     soft, sel = lib.coupled_convex(T(ssd_o, device), T(am_o, device, torch.int64), T(mesh, device), hw, want_sel=True)
     assert (N(sel) == sel_o[1:]).all(), "coupled_convex per-pass argmin"
     assert_bits_equal(N(soft), soft_o, "coupled_convex soft")
+    # a mesh that is NOT the separable grid (jittered vectors): the generic selection kernel takes over
+    mesh_j = (mesh + r.uniform(-0.2, 0.2, mesh.shape)).astype(np.float32)
+    soft_j, sel_j = orc.coupled_convex(ssd_o, am_o, mesh_j, want_sel=True)
+    soft, sel = lib.coupled_convex(T(ssd_o, device), T(am_o, device, torch.int64), T(mesh_j, device), hw, want_sel=True)
+    assert (N(sel) == sel_j[1:]).all(), "coupled_convex per-pass argmin (non-separable mesh)"
+    assert_bits_equal(N(soft), soft_j, "coupled_convex soft (non-separable mesh)")
     # ragged voxel count (scalar path of the streaming kernel)
     h2, w2, d2 = 3, 5, 7
     fix = r.rand(C, h2, w2, d2).astype(np.float32)
