@@ -50,6 +50,7 @@ _SIGS = {
     "ca_adam_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "ca_adam_run": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ca_pack_field": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "ca_apply_convex": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)
 ABI_VERSION = 1
@@ -387,6 +388,21 @@ class Lib:
         if out is None:
             out = torch.empty((H, W, D, 3), dtype=torch.float64, device=field.device)
         self._chk(self.dll.ca_pack_field(self._p(field), H, W, D, int(round_half), self._p(out), self._stream(field)))
+        return out
+
+
+    def apply_convex(self, disp, moving):
+        """moving (H,W,D) f32/f64 warped by disp (H,W,D,3) f64 (apply_convex.py:13-24)."""
+        disp = self._t(disp, torch.float64)
+        if moving.dtype not in (torch.float32, torch.float64):
+            raise TypeError("apply_convex: moving must be float32 or float64")
+        moving = self._t(moving, moving.dtype)
+        H, W, D = moving.shape
+        if tuple(disp.shape) != (H, W, D, 3):
+            raise ValueError("apply_convex: disp must be (H,W,D,3) matching moving")
+        out = torch.empty_like(moving)
+        self._chk(self.dll.ca_apply_convex(self._p(disp), self._p(moving), int(moving.dtype == torch.float64), H, W, D, self._p(out),
+                                          self._stream(moving)))
         return out
 
 

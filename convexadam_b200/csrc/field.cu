@@ -224,3 +224,48 @@ extern "C" int ca_pack_field(const float* field, int H, int W, int D, int round_
     CA_CHECK_LAUNCH("pack_field");
     return CA_OK;
 }
+
+
+// ---- apply_convex (reference src/convexAdam/apply_convex.py:13-24) -----------------------------------------------------
+// warped = scipy.ndimage.map_coordinates(moving, disp.transpose(3,0,1,2) + identity, order=1): linear interpolation in
+// float64 at x + disp(x); a point with any coordinate outside [0, size-1] gets cval = 0 (mode='constant': no
+// interpolation beyond the edges), the upper neighbour index is clamped (its weight is then 0).  Output in the dtype of
+// `moving`.  disp: (H,W,D,3) float64, the layout convex_adam_pt returns.
+template <typename T>
+__global__ void __launch_bounds__(256) k_apply_convex(const double* __restrict__ disp, const T* __restrict__ moving, int H, int W,
+                                                      int D, T* __restrict__ out) {
+    const int64_t n = (int64_t)H * W * D;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+        const int z = (int)(o % D), y = (int)((o / D) % W), x = (int)(o / ((int64_t)D * W));
+        const double cx = disp[3 * o] + (double)x, cy = disp[3 * o + 1] + (double)y, cz = disp[3 * o + 2] + (double)z;
+        double v = 0.0;
+        if (!(cx < 0.0 || cx > (double)(H - 1) || cy < 0.0 || cy > (double)(W - 1) || cz < 0.0 || cz > (double)(D - 1))) {
+            const double fx = floor(cx), fy = floor(cy), fz = floor(cz);
+            const double tx = cx - fx, ty = cy - fy, tz = cz - fz;
+            const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+            const int x1 = ca_min(x0 + 1, H - 1), y1 = ca_min(y0 + 1, W - 1), z1 = ca_min(z0 + 1, D - 1);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int xi = (c & 4) ? x1 : x0, yi = (c & 2) ? y1 : y0, zi = (c & 1) ? z1 : z0;
+                const double w = ((c & 4) ? tx : 1.0 - tx) * ((c & 2) ? ty : 1.0 - ty) * ((c & 1) ? tz : 1.0 - tz);
+                v += (double)moving[((int64_t)xi * W + yi) * D + zi] * w;
+            }
+        }
+        out[o] = (T)v;
+    }
+}
+
+extern "C" int ca_apply_convex(const double* disp, const void* moving, int moving_is_f64, int H, int W, int D, void* warped,
+                               ca_stream_t stream) {
+    CA_CHECK_ARG(disp && moving && warped && H > 0 && W > 0 && D > 0, "apply_convex: bad argument");
+    const int64_t n = (int64_t)H * W * D;
+    if (moving_is_f64) {
+        auto k = k_apply_convex<double>;
+        CA_LAUNCH(k, dim3(field_grid(n)), dim3(256), 0, (cudaStream_t)stream, disp, (const double*)moving, H, W, D, (double*)warped);
+    } else {
+        auto k = k_apply_convex<float>;
+        CA_LAUNCH(k, dim3(field_grid(n)), dim3(256), 0, (cudaStream_t)stream, disp, (const float*)moving, H, W, D, (float*)warped);
+    }
+    CA_CHECK_LAUNCH("apply_convex");
+    return CA_OK;
+}

@@ -15,6 +15,7 @@
  *   ca_trilinear           F.interpolate(mode='trilinear')   convex_adam_MIND.py:141,153,182
  *   ca_adam_run            the Adam instance-optimisation    convex_adam_MIND.py:147-181
  *   ca_pack_field          dtype rounding + np.stack(...,3)  convex_adam_MIND.py:198-202
+ *   ca_apply_convex        map_coordinates warp              apply_convex.py:13-24
  *
  * Conventions: every pointer is a DEVICE pointer to a contiguous array owned by the caller;
  * no function allocates, none synchronises, all work is enqueued on `stream` (a cudaStream_t); the functions are
@@ -197,6 +198,13 @@ CA_API int ca_adam_run_window(const float* fix, const float* mov, int C, int ha,
  * field (3,H,W,D) f32 -> out (H,W,D,3) f64; round_half != 0 rounds every value through IEEE half first
  * (the reference's `.to(dtype)` when dtype=float16). */
 CA_API int ca_pack_field(const float* field, int H, int W, int D, int round_half, double* out, ca_stream_t stream);
+
+/* ---- apply_convex (apply_convex.py:13-24): the warp either side of the path --------------------------------------
+ * warped(x) = moving interpolated linearly (float64 arithmetic) at x + disp(x); 0 where any coordinate leaves
+ * [0, size-1] (scipy.ndimage.map_coordinates, order=1, mode='constant').  disp (H,W,D,3) f64 -- the array
+ * convex_adam_pt returns; moving, warped (H,W,D) f32 or f64 (moving_is_f64). */
+CA_API int ca_apply_convex(const double* disp, const void* moving, int moving_is_f64, int H, int W, int D, void* warped,
+                    ca_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -256,3 +256,32 @@ def field_from_features(ff, fm, shape, lambda_weight, grid_sp, disp_hw, selected
                 disp_hr = avgpool3d(disp_hr, k, 1, k // 2)
         st.update(adam_state=state, u=u)
     return np.stack([disp_hr[0], disp_hr[1], disp_hr[2]], 3).astype(np.float64)
+
+
+def apply_convex(disp, moving):
+    """apply_convex (reference apply_convex.py:13-24) = scipy.ndimage.map_coordinates(moving, disp^T + identity, order=1,
+    mode='constant', cval=0): float64 linear interpolation at x + disp(x); 0 where a coordinate leaves [0, size-1]; the
+    upper neighbour index clamped.  scipy (third-party, where the arithmetic lives) is restated here in numpy;
+    tests/test_oracle_golden.py pins it against scipy itself."""
+    moving = np.asarray(moving)
+    disp = np.asarray(disp, np.float64)
+    H, W, D = moving.shape
+    ident = np.meshgrid(np.arange(H), np.arange(W), np.arange(D), indexing="ij")
+    c = [disp[..., k] + ident[k] for k in range(3)]
+    inside = np.ones(moving.shape, bool)
+    for k, n in enumerate((H, W, D)):
+        inside &= ~((c[k] < 0) | (c[k] > n - 1))
+    f = [np.floor(np.where(inside, c[k], 0.0)) for k in range(3)]
+    t = [np.where(inside, c[k], 0.0) - f[k] for k in range(3)]
+    i0 = [f[k].astype(np.int64) for k in range(3)]
+    i1 = [np.minimum(i0[k] + 1, n - 1) for k, n in enumerate((H, W, D))]
+    m64 = moving.astype(np.float64)
+    v = np.zeros(moving.shape, np.float64)
+    for corner in range(8):
+        sel = [(corner >> 2) & 1, (corner >> 1) & 1, corner & 1]
+        idx = tuple(i1[k] if sel[k] else i0[k] for k in range(3))
+        w = np.ones(moving.shape, np.float64)
+        w = (t[0] if sel[0] else 1.0 - t[0]) * (t[1] if sel[1] else 1.0 - t[1]) * (t[2] if sel[2] else 1.0 - t[2])
+        v += m64[idx] * w
+    out_dtype = moving.dtype if moving.dtype in (np.float32, np.float64) else np.float64
+    return np.where(inside, v, 0.0).astype(out_dtype)

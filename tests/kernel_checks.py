@@ -333,3 +333,25 @@ def check_golden_convex_stage(lib, device, g, disp_hw):
     b = lib.field_affine(soft_, flip=True, div=scale)
     ice, _ = lib.inverse_consistency(a, b, 15)
     assert_bits_equal(N(ice), g["ice"], "inverse-consistent field vs reference golden")
+
+
+def check_apply_convex(lib, device, shape=(9, 11, 13)):
+    """ca_apply_convex vs the oracle's restatement of scipy.ndimage.map_coordinates(order=1): float32 and float64 images,
+    points inside, on the faces, and outside the volume."""
+    r = rng(90)
+    H, W, D = shape
+    disp = (r.randn(H, W, D, 3) * 2.5).astype(np.float64)
+    disp[0, 0, 0] = 0.0                                        # exactly on a corner
+    disp[-1, -1, -1] = 0.0                                     # exactly on the far corner (upper index clamped)
+    disp[1, 1, 1] = (-1.0, 0.0, 0.0)                           # lands exactly on the face x = 0
+    disp[2, 2, 2] = (-2.0 - 1e-12, 0.0, 0.0)                   # a hair outside -> 0
+    for dt, tdt in ((np.float32, torch.float32), (np.float64, torch.float64)):
+        mov = (r.rand(H, W, D) * 100).astype(dt)
+        want = orc.apply_convex(disp, mov)
+        got = N(lib.apply_convex(T(disp, device, torch.float64), T(mov, device, tdt)))
+        assert got.dtype == dt
+        # float64 accumulation in a different corner order: a few ulp of double; exact after rounding to float32
+        assert np.abs(got.astype(np.float64) - want.astype(np.float64)).max() <= (0.0 if dt == np.float32 else 1e-12 * 100), dt
+    ident = np.zeros((H, W, D, 3))
+    mov = r.rand(H, W, D).astype(np.float32)
+    assert (N(lib.apply_convex(T(ident, device, torch.float64), T(mov, device))) == mov).all(), "zero field must return the image"

@@ -50,6 +50,31 @@ def test_coupled(lib, dev):
     kc.check_coupled(lib, dev, h=6, w=7, d=9, hw=6)
 
 
+def test_apply_convex(lib, dev):
+    kc.check_apply_convex(lib, dev, shape=(20, 17, 23))
+
+
+def test_apply_convex_matches_scipy_and_api(lib, dev):
+    """The public drop-in (convexadam_b200.apply_convex.apply_convex) against scipy.ndimage.map_coordinates itself -- the
+    call the reference makes (apply_convex.py:23) -- on a 96x80x128 volume."""
+    from scipy.ndimage import map_coordinates
+    from convexadam_b200.apply_convex import apply_convex
+    rs = np.random.RandomState(3)
+    H, W, D = 96, 80, 128
+    mov = (rs.rand(H, W, D) * 1000).astype(np.float32)
+    disp = (rs.randn(H, W, D, 3) * 4).astype(np.float64)
+    ident = np.meshgrid(np.arange(H), np.arange(W), np.arange(D), indexing="ij")
+    # numpy input: validate_image casts to float64 (utils.py:276), so the reference interpolates and returns float64
+    want = map_coordinates(mov.astype(np.float64), disp.transpose(3, 0, 1, 2) + ident, order=1)
+    got = apply_convex(disp, mov)
+    assert got.dtype == want.dtype and got.shape == want.shape
+    assert np.abs(got - want).max() <= 1e-12 * 1000                 # float64 sums in a different corner order
+    # torch float32 input keeps its dtype, as in the reference
+    want32 = map_coordinates(mov, disp.transpose(3, 0, 1, 2) + ident, order=1)
+    got32 = apply_convex(torch.from_numpy(disp), torch.from_numpy(mov))
+    assert got32.dtype == np.float32 and (got32 == want32).mean() > 0.9999 and np.abs(got32 - want32).max() <= 1e-4
+
+
 def test_certified(lib, dev):
     kc.check_certified(lib, dev, cases=((12, 10, 9, 16, 3), (16, 6, 7, 8, 1), (3, 5, 6, 9, 4), (12, 8, 6, 12, 6), (12, 7, 9, 10, 2)))
 

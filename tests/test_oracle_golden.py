@@ -141,3 +141,25 @@ def test_full_path_vs_reference_field(case):
     f = orc.convex_adam_pt(g["fixed"], g["moving"], kw["mind_r"], kw["mind_d"], kw["lambda_weight"], kw["grid_sp"],
                            kw["disp_hw"], niter, kw["smooth"], kw["grid_sp_adam"], True)
     assert np.abs(f[::2, ::2, ::2] - g["field"]).max() <= 1e-3
+
+
+def test_apply_convex_oracle_vs_scipy():
+    """apply_convex.py:23 calls scipy.ndimage.map_coordinates(order=1); the oracle's numpy restatement against scipy
+    itself (the third-party library where the arithmetic lives, present in this image): float32 images exact, float64
+    within a few ulp (corner accumulation order), out-of-volume points zero."""
+    import numpy as np
+    from scipy.ndimage import map_coordinates
+    from oracle import ca_oracle as orc
+    rs = np.random.RandomState(11)
+    H, W, D = 12, 10, 14
+    disp = (rs.randn(H, W, D, 3) * 3).astype(np.float64)
+    disp[0, 0, 0] = 0
+    disp[-1, -1, -1] = 0
+    ident = np.meshgrid(np.arange(H), np.arange(W), np.arange(D), indexing="ij")
+    for dt in (np.float32, np.float64):
+        mov = (rs.rand(H, W, D) * 50).astype(dt)
+        want = map_coordinates(mov, disp.transpose(3, 0, 1, 2) + ident, order=1)
+        got = orc.apply_convex(disp, mov)
+        assert got.dtype == want.dtype
+        assert np.abs(got.astype(np.float64) - want.astype(np.float64)).max() <= (0.0 if dt == np.float32 else 1e-13 * 50)
+    assert (want == 0).any() and (want != 0).any()
