@@ -765,6 +765,7 @@ static int correlate_impl(bool fast, const float* fix, const float* mov, int C, 
         ca_set_error("correlate: row tile needs %zu bytes of shared memory", p.box_smem);
         return CA_ERR_UNSUPPORTED;
     }
+    // (balancing the chunks, 4+3+3+3 kW groups instead of 4+4+4+1, was measured and is slower: 7.99 vs 7.89 ms per direction)
     for (int cs = 0; cs < npairs; cs += p.G) {
         const int g = ca_min(p.G, npairs - cs);
         void* tm = ca_timing_begin(CA_T_RAW, st);
