@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) k_planar_to_cl(const float* __restrict__ 
         }
 }
 
-__global__ void __launch_bounds__(128) k_adam_grad(const float* __restrict__ u, const float4* __restrict__ fixcl,
+__global__ void __launch_bounds__(128, 5) k_adam_grad(const float* __restrict__ u, const float4* __restrict__ fixcl,
                                                    const float4* __restrict__ movcl, int CG, AdamGeom g,
                                                    const float* __restrict__ g0x, const float* __restrict__ g0y,
                                                    const float* __restrict__ g0z, float* __restrict__ gu) {
@@ -114,20 +114,12 @@ __global__ void __launch_bounds__(128) k_adam_grad(const float* __restrict__ u, 
     const float xz[4] = {sx * sz, tx * sz, sx * tz, tx * tz};
     const float xy[4] = {sx * sy, tx * sy, sx * ty, tx * ty};
     float gix = 0.f, giy = 0.f, giz = 0.f;
-    // the 8-corner gather of channel group cg+1 is in flight while group cg is reduced
-    float4 val[8], nval[8], f, nf;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) nval[t] = inb[t] ? __ldg(movcl + off[t]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    nf = __ldg(fixcl + of * CG);
+    // (an explicit register double buffer of the next group's gather was measured slower than one more resident CTA)
+    float4 val[8], f;
     for (int cg = 0; cg < CG; ++cg) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) val[t] = nval[t];
-        f = nf;
-        if (cg + 1 < CG) {
-#pragma unroll
-            for (int t = 0; t < 8; ++t) nval[t] = inb[t] ? __ldg(movcl + off[t] + cg + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-            nf = __ldg(fixcl + of * CG + cg + 1);
-        }
+        for (int t = 0; t < 8; ++t) val[t] = inb[t] ? __ldg(movcl + off[t] + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+        f = __ldg(fixcl + of * CG + cg);
         float4 smp = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
