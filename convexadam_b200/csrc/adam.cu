@@ -309,7 +309,7 @@ static inline unsigned adam_grid(int64_t n, int block) {
     return (unsigned)(b < 1 ? 1 : b);
 }
 
-#define CA_BOX3_LX 16
+#define CA_BOX3_LX 12
 #define CA_BOX3_SMEM (96 * 1024)
 
 // rows per CTA of k_box3_p such that both shared-memory buffers fit; 0: the plane rows are too long

@@ -11,7 +11,12 @@ from convexadam_b200._native import get_lib  # noqa: E402
 from convexadam_b200.synth import make_pair  # noqa: E402
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
-lib = get_lib()
+if "--lib" in sys.argv:          # a variant build of the library (tuning): python tools/time_corr.py 5 --lib path/to/lib.so
+    from convexadam_b200._native import Lib
+    lib = Lib(sys.argv[sys.argv.index("--lib") + 1])
+    print("library:", lib.path)
+else:
+    lib = get_lib()
 dev = torch.device("cuda:0")
 f, m = make_pair((192, 160, 256), seed=0)
 fs, _ = lib.mindssc_pooled(f.to(dev), 1, 2, 2)
