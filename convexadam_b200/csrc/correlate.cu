@@ -741,7 +741,9 @@ static int correlate_impl(bool fast, const float* fix, const float* mov, int C, 
     const int S = p.S, npairs = S * S;
     {
         const int64_t tf = (int64_t)C * h * w * p.dF, tm = (int64_t)C * (h + 2 * disp_hw) * (w + 2 * disp_hw) * p.dP;
-        CA_LAUNCH(k_pad_features, dim3((unsigned)ca_min((int)ca_divup(tf, 256), 148 * 16)), dim3(256), 0, st, fix, C, h, w, d, 0, p.dF, fixp);
+        // the fixed features are used in place when their rows already have the kernels' pitch and alignment
+        if (p.dF == d && (((uintptr_t)fix) & 15) == 0) fixp = const_cast<float*>(fix);
+        else CA_LAUNCH(k_pad_features, dim3((unsigned)ca_min((int)ca_divup(tf, 256), 148 * 16)), dim3(256), 0, st, fix, C, h, w, d, 0, p.dF, fixp);
         CA_LAUNCH(k_pad_features, dim3((unsigned)ca_min((int)ca_divup(tm, 256), 148 * 16)), dim3(256), 0, st, mov, C, h, w, d, disp_hw, p.dP, movp);
         CA_CHECK_LAUNCH("correlate/pad");
         // zero the halo rows / pad columns of the chunk buffer once; the raw kernels only ever write interiors

@@ -163,18 +163,40 @@ __global__ void __launch_bounds__(128) k_mind_phase_b(const float* __restrict__ 
     float acc[12];
 #pragma unroll
     for (int c = 0; c < 12; ++c) acc[c] = 0.f;
-    for (int a = 0; a < gs; ++a)
-        for (int b = 0; b < gs; ++b)
-            for (int e = 0; e < gs; ++e) {
-                const int64_t q = ((int64_t)(x * gs + a) * W + (y * gs + b)) * D + (z * gs + e);
-                float vv = __ldg(var + q);
-                vv = vv < lo ? lo : (vv > hi ? hi : vv);
+    if (gs == 2 && (D & 1) == 0) {
+        // the common pooling factor: the two voxels along D come as one aligned 64-bit load (coalesced across the warp),
+        // same summation order (a, b, e ascending) as the generic loop below
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int64_t q = ((int64_t)(x * 2 + a) * W + (y * 2 + b)) * D + z * 2;
+                float2 vv = __ldg(reinterpret_cast<const float2*>(var + q));
+                vv.x = vv.x < lo ? lo : (vv.x > hi ? hi : vv.x);
+                vv.y = vv.y < lo ? lo : (vv.y > hi ? hi : vv.y);
+                float2 mm[12];
+#pragma unroll
+                for (int c = 0; c < 12; ++c) mm[c] = __ldg(reinterpret_cast<const float2*>(mind + c * V + q));
 #pragma unroll
                 for (int c = 0; c < 12; ++c) {
-                    const float f = expf(-ca_div(__ldg(mind + c * V + q), vv));
-                    acc[c] = __fadd_rn(acc[c], f);
+                    acc[c] = __fadd_rn(acc[c], expf(-ca_div(mm[c].x, vv.x)));
+                    acc[c] = __fadd_rn(acc[c], expf(-ca_div(mm[c].y, vv.y)));
                 }
             }
+    } else {
+        for (int a = 0; a < gs; ++a)
+            for (int b = 0; b < gs; ++b)
+                for (int e = 0; e < gs; ++e) {
+                    const int64_t q = ((int64_t)(x * gs + a) * W + (y * gs + b)) * D + (z * gs + e);
+                    float vv = __ldg(var + q);
+                    vv = vv < lo ? lo : (vv > hi ? hi : vv);
+#pragma unroll
+                    for (int c = 0; c < 12; ++c) {
+                        const float f = expf(-ca_div(__ldg(mind + c * V + q), vv));
+                        acc[c] = __fadd_rn(acc[c], f);
+                    }
+                }
+    }
     const int64_t o = ((int64_t)x * w + y) * d + z;
 #pragma unroll
     for (int c = 0; c < 12; ++c) out[c * n + o] = (gs == 1) ? acc[c] : ca_div(acc[c], cnt);

@@ -128,3 +128,17 @@ def test_full_size_certified_mode_equals_exact_mode():
     c = pipeline.register_mind(fixed.to(dev), moving.to(dev), pipeline.Params(mode="certified", overlap="1", **kw))
     torch.cuda.synchronize()
     assert bool((a.view(torch.int32) == c.view(torch.int32)).all())
+
+
+def test_settings_sweep_equals_individual_calls():
+    """convexadam_b200.search.convex_fields (features computed once) == one convex_adam_pt call per
+    setting with lambda_weight=0, bit for bit."""
+    from convexadam_b200.search import convex_fields
+    from convexadam_b200.synth import make_pair
+    fixed, moving = make_pair((48, 42, 54), seed=4, disp_scale=0.1)
+    settings = [(2, 3), (3, 2), (2, 2), (6, 4)]
+    got = convex_fields(fixed, moving, settings)
+    for (gs, hw), g in zip(settings, got):
+        want = api()(fixed, moving, mind_r=1, mind_d=2, lambda_weight=0, grid_sp=gs, disp_hw=hw, selected_niter=1,
+                     selected_smooth=0, grid_sp_adam=2, ic=True, dtype=torch.float32)
+        assert g.shape == want.shape and (g == want).all(), (gs, hw)
