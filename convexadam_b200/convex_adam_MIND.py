@@ -62,6 +62,16 @@ def extract_features(img_fixed, img_moving, mind_r, mind_d, use_mask, mask_fixed
     return ff, fm
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_stream(device):
+    key = str(device)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device)
+    return _COPY_STREAMS[key]
+
+
 def convex_adam_pt(
     img_fixed,
     img_moving,
@@ -104,7 +114,18 @@ def convex_adam_pt(
     t0 = time.time()
     with torch.cuda.device(device):
         fixed_dev = img_fixed.to(device, non_blocking=True).contiguous()
-        moving_dev = img_moving.to(device, non_blocking=True).contiguous()
+        moving_ready = None
+        if img_moving.is_cuda or use_mask or (split_over is not None and split_over is not False):
+            moving_dev = img_moving.to(device, non_blocking=True).contiguous()
+        else:
+            # the moving image travels on a side stream while the fixed image's descriptors are computed
+            main = torch.cuda.current_stream(device)
+            side = _copy_stream(device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                moving_dev = img_moving.to(device, non_blocking=True).contiguous()
+            moving_ready = side.record_event()
+            moving_dev.record_stream(main)
         if use_mask:
             import nibabel as nib
             mask_fixed = torch.from_numpy(nib.load(path_fixed_mask).get_fdata()).float()
@@ -115,7 +136,7 @@ def convex_adam_pt(
             from . import slab
             disp = slab.register_mind_slab(fixed_dev, moving_dev, prm, lib, None if split_over is True else split_over)
         else:
-            disp = pipeline.register_mind(fixed_dev, moving_dev, prm, lib)
+            disp = pipeline.register_mind(fixed_dev, moving_dev, prm, lib, moving_ready=moving_ready)
         packed = lib.pack_field(disp, round_half=(dtype == torch.float16))
         host = torch.empty(packed.shape, dtype=torch.float64, pin_memory=True)
         host.copy_(packed, non_blocking=True)

@@ -184,9 +184,11 @@ def register_features(lib: Lib, fix_s, mov_s, fix_a, mov_a, shape, prm: Params, 
     return disp
 
 
-def register_mind(fixed_dev, moving_dev, prm: Params, lib: Lib = None, ssd_buf=None):
+def register_mind(fixed_dev, moving_dev, prm: Params, lib: Lib = None, ssd_buf=None, moving_ready=None):
     """fixed_dev, moving_dev: (H,W,D) float32 CUDA tensors.  Returns the dense field (3,H',W',D') float32 on the
-    device (voxel units, channel c = displacement along array axis c)."""
+    device (voxel units, channel c = displacement along array axis c).  moving_ready: optional CUDA event after which
+    moving_dev holds its data (its host-to-device copy may still be in flight on another stream while the fixed image's
+    descriptors are computed)."""
     lib = lib or get_lib()
     H, W, D = fixed_dev.shape
     _mark("start")
@@ -194,6 +196,8 @@ def register_mind(fixed_dev, moving_dev, prm: Params, lib: Lib = None, ssd_buf=N
     need_adam = prm.lambda_weight > 0
     gs_b = 0 if (same or not need_adam) else prm.grid_sp_adam
     fix_s, fix_a = lib.mindssc_pooled(fixed_dev, prm.mind_r, prm.mind_d, prm.grid_sp, gs_b)
+    if moving_ready is not None:
+        torch.cuda.current_stream(fixed_dev.device).wait_event(moving_ready)
     mov_s, mov_a = lib.mindssc_pooled(moving_dev, prm.mind_r, prm.mind_d, prm.grid_sp, gs_b)
     if same:
         fix_a, mov_a = fix_s, mov_s
