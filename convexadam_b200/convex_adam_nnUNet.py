@@ -61,7 +61,10 @@ def convex_adam_pt(pred_fixed, pred_moving, lambda_weight=1.25, grid_sp=6, disp_
         w = 10 * weight
     # the reference honours selected_smooth in {3,5} only (nnUNet.py:136-144)
     smooth = selected_smooth if selected_smooth in (3, 5) else 0
-    prm = pipeline.Params(1, 2, lambda_weight, grid_sp, disp_hw, selected_niter, smooth, grid_sp_adam, ic)
+    # one-hot label features give many exactly equal costs: the certified mode would re-decide them one candidate at a
+    # time (same selections, no speed-up there), so this path takes the exact cost volume by default
+    prm = pipeline.Params(1, 2, lambda_weight, grid_sp, disp_hw, selected_niter, smooth, grid_sp_adam, ic,
+                          mode=os.environ.get("CONVEXADAM_B200_MODE", "exact"))
     with torch.cuda.device(dev):
         lf = pred_fixed.reshape(H, W, D).to(dev).contiguous()
         lm = pred_moving.reshape(H, W, D).to(dev).contiguous()
