@@ -48,8 +48,8 @@ __global__ void __launch_bounds__(128, 5) k_adam_grad(const float* __restrict__ 
     const int ha = g.ha, wa = g.wa, da = g.da;
     const int n = g.hl * wa * da;                   // field arrays: window-local indexing
     const int z = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    const int y = (int)blockIdx.y, xl = (int)blockIdx.z, x = xl + g.lo;
-    if (z >= da) return;
+    const int y = (int)(blockIdx.y * blockDim.y + threadIdx.y), xl = (int)(blockIdx.z * blockDim.z + threadIdx.z), x = xl + g.lo;
+    if (z >= da || y >= wa || xl >= g.hl) return;
     const int o = (xl * wa + y) * da + z;
     const int of = (x * wa + y) * da + z;           // feature arrays: whole-grid indexing
     const float u0 = u[o], u1 = u[n + o], u2 = u[2 * n + o];
@@ -417,9 +417,9 @@ extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int
             if ((rc = box(t0, t1)) != CA_OK) return rc;
             if ((rc = box(t1, u_out)) != CA_OK) return rc;
         }
-        const int bx = da >= 128 ? 128 : (da >= 64 ? 64 : 32);
+        const int bx = 32, by = 4, bz = 1;      // 32 x 4 voxels per CTA: neighbouring rows share corner gathers in L1
         void* tmg = ca_timing_begin(CA_T_ADAM_GRAD, st);
-        CA_LAUNCH(k_adam_grad, dim3((unsigned)((da + bx - 1) / bx), (unsigned)wa, (unsigned)hl), dim3(bx), 0, st, u_out, fixcl, movcl, CG,
+        CA_LAUNCH(k_adam_grad, dim3((unsigned)((da + bx - 1) / bx), (unsigned)((wa + by - 1) / by), (unsigned)((hl + bz - 1) / bz)), dim3(bx, by, bz), 0, st, u_out, fixcl, movcl, CG,
                   g, g0x, g0y, g0z, gu);
         ca_timing_end(tmg, st);
         CA_CHECK_LAUNCH("adam_grad");
