@@ -50,3 +50,59 @@ def register_pairs(pairs: Sequence, gather: bool = True, register_fn: Optional[C
         for i, f in part.items():
             results[i] = f
     return results
+
+
+def register_pairs_pipelined(pairs: Sequence, depth: int = 2, device=None, dtype=torch.float32, **kw):
+    """Registers the pairs of THIS process back to back with `depth` of them in flight on as many CUDA streams: the
+    Adam stage of one pair (small latency-bound kernels) shares the GPU with the cost-volume stage of the next (issue-
+    and bandwidth-bound kernels), and the host<->device copies of one pair overlap the compute of another.  The kernels
+    are the ones `convex_adam_pt` runs, each pair on its own stream, so every field is bit-identical to
+    `convex_adam_pt(fixed, moving, dtype=dtype, **kw)`.  pairs: sequence of (fixed, moving) volumes (or callables
+    returning such a tuple).  Returns one (H,W,D,3) float64 array per pair.  MIND path, no masks."""
+    from . import pipeline
+    from ._native import get_lib
+    from .convex_adam_utils import validate_image
+    if depth < 1:
+        raise ValueError("depth must be >= 1")
+    lib = get_lib()
+    dev = torch.device(device if device is not None else "cuda")
+    names = ("mind_r", "mind_d", "lambda_weight", "grid_sp", "disp_hw", "selected_niter", "selected_smooth", "grid_sp_adam", "ic")
+    unknown = set(kw) - set(names)
+    if unknown:
+        raise TypeError(f"unexpected arguments {sorted(unknown)}")
+    prm = pipeline.Params(**{k: kw[k] for k in names if k in kw})
+    results: List[Optional[np.ndarray]] = [None] * len(pairs)
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream(dev)
+        streams = [torch.cuda.Stream(dev) for _ in range(depth)]
+        pending = []                                   # (index, host tensor, event) in issue order
+
+        def collect(upto):
+            while len(pending) > upto:
+                i, host, ev = pending.pop(0)
+                ev.synchronize()
+                results[i] = host.numpy()
+
+        for i in range(len(pairs)):
+            item = pairs[i]() if callable(pairs[i]) else pairs[i]
+            fixed, moving = validate_image(item[0]).float(), validate_image(item[1]).float()
+            st = streams[i % depth]
+            st.wait_stream(main)
+            try:
+                with torch.cuda.stream(st):
+                    fd = fixed.to(dev, non_blocking=True).contiguous()
+                    md = moving.to(dev, non_blocking=True).contiguous()
+                    disp = pipeline.register_mind(fd, md, prm, lib)
+                    packed = lib.pack_field(disp, round_half=(dtype == torch.float16))
+                    host = torch.empty(packed.shape, dtype=torch.float64, pin_memory=True)
+                    host.copy_(packed, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+            except Exception as e:
+                raise RuntimeError(f"registration of pair {i} failed: {e}") from e
+            pending.append((i, host, ev))
+            collect(depth - 1)                         # at most depth pairs enqueued ahead of the host
+        collect(0)
+        for st in streams:
+            main.wait_stream(st)
+    return results

@@ -142,3 +142,15 @@ def test_settings_sweep_equals_individual_calls():
         want = api()(fixed, moving, mind_r=1, mind_d=2, lambda_weight=0, grid_sp=gs, disp_hw=hw, selected_niter=1,
                      selected_smooth=0, grid_sp_adam=2, ic=True, dtype=torch.float32)
         assert g.shape == want.shape and (g == want).all(), (gs, hw)
+
+
+def test_pipelined_batch_equals_individual_calls():
+    """batch.register_pairs_pipelined (two pairs in flight on two streams) == convex_adam_pt per pair, bit for bit."""
+    from convexadam_b200.batch import register_pairs_pipelined
+    from convexadam_b200.synth import make_pair
+    kw = dict(mind_r=1, mind_d=2, lambda_weight=1.25, grid_sp=2, disp_hw=3, selected_niter=6, selected_smooth=0, grid_sp_adam=2, ic=True)
+    pairs = [make_pair((40, 36, 44), seed=s, disp_scale=0.1) for s in range(5)]
+    got = register_pairs_pipelined(pairs, depth=2, **kw)
+    for (f, m), g in zip(pairs, got):
+        want = api()(f, m, dtype=torch.float32, **kw)
+        assert g.dtype == np.float64 and (g == want).all()

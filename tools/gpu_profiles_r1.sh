@@ -3,8 +3,8 @@
 OUT=gpurun_out/${1:-r1final}
 mkdir -p $OUT
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches_bench.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/bench_under_ncu.log 2>&1; echo "list rc=$?"
-for k in k_box12_fast k_raw_ssd_staged k_blockmin_argmin k_cost_argmin_pruned k_cc_fixup; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o $OUT/prof_$k python tools/profile_corr.py --fast --cc > /dev/null 2>&1; echo "$k rc=$?"
+for k in k_box12_fast k_raw_ssd_staged k_blockmin_argmin k_cost_argmin_sep k_cc_fixup; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 0 -c 1 -f -o $OUT/prof_$k python tools/profile_corr.py --fast --cc > /dev/null 2>&1; echo "$k rc=$?"
 done
 for k in k_adam_grad k_box3_h k_box3_p k_mind_phase_a k_mind_phase_b; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o $OUT/prof_$k python tools/profile_pair.py 2 > /dev/null 2>&1; echo "$k rc=$?"
