@@ -52,13 +52,26 @@ def register_pairs(pairs: Sequence, gather: bool = True, register_fn: Optional[C
     return results
 
 
-def register_pairs_pipelined(pairs: Sequence, depth: int = 2, device=None, dtype=torch.float32, **kw):
-    """Registers the pairs of THIS process back to back with `depth` of them in flight on as many CUDA streams: the
-    Adam stage of one pair (small latency-bound kernels) shares the GPU with the cost-volume stage of the next (issue-
-    and bandwidth-bound kernels), and the host<->device copies of one pair overlap the compute of another.  The kernels
-    are the ones `convex_adam_pt` runs, each pair on its own stream, so every field is bit-identical to
-    `convex_adam_pt(fixed, moving, dtype=dtype, **kw)`.  pairs: sequence of (fixed, moving) volumes (or callables
-    returning such a tuple).  Returns one (H,W,D,3) float64 array per pair.  MIND path, no masks."""
+_STREAMS = {}
+
+
+def _pipeline_streams(dev, depth):
+    key = str(dev)
+    have = _STREAMS.setdefault(key, [])
+    while len(have) < depth:
+        have.append(torch.cuda.Stream(dev))        # cached: torch's allocator keeps one memory pool per stream
+    return have[:depth]
+
+
+def iter_register_pipelined(pairs: Sequence, depth: int = 2, device=None, dtype=torch.float32, **kw):
+    """Generator over the fields of `pairs`, in order, with `depth` pairs in flight on as many CUDA streams: the Adam
+    stage of one pair (small latency-bound kernels) shares the GPU with the cost-volume stage of the next, and the
+    host<->device copies of one pair overlap the compute of another.  The kernels are the ones `convex_adam_pt` runs,
+    each pair on its own stream, so every field is bit-identical to `convex_adam_pt(fixed, moving, dtype=dtype, **kw)`.
+    pairs: sequence of (fixed, moving) volumes (or callables returning such a tuple).  Yields (H,W,D,3) float64 arrays
+    that live in pinned host memory (as convex_adam_pt's result does): drop each one when done with it and its buffer is
+    recycled for a later pair -- copying 189 MB per field on the host would cost more than the registration.
+    MIND path, no masks."""
     from . import pipeline
     from ._native import get_lib
     from .convex_adam_utils import validate_image
@@ -71,18 +84,10 @@ def register_pairs_pipelined(pairs: Sequence, depth: int = 2, device=None, dtype
     if unknown:
         raise TypeError(f"unexpected arguments {sorted(unknown)}")
     prm = pipeline.Params(**{k: kw[k] for k in names if k in kw})
-    results: List[Optional[np.ndarray]] = [None] * len(pairs)
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream(dev)
-        streams = [torch.cuda.Stream(dev) for _ in range(depth)]
-        pending = []                                   # (index, host tensor, event) in issue order
-
-        def collect(upto):
-            while len(pending) > upto:
-                i, host, ev = pending.pop(0)
-                ev.synchronize()
-                results[i] = host.numpy()
-
+        streams = _pipeline_streams(dev, depth)
+        pending = []                                   # (host tensor, event) in issue order
         for i in range(len(pairs)):
             item = pairs[i]() if callable(pairs[i]) else pairs[i]
             fixed, moving = validate_image(item[0]).float(), validate_image(item[1]).float()
@@ -100,9 +105,22 @@ def register_pairs_pipelined(pairs: Sequence, depth: int = 2, device=None, dtype
                     ev.record(st)
             except Exception as e:
                 raise RuntimeError(f"registration of pair {i} failed: {e}") from e
-            pending.append((i, host, ev))
-            collect(depth - 1)                         # at most depth pairs enqueued ahead of the host
-        collect(0)
+            pending.append((host, ev))
+            del fd, md, disp, packed, host
+            while len(pending) >= depth:               # at most `depth` pairs enqueued ahead of the consumer
+                h, e = pending.pop(0)
+                e.synchronize()
+                yield h.numpy()
+                del h
+        while pending:
+            h, e = pending.pop(0)
+            e.synchronize()
+            yield h.numpy()
+            del h
         for st in streams:
             main.wait_stream(st)
-    return results
+
+
+def register_pairs_pipelined(pairs: Sequence, depth: int = 2, device=None, dtype=torch.float32, **kw):
+    """list(iter_register_pipelined(...)): every field is kept, each in its own pinned buffer."""
+    return list(iter_register_pipelined(pairs, depth=depth, device=device, dtype=dtype, **kw))
