@@ -211,42 +211,69 @@ __global__ void __launch_bounds__(256, 2) k_raw_ssd_staged(RawStagedArgs a) {
     ca_mbar_wait(&bar, 0);
     const int ty = (int)threadIdx.y, z0 = 4 * (int)threadIdx.x;
     const int y = y0t + ty;
-    if (y >= a.w) return;
+    const bool active = y < a.w;
+    const bool lpad = threadIdx.x == 0, rpad = threadIdx.x == blockDim.x - 1;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // The chunk buffer's zero halo (rows -2,-1,w,w+1 and the 4+4 pad columns of every row, read by the box kernels without
+    // bounds checks) is written here, next to the data: the edge threads of a row add the pad quads, the first / last row
+    // tile adds the two halo rows above / below the volume.
+    const bool top = y0t == 0 && ty < 2, bottom = y0t + CA_RAW_TY >= a.w && ty < 2;
     const float* fs = sfix + ty * a.dF + z0;
-    float* rp0 = a.raw + (int64_t)blockIdx.z * a.rl.xPitch + (int64_t)(y + 2) * a.rl.rowPitch + 4 + z0;
+    float* slice0 = a.raw + (int64_t)blockIdx.z * a.rl.xPitch + 4 + z0;           // buffer row 0 of this x, column of z0
+    float* rp0 = slice0 + (int64_t)(y + 2) * a.rl.rowPitch;
     for (int kWl = 0; kWl < a.NW; ++kWl) {
         float acc[S][4];
 #pragma unroll
         for (int k = 0; k < S; ++k)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[k][i] = 0.f;
-        const float* ms = smov + (ty + kWl) * a.dP + z0;
-        for (int c = 0; c < a.C; ++c) {
-            const float4 f4 = *reinterpret_cast<const float4*>(fs + c * fch);
-            const float f[4] = {f4.x, f4.y, f4.z, f4.w};
-            float m[NM];
+        if (active) {
+            const float* ms = smov + (ty + kWl) * a.dP + z0;
+            for (int c = 0; c < a.C; ++c) {
+                const float4 f4 = *reinterpret_cast<const float4*>(fs + c * fch);
+                const float f[4] = {f4.x, f4.y, f4.z, f4.w};
+                float m[NM];
 #pragma unroll
-            for (int j = 0; j < NM / 4; ++j) {
-                const float4 m4 = *reinterpret_cast<const float4*>(ms + c * mch + 4 * j);
-                m[4 * j + 0] = m4.x; m[4 * j + 1] = m4.y; m[4 * j + 2] = m4.z; m[4 * j + 3] = m4.w;
-            }
-#pragma unroll
-            for (int k = 0; k < S; ++k)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float df = __fsub_rn(f[i], m[i + k]);
-                    acc[k][i] = FAST ? __fmaf_rn(df, df, acc[k][i]) : __fadd_rn(acc[k][i], __fmul_rn(df, df));
+                for (int j = 0; j < NM / 4; ++j) {
+                    const float4 m4 = *reinterpret_cast<const float4*>(ms + c * mch + 4 * j);
+                    m[4 * j + 0] = m4.x; m[4 * j + 1] = m4.y; m[4 * j + 2] = m4.z; m[4 * j + 3] = m4.w;
                 }
+#pragma unroll
+                for (int k = 0; k < S; ++k)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float df = __fsub_rn(f[i], m[i + k]);
+                        acc[k][i] = FAST ? __fmaf_rn(df, df, acc[k][i]) : __fadd_rn(acc[k][i], __fmul_rn(df, df));
+                    }
+            }
         }
-        float* rp = rp0 + (int64_t)(kWl * S + kH) * S * a.rl.plane;
+        const int64_t poff = (int64_t)(kWl * S + kH) * S * a.rl.plane;
 #pragma unroll
         for (int k = 0; k < S; ++k) {
-            float4 o;
-            o.x = (z0 + 0 < a.d) ? acc[k][0] : 0.f;
-            o.y = (z0 + 1 < a.d) ? acc[k][1] : 0.f;
-            o.z = (z0 + 2 < a.d) ? acc[k][2] : 0.f;
-            o.w = (z0 + 3 < a.d) ? acc[k][3] : 0.f;
-            ca_st_stream4(reinterpret_cast<float4*>(rp + k * a.rl.plane), o);
+            const int64_t pk = poff + k * a.rl.plane;
+            if (active) {
+                float4 o;
+                o.x = (z0 + 0 < a.d) ? acc[k][0] : 0.f;
+                o.y = (z0 + 1 < a.d) ? acc[k][1] : 0.f;
+                o.z = (z0 + 2 < a.d) ? acc[k][2] : 0.f;
+                o.w = (z0 + 3 < a.d) ? acc[k][3] : 0.f;
+                float* rp = rp0 + pk;
+                ca_st_stream4(reinterpret_cast<float4*>(rp), o);
+                if (lpad) ca_st_stream4(reinterpret_cast<float4*>(rp - 4), zero4);
+                if (rpad) ca_st_stream4(reinterpret_cast<float4*>(rp + 4), zero4);
+            }
+            if (top) {
+                float* hp_ = slice0 + pk + (int64_t)ty * a.rl.rowPitch;
+                ca_st_stream4(reinterpret_cast<float4*>(hp_), zero4);
+                if (lpad) ca_st_stream4(reinterpret_cast<float4*>(hp_ - 4), zero4);
+                if (rpad) ca_st_stream4(reinterpret_cast<float4*>(hp_ + 4), zero4);
+            }
+            if (bottom) {
+                float* hp_ = slice0 + pk + (int64_t)(a.w + 2 + ty) * a.rl.rowPitch;
+                ca_st_stream4(reinterpret_cast<float4*>(hp_), zero4);
+                if (lpad) ca_st_stream4(reinterpret_cast<float4*>(hp_ - 4), zero4);
+                if (rpad) ca_st_stream4(reinterpret_cast<float4*>(hp_ + 4), zero4);
+            }
         }
     }
 }
@@ -666,6 +693,16 @@ void launch_raw(bool fast, const float* fixp, const float* movp, int C, int h, i
     else launch_raw_t<HW, false>(fixp, movp, C, h, w, d, chunk_start, g, p, raw, st);
 }
 
+// smem / thread limits of the staged kernel for NW kW groups per chunk
+static bool staged_fits(const CorrPlan& p, int C, int NW) {
+    const size_t smem = ((size_t)C * CA_RAW_TY * p.dF + (size_t)C * (CA_RAW_TY + NW - 1) * p.dP) * sizeof(float);
+    return smem <= 110 * 1024 && (p.dF / 4) * CA_RAW_TY <= 256;
+}
+// true when every chunk of the plan is a set of whole kW groups the staged kernel can take
+static bool all_chunks_staged(const CorrPlan& p, int C) {
+    return use_staged() && p.G % p.S == 0 && staged_fits(p, C, p.G / p.S);
+}
+
 // staged raw kernel for a chunk of whole kW groups (chunk_start = kW0 * S, g = NW * S); false: shape not supported
 template <int HW>
 bool launch_raw_staged(bool fast, const float* fixp, const float* movp, int C, int h, int w, int d, int kW0, int NW, const CorrPlan& p,
@@ -673,7 +710,7 @@ bool launch_raw_staged(bool fast, const float* fixp, const float* movp, int C, i
     constexpr int S = 2 * HW + 1;
     const size_t smem = ((size_t)C * CA_RAW_TY * p.dF + (size_t)C * (CA_RAW_TY + NW - 1) * p.dP) * sizeof(float);
     const int nq = p.dF / 4;
-    if (smem > 110 * 1024 || nq * CA_RAW_TY > 256) return false;     // >= two CTAs per SM, <= 256 threads
+    if (!staged_fits(p, C, NW)) return false;                        // >= two CTAs per SM, <= 256 threads
     RawStagedArgs a;
     a.fixp = fixp; a.movp = movp; a.raw = raw; a.rl = p.rl;
     a.C = C; a.h = h; a.w = w; a.d = d; a.dF = p.dF; a.dP = p.dP; a.r0 = p.r0; a.kW0 = kW0; a.NW = NW;
@@ -747,9 +784,12 @@ static int correlate_impl(bool fast, const float* fix, const float* mov, int C, 
         CA_LAUNCH(k_pad_features, dim3((unsigned)ca_min((int)ca_divup(tm, 256), 148 * 16)), dim3(256), 0, st, mov, C, h, w, d, disp_hw, p.dP, movp);
         CA_CHECK_LAUNCH("correlate/pad");
         // zero the halo rows / pad columns of the chunk buffer once; the raw kernels only ever write interiors
-        const int64_t nslices = (int64_t)p.G * p.S * (p.r1 - p.r0);
-        CA_LAUNCH(k_zero_raw_halo, dim3((unsigned)(nslices < 148 * 32 ? nslices : 148 * 32)), dim3(128), 0, st, raw, nslices, w, p.rl.rowPitch);
-        CA_CHECK_LAUNCH("correlate/zero_halo");
+        // (the staged raw kernel writes the halo of its own planes; only the direct kernel needs it done up front)
+        if (!all_chunks_staged(p, C)) {
+            const int64_t nslices = (int64_t)p.G * p.S * (p.r1 - p.r0);
+            CA_LAUNCH(k_zero_raw_halo, dim3((unsigned)(nslices < 148 * 32 ? nslices : 148 * 32)), dim3(128), 0, st, raw, nslices, w, p.rl.rowPitch);
+            CA_CHECK_LAUNCH("correlate/zero_halo");
+        }
     }
 #ifndef CA_EMU
     {
