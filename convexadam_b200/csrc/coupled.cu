@@ -75,25 +75,29 @@ __global__ void __launch_bounds__(256) k_cost_argmin(const float* __restrict__ s
 }
 
 // soft[c](x) = box3( mesh[c, sel] )(x): ascending (dH,dW,dD) sum of the in-volume taps, / 27  (utils.py:96,107)
-__global__ void __launch_bounds__(256) k_soft_from_keys(const unsigned long long* __restrict__ keys,
+// grid = (ceil(d/128), w, h): no 64-bit index maths; the label is the low word of the key.
+__global__ void __launch_bounds__(128) k_soft_from_keys(const unsigned long long* __restrict__ keys,
                                                         const float* __restrict__ mesh, int h, int w, int d, int L,
                                                         float* __restrict__ soft) {
+    const int z = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, x = (int)blockIdx.z;
+    if (z >= d) return;
     const int64_t n = (int64_t)h * w * d;
-    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
-        const int z = (int)(o % d), y = (int)((o / d) % w), x = (int)(o / ((int64_t)d * w));
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-        for (int xx = ca_max(x - 1, 0); xx < ca_min(x + 2, h); ++xx)
-            for (int yy = ca_max(y - 1, 0); yy < ca_min(y + 2, w); ++yy)
-                for (int zz = ca_max(z - 1, 0); zz < ca_min(z + 2, d); ++zz) {
-                    const int l = (int)(unsigned)(keys[((int64_t)xx * w + yy) * d + zz] & 0xffffffffull);
-                    a0 = __fadd_rn(a0, __ldg(mesh + l));
-                    a1 = __fadd_rn(a1, __ldg(mesh + L + l));
-                    a2 = __fadd_rn(a2, __ldg(mesh + 2 * L + l));
-                }
-        soft[o] = ca_div(a0, 27.f);
-        soft[n + o] = ca_div(a1, 27.f);
-        soft[2 * n + o] = ca_div(a2, 27.f);
-    }
+    const unsigned* lab = reinterpret_cast<const unsigned*>(keys);       // little endian: label = low 32 bits of the key
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int xx = ca_max(x - 1, 0); xx < ca_min(x + 2, h); ++xx)
+        for (int yy = ca_max(y - 1, 0); yy < ca_min(y + 2, w); ++yy) {
+            const int64_t row = ((int64_t)xx * w + yy) * d;
+            for (int zz = ca_max(z - 1, 0); zz < ca_min(z + 2, d); ++zz) {
+                const int l = (int)__ldg(lab + 2 * (row + zz));
+                a0 = __fadd_rn(a0, __ldg(mesh + l));
+                a1 = __fadd_rn(a1, __ldg(mesh + L + l));
+                a2 = __fadd_rn(a2, __ldg(mesh + 2 * L + l));
+            }
+        }
+    const int64_t o = ((int64_t)x * w + y) * d + z;
+    soft[o] = ca_div(a0, 27.f);
+    soft[n + o] = ca_div(a1, 27.f);
+    soft[2 * n + o] = ca_div(a2, 27.f);
 }
 
 __global__ void __launch_bounds__(256) k_keys_to_i64(const unsigned long long* __restrict__ keys, int64_t n,
@@ -808,7 +812,7 @@ extern "C" int ca_coupled_convex(const float* ssd, const int64_t* argmin, const 
                                  int disp_hw, float* disp_soft, int64_t* sel_out, void* workspace, size_t workspace_bytes,
                                  ca_stream_t stream) {
     CA_CHECK_ARG(ssd && mesh && disp_soft && workspace, "coupled_convex: null pointer");
-    CA_CHECK_ARG(h > 0 && w > 0 && d > 0 && disp_hw >= 1 && disp_hw <= 8, "coupled_convex: bad dims");
+    CA_CHECK_ARG(h > 0 && w > 0 && d > 0 && disp_hw >= 1 && disp_hw <= 8 && h < 65536 && w < 65536, "coupled_convex: bad dims");
     if (workspace_bytes < ca_coupled_convex_workspace_bytes(h, w, d, disp_hw)) {
         ca_set_error("coupled_convex: workspace too small");
         return CA_ERR_WORKSPACE;
@@ -830,7 +834,7 @@ extern "C" int ca_coupled_convex(const float* ssd, const int64_t* argmin, const 
     } else if (!argmin) {
         if ((rc = ca_launch_cost_argmin(ssd, n, L, nullptr, nullptr, 0.f, keys, st)) != CA_OK) return rc;
     }
-    CA_LAUNCH(k_soft_from_keys, dim3(small_grid(n)), dim3(256), 0, st, keys, mesh, h, w, d, L, disp_soft);
+    CA_LAUNCH(k_soft_from_keys, dim3((unsigned)ca_divup(d, 128), (unsigned)w, (unsigned)h), dim3(128), 0, st, keys, mesh, h, w, d, L, disp_soft);
     CA_CHECK_LAUNCH("coupled_convex/init");
     for (int j = 0; j < 6; ++j) {
         if (prune) rc = ca_launch_cost_argmin_pruned(ssd, bmin, n, S, mesh, boxes, disp_soft, coeffs[j], d, keys, st);
@@ -840,7 +844,7 @@ extern "C" int ca_coupled_convex(const float* ssd, const int64_t* argmin, const 
             rc = ca_launch_keys_to_i64(keys, n, sel_out + (int64_t)j * n, st);
             if (rc != CA_OK) return rc;
         }
-        CA_LAUNCH(k_soft_from_keys, dim3(small_grid(n)), dim3(256), 0, st, keys, mesh, h, w, d, L, disp_soft);
+        CA_LAUNCH(k_soft_from_keys, dim3((unsigned)ca_divup(d, 128), (unsigned)w, (unsigned)h), dim3(128), 0, st, keys, mesh, h, w, d, L, disp_soft);
         CA_CHECK_LAUNCH("coupled_convex/soft");
     }
     return CA_OK;
@@ -858,7 +862,7 @@ extern "C" int ca_coupled_convex_certified(const float* ssd, const float* fix, c
                                            int w, int d, int disp_hw, float* disp_soft, int64_t* sel_out, int32_t* flagged_out,
                                            void* workspace, size_t workspace_bytes, ca_stream_t stream) {
     CA_CHECK_ARG(ssd && fix && mov && mesh && disp_soft && workspace, "coupled_convex_certified: null pointer");
-    CA_CHECK_ARG(C > 0 && h > 0 && w > 0 && d > 0 && disp_hw >= 1 && disp_hw <= 8, "coupled_convex_certified: bad dims");
+    CA_CHECK_ARG(C > 0 && h > 0 && w > 0 && d > 0 && disp_hw >= 1 && disp_hw <= 8 && h < 65536 && w < 65536, "coupled_convex_certified: bad dims");
     CA_CHECK_ARG((int64_t)h * w * d < (1ll << 31), "coupled_convex_certified: coarse grid too large");
     if (workspace_bytes < ca_coupled_convex_certified_workspace_bytes(h, w, d, disp_hw)) {
         ca_set_error("coupled_convex_certified: workspace too small");
@@ -904,7 +908,7 @@ extern "C" int ca_coupled_convex_certified(const float* ssd, const float* fix, c
             rc = ca_launch_keys_to_i64(keys, n, sel_out + (int64_t)(j + 1) * n, st);
             if (rc != CA_OK) return rc;
         }
-        CA_LAUNCH(k_soft_from_keys, dim3(small_grid(n)), dim3(256), 0, st, keys, mesh, h, w, d, L, disp_soft);
+        CA_LAUNCH(k_soft_from_keys, dim3((unsigned)ca_divup(d, 128), (unsigned)w, (unsigned)h), dim3(128), 0, st, keys, mesh, h, w, d, L, disp_soft);
         CA_CHECK_LAUNCH("coupled_convex_certified/soft");
     }
     if (flagged_out && cudaMemcpyAsync(flagged_out, counters, 7 * sizeof(int), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
