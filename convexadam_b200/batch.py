@@ -53,6 +53,7 @@ def register_pairs(pairs: Sequence, gather: bool = True, register_fn: Optional[C
 
 
 _STREAMS = {}
+_RINGS = {}
 
 
 def _pipeline_streams(dev, depth):
@@ -63,14 +64,15 @@ def _pipeline_streams(dev, depth):
     return have[:depth]
 
 
-def iter_register_pipelined(pairs: Sequence, depth: int = 2, device=None, dtype=torch.float32, **kw):
+def iter_register_pipelined(pairs: Sequence, depth: int = 2, device=None, dtype=torch.float32, copy: bool = False, **kw):
     """Generator over the fields of `pairs`, in order, with `depth` pairs in flight on as many CUDA streams: the Adam
     stage of one pair (small latency-bound kernels) shares the GPU with the cost-volume stage of the next, and the
     host<->device copies of one pair overlap the compute of another.  The kernels are the ones `convex_adam_pt` runs,
     each pair on its own stream, so every field is bit-identical to `convex_adam_pt(fixed, moving, dtype=dtype, **kw)`.
-    pairs: sequence of (fixed, moving) volumes (or callables returning such a tuple).  Yields (H,W,D,3) float64 arrays
-    that live in pinned host memory (as convex_adam_pt's result does): drop each one when done with it and its buffer is
-    recycled for a later pair -- copying 189 MB per field on the host would cost more than the registration.
+    pairs: sequence of (fixed, moving) volumes (or callables returning such a tuple).  Yields (H,W,D,3) float64 arrays.
+    copy=False (default): each array is a view of one of depth+2 pinned staging buffers that are reused round-robin --
+    it stays valid until TWO further fields have been yielded (consume or copy it before asking for the third); copying
+    189 MB per field on the host would cost more than the registration itself.  copy=True yields arrays that own their memory.
     MIND path, no masks."""
     from . import pipeline
     from ._native import get_lib
@@ -88,6 +90,8 @@ def iter_register_pipelined(pairs: Sequence, depth: int = 2, device=None, dtype=
         main = torch.cuda.current_stream(dev)
         streams = _pipeline_streams(dev, depth)
         pending = []                                   # (host tensor, event) in issue order
+        ring = _RINGS.setdefault(str(dev), {})         # pinned staging buffers, allocated once per device and shape
+        nring = depth + 2
         for i in range(len(pairs)):
             item = pairs[i]() if callable(pairs[i]) else pairs[i]
             fixed, moving = validate_image(item[0]).float(), validate_image(item[1]).float()
@@ -99,7 +103,10 @@ def iter_register_pipelined(pairs: Sequence, depth: int = 2, device=None, dtype=
                     md = moving.to(dev, non_blocking=True).contiguous()
                     disp = pipeline.register_mind(fd, md, prm, lib)
                     packed = lib.pack_field(disp, round_half=(dtype == torch.float16))
-                    host = torch.empty(packed.shape, dtype=torch.float64, pin_memory=True)
+                    key = (tuple(packed.shape), i % nring)
+                    host = ring.get(key)
+                    if host is None:
+                        host = ring[key] = torch.empty(packed.shape, dtype=torch.float64, pin_memory=True)
                     host.copy_(packed, non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(st)
@@ -110,17 +117,15 @@ def iter_register_pipelined(pairs: Sequence, depth: int = 2, device=None, dtype=
             while len(pending) >= depth:               # at most `depth` pairs enqueued ahead of the consumer
                 h, e = pending.pop(0)
                 e.synchronize()
-                yield h.numpy()
-                del h
+                yield h.numpy().copy() if copy else h.numpy()
         while pending:
             h, e = pending.pop(0)
             e.synchronize()
-            yield h.numpy()
-            del h
+            yield h.numpy().copy() if copy else h.numpy()
         for st in streams:
             main.wait_stream(st)
 
 
 def register_pairs_pipelined(pairs: Sequence, depth: int = 2, device=None, dtype=torch.float32, **kw):
-    """list(iter_register_pipelined(...)): every field is kept, each in its own pinned buffer."""
-    return list(iter_register_pipelined(pairs, depth=depth, device=device, dtype=dtype, **kw))
+    """list(iter_register_pipelined(..., copy=True)): every field is kept, each owning its memory."""
+    return list(iter_register_pipelined(pairs, depth=depth, device=device, dtype=dtype, copy=True, **kw))

@@ -151,6 +151,13 @@ def test_pipelined_batch_equals_individual_calls():
     kw = dict(mind_r=1, mind_d=2, lambda_weight=1.25, grid_sp=2, disp_hw=3, selected_niter=6, selected_smooth=0, grid_sp_adam=2, ic=True)
     pairs = [make_pair((40, 36, 44), seed=s, disp_scale=0.1) for s in range(5)]
     got = register_pairs_pipelined(pairs, depth=2, **kw)
-    for (f, m), g in zip(pairs, got):
-        want = api()(f, m, dtype=torch.float32, **kw)
+    wants = [api()(f, m, dtype=torch.float32, **kw) for f, m in pairs]
+    for g, want in zip(got, wants):
         assert g.dtype == np.float64 and (g == want).all()
+    # the zero-copy generator: each field is checked while it is the current one
+    from convexadam_b200.batch import iter_register_pipelined
+    n = 0
+    for g, want in zip(iter_register_pipelined(pairs, depth=2, **kw), wants):
+        assert (g == want).all()
+        n += 1
+    assert n == len(pairs)
