@@ -312,7 +312,7 @@ def main():
                           "fp32-issue-bound by design: 24 flop per written float; bytes = the raw SSD planes it writes"),
               kernel_line("blockmin_argmin", "k_blockmin_argmin (argmin + block/slab minima, one streaming read of the volume)",
                           ndir * ab["blockmin_per_direction"], "hbm", "streaming pass"),
-              kernel_line("select_pass", "k_cost_argmin_pruned (one coupled-convex selection pass, exact pruning)",
+              kernel_line("select_pass", "k_cost_argmin_sep (one coupled-convex selection pass, exact pruning, separable grid)",
                           ndir * 6 * ab["coupled_per_pass"], "hbm",
                           "bytes = what an unpruned pass reads (SURVEY 8d); the pruned pass touches ~5 % of them, hence frac > 1"),
               kernel_line("exact_redecision", "k_cc_fixup (exact re-decision of near-ties)", 0, "hbm", "latency-bound, a few hundred voxels")]
