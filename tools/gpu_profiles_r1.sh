@@ -1,5 +1,6 @@
 #!/bin/bash
 # round-1 evidence: launch list of the bench command + one full capture per main kernel (read back with tools/ncu_summary.py)
+# NB gpurun brings back at most 64 MiB per call: the ten captures are ~50 MB, run the two loops in separate calls if it refuses
 OUT=gpurun_out/${1:-r1final}
 mkdir -p $OUT
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches_bench.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/bench_under_ncu.log 2>&1; echo "list rc=$?"
