@@ -131,3 +131,37 @@ static __device__ __forceinline__ void ca_mbar_wait(unsigned long long* bar, uns
         : "memory");
 }
 #endif
+
+// ---- packed fp32 pairs (sm_100: add/sub/mul/fma .rn.f32x2): IEEE round-to-nearest per lane, i.e. bit-identical to the
+// scalar _rn intrinsics, at one issue slot for two values (the kernels that use them are bound by issue slots)
+#if defined(CA_EMU)
+static inline float2 ca_sub2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+static inline float2 ca_add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+static inline float2 ca_mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+static inline float2 ca_fma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#else
+static __device__ __forceinline__ float2 ca_sub2(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+static __device__ __forceinline__ float2 ca_add2(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+static __device__ __forceinline__ float2 ca_mul2(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+static __device__ __forceinline__ float2 ca_fma2(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+#endif

@@ -222,31 +222,40 @@ __global__ void __launch_bounds__(256, 2) k_raw_ssd_staged(RawStagedArgs a) {
     float* slice0 = a.raw + (int64_t)blockIdx.z * a.rl.xPitch + 4 + z0;           // buffer row 0 of this x, column of z0
     float* rp0 = slice0 + (int64_t)(y + 2) * a.rl.rowPitch;
     for (int kWl = 0; kWl < a.NW; ++kWl) {
-        float acc[S][4];
+        // the 4 voxels x S shifts as packed pairs: acc2[k][p] = voxels (2p, 2p+1) of shift k
+        float2 acc2[S][2];
 #pragma unroll
-        for (int k = 0; k < S; ++k)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[k][i] = 0.f;
+        for (int k = 0; k < S; ++k) acc2[k][0] = acc2[k][1] = make_float2(0.f, 0.f);
         if (active) {
             const float* ms = smov + (ty + kWl) * a.dP + z0;
             for (int c = 0; c < a.C; ++c) {
                 const float4 f4 = *reinterpret_cast<const float4*>(fs + c * fch);
-                const float f[4] = {f4.x, f4.y, f4.z, f4.w};
-                float m[NM];
+                const float2 f2[2] = {make_float2(f4.x, f4.y), make_float2(f4.z, f4.w)};
+                float m[NM + 1];
 #pragma unroll
                 for (int j = 0; j < NM / 4; ++j) {
                     const float4 m4 = *reinterpret_cast<const float4*>(ms + c * mch + 4 * j);
                     m[4 * j + 0] = m4.x; m[4 * j + 1] = m4.y; m[4 * j + 2] = m4.z; m[4 * j + 3] = m4.w;
                 }
+                m[NM] = 0.f;
+                // pairs at even offsets come straight from the loaded quads, pairs at odd offsets from a copy shifted by one
+                float2 me[NM / 2], mo[NM / 2];
+#pragma unroll
+                for (int j = 0; j < NM / 2; ++j) { me[j] = make_float2(m[2 * j], m[2 * j + 1]); mo[j] = make_float2(m[2 * j + 1], m[2 * j + 2]); }
 #pragma unroll
                 for (int k = 0; k < S; ++k)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float df = __fsub_rn(f[i], m[i + k]);
-                        acc[k][i] = FAST ? __fmaf_rn(df, df, acc[k][i]) : __fadd_rn(acc[k][i], __fmul_rn(df, df));
+                    for (int pp = 0; pp < 2; ++pp) {
+                        const int j = 2 * pp + k;                       // first moving value of the pair
+                        const float2 mv = (j & 1) ? mo[j >> 1] : me[j >> 1];
+                        const float2 df = ca_sub2(f2[pp], mv);
+                        acc2[k][pp] = FAST ? ca_fma2(df, df, acc2[k][pp]) : ca_add2(acc2[k][pp], ca_mul2(df, df));
                     }
             }
         }
+        float acc[S][4];
+#pragma unroll
+        for (int k = 0; k < S; ++k) { acc[k][0] = acc2[k][0].x; acc[k][1] = acc2[k][0].y; acc[k][2] = acc2[k][1].x; acc[k][3] = acc2[k][1].y; }
         const int64_t poff = (int64_t)(kWl * S + kH) * S * a.rl.plane;
 #pragma unroll
         for (int k = 0; k < S; ++k) {
