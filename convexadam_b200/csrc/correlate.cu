@@ -248,8 +248,16 @@ __global__ void __launch_bounds__(256, 2) k_raw_ssd_staged(RawStagedArgs a) {
                     for (int pp = 0; pp < 2; ++pp) {
                         const int j = 2 * pp + k;                       // first moving value of the pair
                         const float2 mv = (j & 1) ? mo[j >> 1] : me[j >> 1];
-                        const float2 df = ca_sub2(f2[pp], mv);
-                        acc2[k][pp] = FAST ? ca_fma2(df, df, acc2[k][pp]) : ca_add2(acc2[k][pp], ca_mul2(df, df));
+                        if (FAST) {
+                            const float2 df = ca_sub2(f2[pp], mv);
+                            acc2[k][pp] = ca_fma2(df, df, acc2[k][pp]);
+                        } else {
+                            // exact mode stays scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (even through
+                            // an fma with a -0 addend), which it never does for the scalar _rn intrinsics
+                            const float dx = __fsub_rn(f2[pp].x, mv.x), dy = __fsub_rn(f2[pp].y, mv.y);
+                            acc2[k][pp].x = __fadd_rn(acc2[k][pp].x, __fmul_rn(dx, dx));
+                            acc2[k][pp].y = __fadd_rn(acc2[k][pp].y, __fmul_rn(dy, dy));
+                        }
                     }
             }
         }
