@@ -35,3 +35,13 @@ def test_correlate_slab(lib): kc.check_correlate_slab(lib, DEV)
 def test_cc_pieces(lib): kc.check_cc_pieces(lib, DEV)
 def test_adam_window(lib): kc.check_adam_window(lib, DEV)
 def test_apply_convex(lib): kc.check_apply_convex(lib, DEV)
+
+
+def test_kernel_timing_binding(lib):
+    """The measurement aid of bench.py: the slot names map onto the C enum and the calls are harmless no-ops in this build."""
+    lib.kernel_timing(("raw_ssd", "box_filters", "select_pass"))
+    kc.check_certified(lib, DEV, cases=((3, 4, 5, 7, 1),), tie_case=False)
+    assert lib.kernel_times() == {}
+    lib.kernel_timing(())
+    with pytest.raises(ValueError):
+        lib.kernel_timing(("no_such_kernel",))
