@@ -16,11 +16,10 @@ if [ "$2" != "quick" ]; then
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv python tools/profile_pair.py 10 > $OUT/ncu_list.log 2>&1; echo "ncu list rc=$?"
 tail -2 $OUT/ncu_list.log
-echo "== ncu full captures"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_cost_argmin -s 3 -c 2 -f -o $OUT/prof_cost_argmin python tools/profile_pair.py 1 > $OUT/ncu_full1.log 2>&1; echo "rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_raw_ssd -s 20 -c 1 -f -o $OUT/prof_raw_ssd python tools/profile_pair.py 1 > $OUT/ncu_full2.log 2>&1; echo "rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_box3_exact -s 40 -c 2 -f -o $OUT/prof_box3 python tools/profile_pair.py 1 > $OUT/ncu_full3.log 2>&1; echo "rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_adam_grad -s 0 -c 1 -f -o $OUT/prof_adam_grad python tools/profile_pair.py 2 > $OUT/ncu_full4.log 2>&1; echo "rc=$?"
+echo "== ncu full captures (dominant kernels; the full set is tools/gpu_profiles_r1.sh)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_box12_fast -s 1 -c 1 -f -o $OUT/prof_k_box12_fast python tools/profile_corr.py --fast > $OUT/ncu_full1.log 2>&1; echo "rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_raw_ssd_staged -s 1 -c 1 -f -o $OUT/prof_k_raw_ssd_staged python tools/profile_corr.py --fast > $OUT/ncu_full2.log 2>&1; echo "rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_adam_grad -s 1 -c 1 -f -o $OUT/prof_k_adam_grad python tools/profile_pair.py 2 > $OUT/ncu_full3.log 2>&1; echo "rc=$?"
 ls -la $OUT
 fi
 echo "== memcheck (small)"; timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a $OUT/memcheck.log
