@@ -355,3 +355,10 @@ def check_apply_convex(lib, device, shape=(9, 11, 13)):
     ident = np.zeros((H, W, D, 3))
     mov = r.rand(H, W, D).astype(np.float32)
     assert (N(lib.apply_convex(T(ident, device, torch.float64), T(mov, device))) == mov).all(), "zero field must return the image"
+
+
+def random_small_shapes(seed, count, max_hw=3):
+    """(C, h, w, d, hw) with degenerate extents (1-wide axes, d not a multiple of 4, fewer rows than a tile)."""
+    rs = np.random.RandomState(seed)
+    return tuple((int(rs.randint(1, 14)), int(rs.randint(1, 9)), int(rs.randint(1, 11)), int(rs.randint(1, 19)), int(rs.randint(1, max_hw + 1)))
+                 for _ in range(count))

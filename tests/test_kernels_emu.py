@@ -45,3 +45,10 @@ def test_kernel_timing_binding(lib):
     lib.kernel_timing(())
     with pytest.raises(ValueError):
         lib.kernel_timing(("no_such_kernel",))
+
+
+def test_random_small_shapes(lib):
+    """Exact and certified correlate / coupled_convex on randomly drawn degenerate shapes (poisoned workspaces)."""
+    shapes = kc.random_small_shapes(123, 10)
+    kc.check_certified(lib, DEV, cases=shapes, tie_case=False)
+    kc.check_correlate(lib, DEV, cases=shapes[:6])

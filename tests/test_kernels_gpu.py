@@ -75,6 +75,12 @@ def test_apply_convex_matches_scipy_and_api(lib, dev):
     assert got32.dtype == np.float32 and (got32 == want32).mean() > 0.9999 and np.abs(got32 - want32).max() <= 1e-4
 
 
+def test_random_small_shapes(lib, dev):
+    shapes = kc.random_small_shapes(321, 16, max_hw=5)
+    kc.check_certified(lib, dev, cases=shapes, tie_case=False)
+    kc.check_correlate(lib, dev, cases=shapes[:8])
+
+
 def test_certified(lib, dev):
     kc.check_certified(lib, dev, cases=((12, 10, 9, 16, 3), (16, 6, 7, 8, 1), (3, 5, 6, 9, 4), (12, 8, 6, 12, 6), (12, 7, 9, 10, 2)))
 
