@@ -51,6 +51,8 @@ _SIGS = {
     "ca_adam_run": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ca_pack_field": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "ca_apply_convex": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "ca_field_mean_workspace_bytes": (_sz, []),
+    "ca_field_mean": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _sz, _vp]),
 }
 EXPORTS = tuple(_SIGS)
 ABI_VERSION = 1
@@ -390,6 +392,22 @@ class Lib:
         self._chk(self.dll.ca_pack_field(self._p(field), H, W, D, int(round_half), self._p(out), self._stream(field)))
         return out
 
+
+    def field_mean(self, field, mask=None, round_half=False):
+        """(mean displacement per channel, voxel count) of a (3,H,W,D) f32 field over mask != 0 (uint8) or everywhere:
+        a (4,) float64 device tensor."""
+        field = self._t(field)
+        n = field[0].numel()
+        if mask is not None:
+            mask = self._t(mask, torch.uint8)
+            if mask.numel() != n:
+                raise ValueError("field_mean: mask must have one entry per voxel")
+        out = torch.empty(4, dtype=torch.float64, device=field.device)
+        nb = self.dll.ca_field_mean_workspace_bytes()
+        ws = self._ws(nb, field)
+        self._chk(self.dll.ca_field_mean(self._p(field), self._p(mask), n, int(round_half), self._p(out), self._p(ws), nb,
+                                        self._stream(field)))
+        return out
 
     def apply_convex(self, disp, moving):
         """moving (H,W,D) f32/f64 warped by disp (H,W,D,3) f64 (apply_convex.py:13-24)."""

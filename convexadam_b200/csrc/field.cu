@@ -269,3 +269,67 @@ extern "C" int ca_apply_convex(const double* disp, const void* moving, int movin
     CA_CHECK_LAUNCH("apply_convex");
     return CA_OK;
 }
+
+
+// ---- mean displacement (reference src/convexAdam/convex_adam_translation.py:88-96) -------------------------------------
+// translation = np.mean(field[mask], axis=0) (or over the whole volume): three float64 sums and a count, reduced in two
+// deterministic levels (per-CTA partials in a fixed order, then one CTA), so the 189 MB field need not leave the device
+// when only its mean is wanted.  field: planar (3,n) f32 as the pipeline produces it; mask: optional (n) uint8.
+__global__ void __launch_bounds__(256) k_field_sum_partial(const float* __restrict__ field, const unsigned char* __restrict__ mask,
+                                                           int64_t n, int round_half, double* __restrict__ partial) {
+    __shared__ double red[4][256];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, cnt = 0.0;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+        if (mask && !mask[o]) continue;
+        float a = field[o], b = field[n + o], c = field[2 * n + o];
+        if (round_half) { a = ca_round_half(a); b = ca_round_half(b); c = ca_round_half(c); }
+        s0 += (double)a; s1 += (double)b; s2 += (double)c; cnt += 1.0;
+    }
+    red[0][threadIdx.x] = s0; red[1][threadIdx.x] = s1; red[2][threadIdx.x] = s2; red[3][threadIdx.x] = cnt;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if ((int)threadIdx.x < k)
+            for (int j = 0; j < 4; ++j) red[j][threadIdx.x] += red[j][threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) partial[(int64_t)blockIdx.x * 4 + threadIdx.x] = red[threadIdx.x][0];
+}
+__global__ void __launch_bounds__(256) k_field_sum_final(const double* __restrict__ partial, int nblocks, double* __restrict__ out) {
+    __shared__ double red[4][256];
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int b = threadIdx.x; b < nblocks; b += 256)
+        for (int j = 0; j < 4; ++j) s[j] += partial[(int64_t)b * 4 + j];
+    for (int j = 0; j < 4; ++j) red[j][threadIdx.x] = s[j];
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if ((int)threadIdx.x < k)
+            for (int j = 0; j < 4; ++j) red[j][threadIdx.x] += red[j][threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double c = red[3][0];
+        out[0] = c > 0.0 ? red[0][0] / c : 0.0;
+        out[1] = c > 0.0 ? red[1][0] / c : 0.0;
+        out[2] = c > 0.0 ? red[2][0] / c : 0.0;
+        out[3] = c;
+    }
+}
+
+extern "C" size_t ca_field_mean_workspace_bytes(void) { return (size_t)1024 * 4 * sizeof(double); }
+
+extern "C" int ca_field_mean(const float* field, const unsigned char* mask, int64_t n, int round_half, double* out4, void* workspace,
+                             size_t workspace_bytes, ca_stream_t stream) {
+    CA_CHECK_ARG(field && out4 && workspace && n > 0, "field_mean: bad argument");
+    if (workspace_bytes < ca_field_mean_workspace_bytes()) {
+        ca_set_error("field_mean: workspace too small");
+        return CA_ERR_WORKSPACE;
+    }
+    int64_t nb = ca_divup(n, 256 * 16);
+    if (nb > 1024) nb = 1024;
+    if (nb < 1) nb = 1;
+    double* partial = (double*)workspace;
+    CA_LAUNCH(k_field_sum_partial, dim3((unsigned)nb), dim3(256), 0, (cudaStream_t)stream, field, mask, n, round_half, partial);
+    CA_LAUNCH(k_field_sum_final, dim3(1), dim3(256), 0, (cudaStream_t)stream, partial, (int)nb, out4);
+    CA_CHECK_LAUNCH("field_mean");
+    return CA_OK;
+}

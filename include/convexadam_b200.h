@@ -16,6 +16,7 @@
  *   ca_adam_run            the Adam instance-optimisation    convex_adam_MIND.py:147-181
  *   ca_pack_field          dtype rounding + np.stack(...,3)  convex_adam_MIND.py:198-202
  *   ca_apply_convex        map_coordinates warp              apply_convex.py:13-24
+ *   ca_field_mean          np.mean(field[mask], axis=0)      convex_adam_translation.py:88-96
  *
  * Conventions: every pointer is a DEVICE pointer to a contiguous array owned by the caller;
  * no function allocates, none synchronises, all work is enqueued on `stream` (a cudaStream_t); the functions are
@@ -205,6 +206,14 @@ CA_API int ca_pack_field(const float* field, int H, int W, int D, int round_half
  * convex_adam_pt returns; moving, warped (H,W,D) f32 or f64 (moving_is_f64). */
 CA_API int ca_apply_convex(const double* disp, const void* moving, int moving_is_f64, int H, int W, int D, void* warped,
                     ca_stream_t stream);
+
+/* ---- mean displacement (convex_adam_translation.py:88-96) -----------------------------------------------------------
+ * out4 = (mean of channel 0, 1, 2 over the voxels with mask != 0 -- all voxels when mask is NULL --, voxel count) in
+ * float64; field planar (3,n) f32 on the device, mask optional (n) uint8; round_half as in ca_pack_field.  Lets a
+ * translation-only caller skip the transfer of the dense field. */
+CA_API size_t ca_field_mean_workspace_bytes(void);
+CA_API int ca_field_mean(const float* field, const unsigned char* mask, int64_t n, int round_half, double* out4, void* workspace,
+                  size_t workspace_bytes, ca_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -285,3 +285,12 @@ def apply_convex(disp, moving):
         v += m64[idx] * w
     out_dtype = moving.dtype if moving.dtype in (np.float32, np.float64) else np.float64
     return np.where(inside, v, 0.0).astype(out_dtype)
+
+
+def translation_from_field(field, spacing_zyx, seg=None):
+    """convex_adam_translation.py:88-104: mean of the (H,W,D,3) field (inside seg > 0 when given), divided by the moving
+    spacing, rounded to whole voxels, back to mm, reversed to (x,y,z)."""
+    field = np.asarray(field, np.float64)
+    t = field[np.asarray(seg) > 0].mean(axis=0) if seg is not None else field.mean(axis=(0, 1, 2))
+    spacing = np.asarray(spacing_zyx, np.float64)
+    return t, tuple(list((np.round(t / spacing, decimals=0) * spacing)[::-1]))

@@ -362,3 +362,18 @@ def random_small_shapes(seed, count, max_hw=3):
     rs = np.random.RandomState(seed)
     return tuple((int(rs.randint(1, 14)), int(rs.randint(1, 9)), int(rs.randint(1, 11)), int(rs.randint(1, 19)), int(rs.randint(1, max_hw + 1)))
                  for _ in range(count))
+
+
+def check_field_mean(lib, device, shape=(9, 10, 11)):
+    """ca_field_mean vs numpy float64 means (whole volume, masked, empty mask, half-rounded values)."""
+    r = rng(95)
+    f = (r.randn(3, *shape) * 5).astype(np.float32)
+    got = N(lib.field_mean(T(f, device)))
+    assert np.abs(got[:3] - f.astype(np.float64).reshape(3, -1).mean(1)).max() <= 1e-12 and got[3] == f[0].size
+    mask = (r.rand(*shape) > 0.6)
+    got = N(lib.field_mean(T(f, device), T(mask.astype(np.uint8), device, torch.uint8)))
+    assert np.abs(got[:3] - f.astype(np.float64)[:, mask].mean(1)).max() <= 1e-12 and got[3] == mask.sum()
+    got = N(lib.field_mean(T(f, device), T(np.zeros(shape, np.uint8), device, torch.uint8)))
+    assert (got == 0).all()
+    got = N(lib.field_mean(T(f, device), round_half=True))
+    assert np.abs(got[:3] - f.astype(np.float16).astype(np.float64).reshape(3, -1).mean(1)).max() <= 1e-12

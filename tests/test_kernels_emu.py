@@ -52,3 +52,6 @@ def test_random_small_shapes(lib):
     shapes = kc.random_small_shapes(123, 10)
     kc.check_certified(lib, DEV, cases=shapes, tie_case=False)
     kc.check_correlate(lib, DEV, cases=shapes[:6])
+
+
+def test_field_mean(lib): kc.check_field_mean(lib, DEV)

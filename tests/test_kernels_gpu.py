@@ -75,6 +75,9 @@ def test_apply_convex_matches_scipy_and_api(lib, dev):
     assert got32.dtype == np.float32 and (got32 == want32).mean() > 0.9999 and np.abs(got32 - want32).max() <= 1e-4
 
 
+def test_field_mean(lib, dev): kc.check_field_mean(lib, dev, shape=(33, 20, 41))
+
+
 def test_random_small_shapes(lib, dev):
     shapes = kc.random_small_shapes(321, 16, max_hw=5)
     kc.check_certified(lib, dev, cases=shapes, tie_case=False)

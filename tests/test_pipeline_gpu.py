@@ -161,3 +161,24 @@ def test_pipelined_batch_equals_individual_calls():
         assert (g == want).all()
         n += 1
     assert n == len(pairs)
+
+
+def test_translation_core_equals_reference_formula():
+    """convex_adam_translation.py:83-104 on arrays: the device-side mean == np.mean of convex_adam_pt's field (whole volume
+    and inside a segmentation), and the rounded translation == the oracle's restatement of the reference formula."""
+    from convexadam_b200.convex_adam_translation import convex_adam_translation_arrays, mean_displacement
+    from convexadam_b200.synth import make_pair
+    from oracle import ca_oracle as orc
+    fixed, _ = make_pair((54, 48, 60), seed=6)
+    moving = torch.roll(fixed, (3, -2, 1), (0, 1, 2))
+    kw = dict(grid_sp=3, disp_hw=3, selected_niter=8)
+    field = api()(fixed, moving, **kw)                                    # default dtype float16, as the wrapper calls it
+    seg = np.zeros((54, 48, 60), np.uint8)
+    seg[15:40, 12:36, 18:45] = 1
+    spacing = (3.0, 0.5, 0.5)
+    for s in (None, seg):
+        got = mean_displacement(fixed, moving, s, **kw)
+        want_mean, want_xyz = orc.translation_from_field(field, spacing, s)
+        assert np.abs(got - want_mean).max() <= 1e-9
+        assert convex_adam_translation_arrays(fixed, moving, spacing, s, **kw) == want_xyz
+    assert np.abs(want_mean - np.array([3.0, -2.0, 1.0])).max() < 0.5
