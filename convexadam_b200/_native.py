@@ -35,6 +35,10 @@ _SIGS = {
     "ca_cc_blockmin": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _sz, _vp]),
     "ca_cc_select": (_i, [_vp, _i64, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ca_cc_smooth": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "ca_correlate_slab_fast": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "ca_cc_certified_workspace_bytes": (_sz, [_i64]),
+    "ca_cc_blockmin_certified": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "ca_cc_select_certified": (_i, [_vp, _i64, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "ca_adam_window_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "ca_adam_run_window": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                 _i, _vp]),
@@ -219,17 +223,22 @@ class Lib:
                                        self._p(ws), nb, self._stream(fix)))
         return ssd, am
 
-    def correlate_slab(self, fix, mov, disp_hw, x_begin, x_end, want_argmin=True, out=None):
-        """correlate for the H planes [x_begin, x_end) of the coarse grid only (fix/mov: whole (C,h,w,d) volumes)."""
+    def correlate_slab(self, fix, mov, disp_hw, x_begin, x_end, want_argmin=True, out=None, fast=False):
+        """correlate for the H planes [x_begin, x_end) of the coarse grid only (fix/mov: whole (C,h,w,d) volumes).
+        fast=True: the approximate volume of the certified mode (no argmin)."""
         fix = self._t(fix)
         mov = self._t(mov)
         Cn, h, w, d = fix.shape
         L = (2 * disp_hw + 1) ** 3
         hs = x_end - x_begin
         ssd = out if out is not None else torch.empty((L, hs, w, d), dtype=torch.float32, device=fix.device)
-        am = torch.empty((hs, w, d), dtype=torch.int64, device=fix.device) if want_argmin else None
+        am = torch.empty((hs, w, d), dtype=torch.int64, device=fix.device) if (want_argmin and not fast) else None
         nb = self.dll.ca_correlate_slab_workspace_bytes(Cn, h, w, d, disp_hw, x_begin, x_end)
         ws = self._ws(nb, fix)
+        if fast:
+            self._chk(self.dll.ca_correlate_slab_fast(self._p(fix), self._p(mov), Cn, h, w, d, disp_hw, x_begin, x_end, self._p(ssd),
+                                                     self._p(ws), nb, self._stream(fix)))
+            return ssd, None
         self._chk(self.dll.ca_correlate_slab(self._p(fix), self._p(mov), Cn, h, w, d, disp_hw, x_begin, x_end, self._p(ssd),
                                             self._p(am), self._p(ws), nb, self._stream(fix)))
         return ssd, am
@@ -261,6 +270,42 @@ class Lib:
         ws = self._ws(nb, ssd)
         self._chk(self.dll.ca_cc_select(self._p(ssd), n, disp_hw, self._p(mesh), self._p(soft), float(coeff), self._p(bmin),
                                        self._p(prev), self._p(sel), self._p(ws), nb, self._stream(ssd)))
+        return sel
+
+    def cc_blockmin_certified(self, ssd, disp_hw, mesh, fix, mov, x_begin):
+        """Certified counterpart of cc_blockmin for a slab of the approximate volume: (bmin (S*S+2*S,hs,w,d), exact argmin)."""
+        ssd = self._t(ssd)
+        fix = self._t(fix)
+        mov = self._t(mov)
+        mesh = self._t(mesh.reshape(3, -1))
+        n = ssd[0].numel()
+        S = 2 * disp_hw + 1
+        Cn, h, w, d = fix.shape
+        bmin = torch.empty((S * S + 2 * S,) + tuple(ssd.shape[1:]), dtype=torch.float32, device=ssd.device)
+        am = torch.empty(ssd.shape[1:], dtype=torch.int64, device=ssd.device)
+        nb = self.dll.ca_cc_certified_workspace_bytes(n)
+        ws = self._ws(nb, ssd)
+        self._chk(self.dll.ca_cc_blockmin_certified(self._p(ssd), n, disp_hw, self._p(mesh), self._p(bmin), self._p(am), self._p(fix),
+                                                   self._p(mov), Cn, h, w, d, x_begin, self._p(ws), nb, self._stream(ssd)))
+        return bmin, am
+
+    def cc_select_certified(self, ssd, disp_hw, mesh, soft, coeff, bmin, prev, fix, mov, x_begin):
+        """Certified counterpart of cc_select(..., bmin=, prev=) for a slab of the approximate volume."""
+        ssd = self._t(ssd)
+        fix = self._t(fix)
+        mov = self._t(mov)
+        mesh = self._t(mesh.reshape(3, -1))
+        soft = self._t(soft)
+        bmin = self._t(bmin)
+        prev = self._t(prev, torch.int64)
+        n = ssd[0].numel()
+        Cn, h, w, d = fix.shape
+        sel = torch.empty(ssd.shape[1:], dtype=torch.int64, device=ssd.device)
+        nb = self.dll.ca_cc_certified_workspace_bytes(n)
+        ws = self._ws(nb, ssd)
+        self._chk(self.dll.ca_cc_select_certified(self._p(ssd), n, disp_hw, self._p(mesh), self._p(soft), float(coeff), self._p(bmin),
+                                                 self._p(prev), self._p(sel), self._p(fix), self._p(mov), Cn, h, w, d, x_begin,
+                                                 self._p(ws), nb, self._stream(ssd)))
         return sel
 
     def cc_smooth(self, sel_window, mesh, disp_hw):

@@ -899,6 +899,12 @@ extern "C" int ca_correlate(const float* fix, const float* mov, int C, int h, in
     return correlate_impl(false, fix, mov, C, h, w, d, disp_hw, 0, h, ssd, argmin, workspace, workspace_bytes, stream);
 }
 
+// ca_correlate_fast for the H planes [x_begin, x_end) only (slab-parallel path)
+extern "C" int ca_correlate_slab_fast(const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, int x_begin,
+                                      int x_end, float* ssd, void* workspace, size_t workspace_bytes, ca_stream_t stream) {
+    return correlate_impl(true, fix, mov, C, h, w, d, disp_hw, x_begin, x_end, ssd, nullptr, workspace, workspace_bytes, stream);
+}
+
 // The cost volume to a few ulp (relative error <= CA_FAST_SSD_REL_ERR of each entry, see coupled.cu): the input of
 // ca_coupled_convex_certified, which still returns the reference's selections bit for bit.
 extern "C" int ca_correlate_fast(const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, float* ssd,

@@ -135,6 +135,7 @@ struct FixupArgs {
     int64_t n;
     float coeff;
     int C, h, w, d, hw;
+    int x0;                     // first H plane of the slab the (L, n) arrays describe (0: the whole volume)
 };
 
 // One CTA per flagged voxel: (1) the minimum approximate cost over ALL labels, (2) the labels within the band of it,
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(128) k_cc_fixup(FixupArgs a) {
     const int64_t cs = (int64_t)a.h * a.w * a.d;
     for (int idx = (int)blockIdx.x; idx < count; idx += (int)gridDim.x) {
         const int v = a.flagged[idx];
-        const int z = v % a.d, y = (v / a.d) % a.w, x = v / (a.d * a.w);
+        const int z = v % a.d, y = (v / a.d) % a.w, x = v / (a.d * a.w) + a.x0;
         const float s0 = a.soft[v], s1 = a.soft[a.n + v], s2 = a.soft[2 * a.n + v];
         if (tid == 0) s_ncand = 0;
         float mn = INFINITY;
@@ -889,7 +890,7 @@ extern "C" int ca_coupled_convex_certified(const float* ssd, const float* fix, c
     if ((rc = ca_launch_mesh_boxes(mesh, S, boxes, st)) != CA_OK) return rc;
     FixupArgs fa;
     fa.ssd = ssd; fa.mesh = mesh; fa.soft = disp_soft; fa.fix = fix; fa.mov = mov; fa.flagged = flagged; fa.keys = keys;
-    fa.n = n; fa.C = C; fa.h = h; fa.w = w; fa.d = d; fa.hw = disp_hw;
+    fa.n = n; fa.C = C; fa.h = h; fa.w = w; fa.d = d; fa.hw = disp_hw; fa.x0 = 0;
     for (int j = -1; j < 6; ++j) {
         const float coeff = j < 0 ? 0.f : coeffs[j];
         int* cnt = counters + (j + 1);
@@ -986,6 +987,89 @@ extern "C" int ca_cc_select(const float* ssd, int64_t n, int disp_hw, const floa
     }
     if (rc != CA_OK) return rc;
     return ca_launch_keys_to_i64(keys, n, sel, st);
+}
+
+// ---- the certified stage in pieces (slab-parallel path): the same kernels restricted to the H planes [x_begin, x_end) ----
+// workspace: [keys n u64 | boxes | flagged n i32 | counter | zero soft 3n f32]
+extern "C" size_t ca_cc_certified_workspace_bytes(int64_t n) {
+    return ca_cc_select_workspace_bytes(n) + (size_t)n * 4 + 256 + 256 + (size_t)3 * n * 4 + 256;
+}
+
+namespace {
+struct CertWs { unsigned long long* keys; float4* boxes; int* flagged; int* counter; float* zsoft; };
+CertWs cert_ws(void* workspace, int64_t n) {
+    CertWs c;
+    c.keys = (unsigned long long*)workspace;
+    c.boxes = (float4*)(((uintptr_t)(c.keys + n) + 255) & ~(uintptr_t)255);
+    c.flagged = (int*)(((uintptr_t)((char*)workspace + ca_cc_select_workspace_bytes(n)) + 255) & ~(uintptr_t)255);
+    c.counter = (int*)(((uintptr_t)(c.flagged + n) + 255) & ~(uintptr_t)255);
+    c.zsoft = (float*)(((uintptr_t)(c.counter + 16) + 255) & ~(uintptr_t)255);
+    return c;
+}
+}  // namespace
+
+// bmin: (S*S + 2*S, n) -- block minima, slab minima, slab runner-ups; argmin (n) int64: the plain argmin of utils.py:87,
+// certified exact (fix, mov: the whole (C,h,w,d) feature volumes the slab's approximate cost volume was built from)
+extern "C" int ca_cc_blockmin_certified(const float* ssd, int64_t n, int disp_hw, const float* mesh, float* bmin, int64_t* argmin,
+                                        const float* fix, const float* mov, int C, int h, int w, int d, int x_begin, void* workspace,
+                                        size_t workspace_bytes, ca_stream_t stream) {
+    CA_CHECK_ARG(ssd && mesh && bmin && argmin && fix && mov && workspace && n > 0 && disp_hw >= 1 && disp_hw <= 8, "cc_blockmin_certified: bad argument");
+    CA_CHECK_ARG(C > 0 && h > 0 && w > 0 && d > 0 && x_begin >= 0 && n % ((int64_t)w * d) == 0 && x_begin + n / ((int64_t)w * d) <= h,
+                 "cc_blockmin_certified: the slab does not fit the volume");
+    if (workspace_bytes < ca_cc_certified_workspace_bytes(n)) {
+        ca_set_error("cc_blockmin_certified: workspace too small");
+        return CA_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int S = 2 * disp_hw + 1;
+    const CertWs c = cert_ws(workspace, n);
+    float* smin = bmin + (int64_t)S * S * n;
+    float* ssec = smin + (int64_t)S * n;
+    if (cudaMemsetAsync(c.counter, 0, 16 * sizeof(int), st) != cudaSuccess || cudaMemsetAsync(c.zsoft, 0, (size_t)3 * n * 4, st) != cudaSuccess) {
+        ca_set_error("cc_blockmin_certified: memset failed");
+        return CA_ERR_LAUNCH;
+    }
+    int rc = ca_launch_blockmin_argmin(ssd, n, S, bmin, c.keys, st, ssec);
+    if (rc != CA_OK) return rc;
+    CA_LAUNCH(k_certify_argmin, dim3(small_grid(n)), dim3(256), 0, st, smin, ssec, n, S, c.flagged, c.counter);
+    FixupArgs fa;
+    fa.ssd = ssd; fa.mesh = mesh; fa.soft = c.zsoft; fa.fix = fix; fa.mov = mov; fa.flagged = c.flagged; fa.nflagged = c.counter;
+    fa.keys = c.keys; fa.n = n; fa.coeff = 0.f; fa.C = C; fa.h = h; fa.w = w; fa.d = d; fa.hw = disp_hw; fa.x0 = x_begin;
+    CA_LAUNCH(k_cc_fixup, dim3(148 * 8), dim3(128), 0, st, fa);
+    CA_CHECK_LAUNCH("cc_blockmin_certified");
+    return ca_launch_keys_to_i64(c.keys, n, argmin, st);
+}
+
+// one certified selection pass over a slab (bmin from ca_cc_blockmin_certified, prev = the previous selection)
+extern "C" int ca_cc_select_certified(const float* ssd, int64_t n, int disp_hw, const float* mesh, const float* soft, float coeff,
+                                      const float* bmin, const int64_t* prev, int64_t* sel, const float* fix, const float* mov, int C,
+                                      int h, int w, int d, int x_begin, void* workspace, size_t workspace_bytes, ca_stream_t stream) {
+    CA_CHECK_ARG(ssd && mesh && soft && bmin && prev && sel && fix && mov && workspace && n > 0 && disp_hw >= 1 && disp_hw <= 8,
+                 "cc_select_certified: bad argument");
+    CA_CHECK_ARG(C > 0 && h > 0 && w > 0 && d > 0 && x_begin >= 0 && n % ((int64_t)w * d) == 0 && x_begin + n / ((int64_t)w * d) <= h,
+                 "cc_select_certified: the slab does not fit the volume");
+    if (workspace_bytes < ca_cc_certified_workspace_bytes(n)) {
+        ca_set_error("cc_select_certified: workspace too small");
+        return CA_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int S = 2 * disp_hw + 1;
+    const CertWs c = cert_ws(workspace, n);
+    if (cudaMemsetAsync(c.counter, 0, 16 * sizeof(int), st) != cudaSuccess) {
+        ca_set_error("cc_select_certified: memset failed");
+        return CA_ERR_LAUNCH;
+    }
+    CA_LAUNCH(k_i64_to_keys, dim3(small_grid(n)), dim3(256), 0, st, prev, n, c.keys);
+    CA_CHECK_LAUNCH("cc_select_certified/keys");
+    int rc;
+    if ((rc = ca_launch_mesh_boxes(mesh, S, c.boxes, st)) != CA_OK) return rc;
+    if ((rc = ca_launch_cost_argmin_pruned(ssd, bmin, n, S, mesh, c.boxes, soft, coeff, 0, c.keys, st, c.flagged, c.counter)) != CA_OK) return rc;
+    FixupArgs fa;
+    fa.ssd = ssd; fa.mesh = mesh; fa.soft = soft; fa.fix = fix; fa.mov = mov; fa.flagged = c.flagged; fa.nflagged = c.counter;
+    fa.keys = c.keys; fa.n = n; fa.coeff = coeff; fa.C = C; fa.h = h; fa.w = w; fa.d = d; fa.hw = disp_hw; fa.x0 = x_begin;
+    CA_LAUNCH(k_cc_fixup, dim3(148 * 8), dim3(128), 0, st, fa);
+    CA_CHECK_LAUNCH("cc_select_certified/fixup");
+    return ca_launch_keys_to_i64(c.keys, n, sel, st);
 }
 
 extern "C" int ca_cc_smooth(const int64_t* sel_window, const float* mesh, int P, int w, int d, int disp_hw, float* soft,

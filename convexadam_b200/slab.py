@@ -89,11 +89,17 @@ class _Comm:
         return torch.cat([p.narrow(dim, 0, e - b) for p, (b, e) in zip(parts, ranges)], dim).contiguous()
 
 
-def coupled_convex_slab(lib: Lib, comm: _Comm, ssd, mesh, disp_hw):
+def coupled_convex_slab(lib: Lib, comm: _Comm, ssd, mesh, disp_hw, certified=None):
     """argmin (utils.py:87) + coupled_convex (utils.py:93-109) on this rank's slab: ssd (L,hs,w,d) -> disp_soft
-    (3,hs,w,d).  One full pass builds the block minima and the argmin; the six regularised passes are pruned."""
+    (3,hs,w,d).  One full pass builds the block minima and the argmin; the six regularised passes are pruned.
+    certified = (fix, mov, x_begin): ssd is the approximate volume of correlate_slab(fast=True) and every selection is
+    certified against the features (same selections as the exact volume, bit for bit)."""
     _, hs, w, d = ssd.shape
-    bmin, sel = lib.cc_blockmin(ssd, disp_hw)
+    if certified is not None:
+        cf, cm, cx0 = certified
+        bmin, sel = lib.cc_blockmin_certified(ssd, disp_hw, mesh, cf, cm, cx0)
+    else:
+        bmin, sel = lib.cc_blockmin(ssd, disp_hw)
     outside = torch.full((1, w, d), -1, dtype=torch.int64, device=ssd.device)
     soft = None
     for j in range(len(CC_COEFFS) + 1):
@@ -102,7 +108,10 @@ def coupled_convex_slab(lib: Lib, comm: _Comm, ssd, mesh, disp_hw):
         soft = lib.cc_smooth(window, mesh, disp_hw)                                   # utils.py:96 / :107
         if j == len(CC_COEFFS):
             break
-        sel = lib.cc_select(ssd, disp_hw, mesh, soft, CC_COEFFS[j], bmin=bmin, prev=sel)   # utils.py:104-105
+        if certified is not None:
+            sel = lib.cc_select_certified(ssd, disp_hw, mesh, soft, CC_COEFFS[j], bmin, sel, cf, cm, cx0)
+        else:
+            sel = lib.cc_select(ssd, disp_hw, mesh, soft, CC_COEFFS[j], bmin=bmin, prev=sel)   # utils.py:104-105
     return soft
 
 
@@ -160,9 +169,12 @@ def register_features_slab(lib: Lib, comm: _Comm, fix_s, mov_s, fix_a, mov_a, sh
     L = (2 * prm.disp_hw + 1) ** 3
     ssd = torch.empty((L, x1 - x0, w, d), dtype=torch.float32, device=fix_s.device)      # reused for the backward direction
 
+    certified = prm.resolved_mode() == "certified"
+
     def one_direction(f, m):
-        lib.correlate_slab(f, m, prm.disp_hw, x0, x1, want_argmin=False, out=ssd)
-        return comm.gather_planes(coupled_convex_slab(lib, comm, ssd, mesh, prm.disp_hw), ranges)
+        lib.correlate_slab(f, m, prm.disp_hw, x0, x1, want_argmin=False, out=ssd, fast=certified)
+        soft_slab = coupled_convex_slab(lib, comm, ssd, mesh, prm.disp_hw, (f, m, x0) if certified else None)
+        return comm.gather_planes(soft_slab, ranges)
 
     soft = one_direction(fix_s, mov_s)
     if prm.ic:

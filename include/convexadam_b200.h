@@ -135,6 +135,20 @@ CA_API int ca_coupled_convex_certified(const float* ssd, const float* fix, const
                                 int w, int d, int disp_hw, float* disp_soft, int64_t* sel_out, int32_t* flagged_out,
                                 void* workspace, size_t workspace_bytes, ca_stream_t stream);
 
+/* The certified mode in pieces, for the slab-parallel path: ca_correlate_slab_fast is ca_correlate_fast for the H planes
+ * [x_begin, x_end); ca_cc_blockmin_certified builds bmin (S*S + 2*S, n: block minima, slab minima, slab runner-ups) and the
+ * plain argmin of the slab, certified exact; ca_cc_select_certified is one certified selection pass (ca_cc_select with
+ * pruning).  fix, mov: the whole (C,h,w,d) feature volumes; x_begin: the slab's first plane; n = slab voxels. */
+CA_API int ca_correlate_slab_fast(const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, int x_begin,
+                           int x_end, float* ssd, void* workspace, size_t workspace_bytes, ca_stream_t stream);
+CA_API size_t ca_cc_certified_workspace_bytes(int64_t n);
+CA_API int ca_cc_blockmin_certified(const float* ssd, int64_t n, int disp_hw, const float* mesh, float* bmin, int64_t* argmin,
+                             const float* fix, const float* mov, int C, int h, int w, int d, int x_begin, void* workspace,
+                             size_t workspace_bytes, ca_stream_t stream);
+CA_API int ca_cc_select_certified(const float* ssd, int64_t n, int disp_hw, const float* mesh, const float* soft, float coeff,
+                           const float* bmin, const int64_t* prev, int64_t* sel, const float* fix, const float* mov, int C, int h,
+                           int w, int d, int x_begin, void* workspace, size_t workspace_bytes, ca_stream_t stream);
+
 /* coupled_convex in pieces (the loop of utils.py:98-107 run by the host, for H slabs with a halo exchange in between):
  * ca_cc_blockmin: bmin (S*S + S, n): per-voxel minima over the S*S blocks of S consecutive labels, followed by the minima
  *               over the S slabs of S blocks; and (argmin != NULL) the plain argmin of utils.py:87 in the same pass.

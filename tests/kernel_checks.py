@@ -194,6 +194,21 @@ def check_cc_pieces(lib, device, C=6, h=7, w=5, d=8, hw=2, cut=3):
             sels = [lib.cc_select(ssds[i], hw, mesh, softs[i], coeff) for i in range(2)]
     got = torch.cat(softs, 1)
     assert_bits_equal(N(got), N(want), "coupled_convex in slabs")
+    # the certified pieces on slabs of the APPROXIMATE volume (slab-parallel certified mode) give the same field
+    fs = [lib.correlate_slab(fix, mov, hw, a, b, fast=True)[0] for a, b in slabs]
+    cb = [lib.cc_blockmin_certified(fs[i], hw, mesh, fix, mov, slabs[i][0]) for i in range(2)]
+    csel = [cb[i][1] for i in range(2)]
+    for i in range(2):
+        assert (N(csel[i]) == N(am[slabs[i][0]:slabs[i][1]])).all(), "cc_blockmin_certified argmin"
+    csoft = None
+    for j in range(7):
+        wins = [torch.cat([pad, csel[0], csel[1][:1]], 0), torch.cat([csel[0][-1:], csel[1], pad], 0)]
+        csoft = [lib.cc_smooth(wv.contiguous(), mesh, hw) for wv in wins]
+        if j == 6:
+            break
+        coeff = (0.003, 0.01, 0.03, 0.1, 0.3, 1.0)[j]
+        csel = [lib.cc_select_certified(fs[i], hw, mesh, csoft[i], coeff, cb[i][0], csel[i], fix, mov, slabs[i][0]) for i in range(2)]
+    assert_bits_equal(N(torch.cat(csoft, 1)), N(want), "certified coupled_convex in slabs")
     want2, sel2 = lib.coupled_convex(ssd, None, mesh, hw, want_sel=True)       # argmin taken inside
     assert_bits_equal(N(want2), N(want), "coupled_convex with internal argmin")
     assert (N(lib.cc_select(ssd, hw)) == N(am)).all(), "cc_select without regulariser == argmin"
