@@ -169,7 +169,10 @@ def register_features_slab(lib: Lib, comm: _Comm, fix_s, mov_s, fix_a, mov_a, sh
     L = (2 * prm.disp_hw + 1) ** 3
     ssd = torch.empty((L, x1 - x0, w, d), dtype=torch.float32, device=fix_s.device)      # reused for the backward direction
 
-    certified = prm.resolved_mode() == "certified"
+    # The slab path takes the exact cost volume unless the certified mode is asked for explicitly (Params.mode): with
+    # the host-run selection loop the certified pieces measured slower here (34.8 vs 31.0 ms for the config-2 pair on two
+    # GPUs); they exist, and are parity-tested, for slabs whose exact volume would be the bottleneck.
+    certified = prm.mode == "certified"
 
     def one_direction(f, m):
         lib.correlate_slab(f, m, prm.disp_hw, x0, x1, want_argmin=False, out=ssd, fast=certified)

@@ -42,12 +42,13 @@ def test_split_planes():
         slab.split_planes(3, 4)
 
 
-@pytest.mark.parametrize("shape,niter", [((32, 12, 16), 3),      # 8 Adam planes per rank: 7-plane halo exchange
-                                          ((20, 12, 16), 2)])     # 5 per rank: all-gather fallback
-def test_two_ranks_equal_single_process(tmp_path, shape, niter):
+@pytest.mark.parametrize("shape,niter,mode", [((32, 12, 16), 3, ""),            # 8 Adam planes per rank: 7-plane halo exchange
+                                               ((20, 12, 16), 2, ""),            # 5 per rank: all-gather fallback
+                                               ((32, 12, 16), 2, "certified")])  # the certified pieces on slabs
+def test_two_ranks_equal_single_process(tmp_path, shape, niter, mode):
     path = build()
     kw = dict(mind_r=1, mind_d=2, lambda_weight=1.25, grid_sp=2, disp_hw=2, selected_niter=niter, selected_smooth=0,
-              grid_sp_adam=2, ic=True)
+              grid_sp_adam=2, ic=True, mode=mode)
     from convexadam_b200.synth import make_pair
     lib = Lib(path, expect_cuda=False)
     f, m = make_pair(shape, seed=11, disp_scale=0.15)
