@@ -17,20 +17,19 @@ from .convex_adam_utils import validate_image
 
 
 def index_translation_to_world_translation(index_translation: Iterable[float], direction: Iterable[float]) -> np.ndarray:
-    """Translation along the image grid (mm) -> world coordinates (reference :12-29)."""
-    dimension = int(np.sqrt(len(direction)))
-    direction_matrix = np.array(direction).reshape((dimension, dimension))
-    return direction_matrix @ np.array(index_translation)
+    """A translation along the image grid (mm) expressed in world coordinates: direction cosines times the vector
+    (same contract as the reference helper of that name, :12-29)."""
+    cosines = np.asarray(list(direction), dtype=np.float64)
+    dim = int(round(np.sqrt(cosines.size)))
+    return cosines.reshape(dim, dim).dot(np.asarray(list(index_translation), dtype=np.float64))
 
 
 def field_to_translation(translation_zyx, spacing_zyx) -> tuple:
-    """Mean displacement (voxels of the 1 mm grid = mm, array-axis order) -> the translation the reference applies
-    (:99-104): rounded to whole voxels of the moving image, in mm, reversed to (x, y, z)."""
-    spacing_zyx = np.asarray(spacing_zyx, dtype=np.float64)
-    translation_ijk = np.asarray(translation_zyx, dtype=np.float64) / spacing_zyx
-    translation_ijk_voxels = np.round(translation_ijk, decimals=0)
-    translation_ijk_mm = translation_ijk_voxels * spacing_zyx
-    return tuple(list(translation_ijk_mm[::-1]))
+    """Mean displacement on the 1 mm grid (array-axis order, mm) -> the shift the reference applies to the moving image
+    (:99-104): snapped to whole voxels of the moving image's own spacing, given back in mm as (x, y, z)."""
+    sp = np.asarray(spacing_zyx, dtype=np.float64)
+    whole_voxels = np.rint(np.asarray(translation_zyx, dtype=np.float64) / sp)       # np.round(., 0): half to even, like rint
+    return tuple((whole_voxels * sp)[::-1].tolist())
 
 
 def mean_displacement(img_fixed, img_moving, segmentation=None, device=None, dtype=torch.float16, **kw) -> np.ndarray:

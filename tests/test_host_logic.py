@@ -142,3 +142,19 @@ def test_bench_reference_arm_prints_one_json_line():
         assert key in line, key
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_translation_helpers_match_reference_formula():
+    """convex_adam_translation.py:12-29 and :99-104 restated: rounding to whole voxels of the moving spacing, (x,y,z) order."""
+    import numpy as np
+    from convexadam_b200.convex_adam_translation import field_to_translation, index_translation_to_world_translation
+    from oracle import ca_oracle as orc
+    rs = np.random.RandomState(0)
+    for _ in range(100):
+        t, sp = rs.randn(3) * 7, rs.rand(3) * 3 + 0.2
+        field = np.broadcast_to(t, (2, 3, 2, 3)).copy()
+        mean, want = orc.translation_from_field(field, sp)
+        assert np.allclose(mean, t) and field_to_translation(t, sp) == want
+    assert field_to_translation((2.5, -0.5, 1.49), (1.0, 1.0, 1.0)) == (1.0, -0.0, 2.0)        # half to even, reversed
+    got = index_translation_to_world_translation((1, 2, 3), (0, 1, 0, -1, 0, 0, 0, 0, 1))
+    assert np.allclose(got, [2.0, -1.0, 3.0])
