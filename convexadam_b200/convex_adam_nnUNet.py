@@ -32,15 +32,24 @@ def _label_tables(pred_fixed, pred_moving):
     return pos, weight, lut
 
 
+def half_weights(weight):
+    """The value a present class takes in the reference's features, `10 * (onehot.float() * weight).half()` (nnUNet.py:35-36):
+    the weight rounded to half, then multiplied by 10 in half arithmetic.  Returned as float32 (exactly representable)."""
+    return (10 * weight.half()).half().float()
+
+
 def extract_features(pred_fixed, pred_moving):
-    """Weighted one-hot features (1,C,H,W,D) of both label maps in half precision (reference nnUNet.py:19-38)."""
+    """Weighted one-hot features (1,C,H,W,D) of both label maps in half precision (reference nnUNet.py:19-38).  Like the
+    reference, any leading singleton dimensions are accepted (`shape[-3:]`, `view(1,H,W,D)`)."""
     lib = get_lib()
     dev = torch.device("cuda")
+    pred_fixed = torch.as_tensor(pred_fixed)
+    pred_moving = torch.as_tensor(pred_moving)
+    H, W, D = pred_fixed.shape[-3:]
     pos, weight, lut = _label_tables(pred_fixed, pred_moving)
-    w = (10 * weight.half()).float()           # `10 * (onehot.float() * weight).half()`: half(weight), then 10x in half
-    w = w.half().float()
-    ff = lib.onehot_pooled(pred_fixed.float().to(dev).contiguous(), lut.to(dev), w.to(dev), 1)
-    fm = lib.onehot_pooled(pred_moving.float().to(dev).contiguous(), lut.to(dev), w.to(dev), 1)
+    w = half_weights(weight)
+    ff = lib.onehot_pooled(pred_fixed.float().reshape(H, W, D).to(dev).contiguous(), lut.to(dev), w.to(dev), 1)
+    fm = lib.onehot_pooled(pred_moving.float().reshape(H, W, D).to(dev).contiguous(), lut.to(dev), w.to(dev), 1)
     return ff.half().unsqueeze(0), fm.half().unsqueeze(0)
 
 
@@ -56,7 +65,7 @@ def convex_adam_pt(pred_fixed, pred_moving, lambda_weight=1.25, grid_sp=6, disp_
     H, W, D = pred_fixed.shape[-3:]
     pos, weight, lut = _label_tables(pred_fixed, pred_moving)
     if dtype == torch.float16:
-        w = (10 * weight.half()).half().float()
+        w = half_weights(weight)
     else:
         w = 10 * weight
     # the reference honours selected_smooth in {3,5} only (nnUNet.py:136-144)

@@ -341,16 +341,8 @@ static int box3_cubed(const float* in, float* tmp, float* out, int ha, int wa, i
     if (a.Ly < 4) a.Ly = ca_min(4, a.Ty);
     const size_t smem = (size_t)2 * (a.Ty + 6) * da * 4;
     const dim3 grid((unsigned)a.ntiles, (unsigned)ha, 3u);
-#ifndef CA_EMU
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_box3_p<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CA_BOX3_SMEM + 6 * 4096);
-        cudaFuncSetAttribute(k_box3_p<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CA_BOX3_SMEM + 6 * 4096);
-        attr_done = true;
-    }
-#endif
-    if (upd) { auto k = k_box3_p<true>; CA_LAUNCH(k, grid, dim3(256), smem, st, a); }
-    else { auto k = k_box3_p<false>; CA_LAUNCH(k, grid, dim3(256), smem, st, a); }
+    if (upd) { auto k = k_box3_p<true>; CA_SMEM_OPTIN(k, CA_BOX3_SMEM + 6 * 4096); CA_LAUNCH(k, grid, dim3(256), smem, st, a); }
+    else { auto k = k_box3_p<false>; CA_SMEM_OPTIN(k, CA_BOX3_SMEM + 6 * 4096); CA_LAUNCH(k, grid, dim3(256), smem, st, a); }
     CA_CHECK_LAUNCH("box3_p");
     return CA_OK;
 }

@@ -36,6 +36,21 @@ void ca_set_error(const char* fmt, ...);
             return CA_ERR_BAD_ARGUMENT;  \
         }                                \
     } while (0)
+// Opt a kernel in to > 48 KB of dynamic shared memory.  The attribute belongs to the (function, device) pair, so it is
+// set before every such launch on whichever device is current (a host-side table lookup in the runtime; CUTLASS does the
+// same) -- a per-process "done" flag would leave every device but the first without it.
+#ifdef CA_EMU
+#define CA_SMEM_OPTIN(kernel, bytes) do { } while (0)
+#else
+#define CA_SMEM_OPTIN(kernel, bytes)                                                                              \
+    do {                                                                                                          \
+        cudaError_t e__ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+        if (e__ != cudaSuccess) {                                                                                 \
+            ca_set_error("%s: cannot opt in to %d bytes of shared memory: %s", #kernel, (int)(bytes), cudaGetErrorString(e__)); \
+            return CA_ERR_LAUNCH;                                                                                 \
+        }                                                                                                         \
+    } while (0)
+#endif
 #define CA_CHECK_LAUNCH(what)                                                       \
     do {                                                                            \
         cudaError_t e__ = cudaGetLastError();                                       \

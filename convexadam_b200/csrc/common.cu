@@ -2,6 +2,7 @@
 #include "ca_platform.h"
 
 #include <cstdarg>
+#include <mutex>
 
 static thread_local char g_ca_error[512] = "";
 
@@ -36,9 +37,12 @@ constexpr int kMaxTimed = 4096;
 TimedLaunch g_timed[kMaxTimed];
 int g_ntimed = 0, g_ncreated = 0;
 unsigned g_timing = 0;      // bit mask of the slots to time
+std::mutex g_timing_mu;     // the slot table is shared by every host thread that launches through the library
 }  // namespace
 void* ca_timing_begin(int slot, cudaStream_t st) {
-    if (!((g_timing >> slot) & 1u) || g_ntimed >= kMaxTimed) return nullptr;
+    if (!((__atomic_load_n(&g_timing, __ATOMIC_RELAXED) >> slot) & 1u)) return nullptr;     // the common case: timing off
+    std::lock_guard<std::mutex> lock(g_timing_mu);
+    if (g_ntimed >= kMaxTimed) return nullptr;
     TimedLaunch& t = g_timed[g_ntimed];
     if (g_ntimed >= g_ncreated) {
         if (cudaEventCreate(&t.e0) != cudaSuccess || cudaEventCreate(&t.e1) != cudaSuccess) return nullptr;
@@ -52,9 +56,14 @@ void* ca_timing_begin(int slot, cudaStream_t st) {
 void ca_timing_end(void* h, cudaStream_t st) {
     if (h) cudaEventRecord(((TimedLaunch*)h)->e1, st);
 }
-extern "C" void ca_kernel_timing(int slot_mask) { g_timing = (unsigned)slot_mask; g_ntimed = 0; }
+extern "C" void ca_kernel_timing(int slot_mask) {
+    std::lock_guard<std::mutex> lock(g_timing_mu);
+    __atomic_store_n(&g_timing, (unsigned)slot_mask, __ATOMIC_RELAXED);
+    g_ntimed = 0;
+}
 // sums the recorded launches per slot (ms[slot], count[slot], slot < nslots); the caller synchronises first
 extern "C" int ca_kernel_times(double* ms, int* count, int nslots) {
+    std::lock_guard<std::mutex> lock(g_timing_mu);
     for (int i = 0; i < nslots; ++i) { ms[i] = 0.0; count[i] = 0; }
     for (int i = 0; i < g_ntimed; ++i) {
         float t = 0.f;

@@ -732,17 +732,11 @@ bool launch_raw_staged(bool fast, const float* fixp, const float* movp, int C, i
     a.fixp = fixp; a.movp = movp; a.raw = raw; a.rl = p.rl;
     a.C = C; a.h = h; a.w = w; a.d = d; a.dF = p.dF; a.dP = p.dP; a.r0 = p.r0; a.kW0 = kW0; a.NW = NW;
     const dim3 grid((unsigned)S, (unsigned)((w + CA_RAW_TY - 1) / CA_RAW_TY), (unsigned)(p.r1 - p.r0)), block((unsigned)nq, CA_RAW_TY);
-#ifndef CA_EMU
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_raw_ssd_staged<HW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-        cudaFuncSetAttribute(k_raw_ssd_staged<HW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-        attr_done = true;
-    }
-#endif
-    if (fast) { auto k = k_raw_ssd_staged<HW, true>; CA_LAUNCH(k, grid, block, smem, st, a); }
-    else { auto k = k_raw_ssd_staged<HW, false>; CA_LAUNCH(k, grid, block, smem, st, a); }
-    *rc = CA_OK;
+    *rc = [&]() -> int {
+        if (fast) { auto k = k_raw_ssd_staged<HW, true>; CA_SMEM_OPTIN(k, 110 * 1024); CA_LAUNCH(k, grid, block, smem, st, a); }
+        else { auto k = k_raw_ssd_staged<HW, false>; CA_SMEM_OPTIN(k, 110 * 1024); CA_LAUNCH(k, grid, block, smem, st, a); }
+        return CA_OK;
+    }();
     return true;
 }
 }  // namespace
@@ -808,18 +802,6 @@ static int correlate_impl(bool fast, const float* fix, const float* mov, int C, 
             CA_CHECK_LAUNCH("correlate/zero_halo");
         }
     }
-#ifndef CA_EMU
-    {
-        static bool attr_done = false;   // opt in to > 48 KB of dynamic shared memory once
-        if (!attr_done) {
-            cudaFuncSetAttribute(k_box12<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-            cudaFuncSetAttribute(k_box12<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-            cudaFuncSetAttribute(k_box12_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaFuncSetAttribute(k_box12_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr_done = true;
-        }
-    }
-#endif
     if (p.box_smem > 160 * 1024 || (fast && p.boxf_smem > 200 * 1024)) {
         ca_set_error("correlate: row tile needs %zu bytes of shared memory", p.box_smem);
         return CA_ERR_UNSUPPORTED;
@@ -842,6 +824,7 @@ static int correlate_impl(bool fast, const float* fix, const float* mov, int C, 
                 default: staged = launch_raw_staged<8>(fast, fixp, movp, C, h, w, d, cs / S, g / S, p, raw, st, &src); break;
             }
         }
+        if (src != CA_OK) return src;
         if (!staged)
         switch (disp_hw) {
             case 1: launch_raw<1>(fast, fixp, movp, C, h, w, d, cs, g, p, raw, st); break;
@@ -868,11 +851,11 @@ static int correlate_impl(bool fast, const float* fix, const float* mov, int C, 
             f.w = w; f.d = d; f.S = S; f.chunk_start = cs;
             f.r0 = p.r0; f.r1 = p.r1; f.b0 = p.b0; f.b1 = p.b1; f.xb = x_begin; f.xe = x_end;
             f.nq = p.nq; f.RP = p.RP; f.Ty = p.Ty;
-            if ((d & 3) == 0) { auto k = k_box12_fast<true>; CA_LAUNCH(k, bgrid, bblock, p.boxf_smem, st, f); }
-            else { auto k = k_box12_fast<false>; CA_LAUNCH(k, bgrid, bblock, p.boxf_smem, st, f); }
+            if ((d & 3) == 0) { auto k = k_box12_fast<true>; CA_SMEM_OPTIN(k, 200 * 1024); CA_LAUNCH(k, bgrid, bblock, p.boxf_smem, st, f); }
+            else { auto k = k_box12_fast<false>; CA_SMEM_OPTIN(k, 200 * 1024); CA_LAUNCH(k, bgrid, bblock, p.boxf_smem, st, f); }
         } else {
-            if ((d & 3) == 0) { auto k = k_box12<true>; CA_LAUNCH(k, bgrid, bblock, p.box_smem, st, a); }
-            else { auto k = k_box12<false>; CA_LAUNCH(k, bgrid, bblock, p.box_smem, st, a); }
+            if ((d & 3) == 0) { auto k = k_box12<true>; CA_SMEM_OPTIN(k, 160 * 1024); CA_LAUNCH(k, bgrid, bblock, p.box_smem, st, a); }
+            else { auto k = k_box12<false>; CA_SMEM_OPTIN(k, 160 * 1024); CA_LAUNCH(k, bgrid, bblock, p.box_smem, st, a); }
         }
         ca_timing_end(tm, st);
         CA_CHECK_LAUNCH("correlate/box12");

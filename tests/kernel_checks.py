@@ -313,6 +313,9 @@ def check_adam(lib, device, C=12, shape=(10, 12, 14), lam=1.25, steps=(1, 2, 7))
         assert np.abs(N(u) - u_o).max() <= 2e-6 * max(1.0, np.abs(u_o).max()), f"adam u step {k + 1}: {np.abs(N(u) - u_o).max():.2e}"
         gmax = np.abs(g_o).max()
         assert np.abs(N(g) - g_o).max() <= 5e-6 * gmax, f"adam grad step {k + 1}: {np.abs(N(g) - g_o).max() / gmax:.2e}"
+        print(f"[adam vs oracle] step {k + 1}: u rel {np.abs(N(u) - u_o).max() / max(1.0, np.abs(u_o).max()):.2e}, grad rel "
+              f"{np.abs(N(g) - g_o).max() / gmax:.2e}, p abs {np.abs(N(p) - st.p).max():.2e}, m rel "
+              f"{np.abs(N(m) - st.m).max() / max(1.0, np.abs(st.m).max()):.2e}")
         # |dp| <= |dg| / eps (eps = 1e-8, lr = 1): the first step (v = 0) amplifies fp32 gradient noise
         assert np.abs(N(p) - st.p).max() <= (2e-4 if k == 0 else 2e-5), f"adam p step {k + 1}: {np.abs(N(p) - st.p).max():.2e}"
         assert np.abs(N(m) - st.m).max() <= 1e-6 * max(1.0, np.abs(st.m).max())

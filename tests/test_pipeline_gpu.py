@@ -9,6 +9,15 @@ KW_A = dict(mind_r=1, mind_d=2, lambda_weight=1.25, grid_sp=2, disp_hw=3, select
 KW_B = dict(mind_r=1, mind_d=2, lambda_weight=1.25, grid_sp=6, disp_hw=4, selected_smooth=3, grid_sp_adam=2, ic=True)
 
 
+# Teacher-forced Adam step against the reference's own snapshots.  Bounds = 2x what the CUDA path
+# achieves on the B200 (printed by the test; profiles/r2_parity_achieved.txt): the analytic fused gradient sums the 8 corner
+# contributions in a different order from autograd's, and the first step (v = 0: |dp| = |dg| / (|g| + eps) with
+# |g| ~ 1e-7) amplifies that difference.
+TF_GRAD_REL = 5e-6
+TF_P_FIRST = 2e-4
+TF_P_LATER = 2e-5
+
+
 def api():
     from convexadam_b200.convex_adam_MIND import convex_adam_pt
     return convex_adam_pt
@@ -43,8 +52,11 @@ def test_golden_adam_teacher_forced(golden):
         p, m, v = (torch.from_numpy(g[f"adam{k}_{n}"].copy()).to(dev) for n in ("p", "m", "v"))
         u, gr = lib.adam_run(pf, pm, 1.25, p, m, v, k + 1, 1, want_grad=True)
         gref = g[f"adam{k}_g"]
-        assert np.abs(gr.cpu().numpy() - gref).max() <= 5e-6 * np.abs(gref).max()
-        assert np.abs(p.cpu().numpy() - g[f"adam{k}_p_next"]).max() <= (2e-4 if k == 0 else 2e-5)
+        eg = np.abs(gr.cpu().numpy() - gref).max() / np.abs(gref).max()
+        ep = np.abs(p.cpu().numpy() - g[f"adam{k}_p_next"]).max()
+        print(f"[cuda] teacher-forced Adam step {k + 1} vs reference snapshot: grad rel {eg:.2e}, p_next abs {ep:.2e}")
+        assert eg <= TF_GRAD_REL
+        assert ep <= (TF_P_FIRST if k == 0 else TF_P_LATER)
 
 
 def test_fp16_output_rounding_and_types(golden):
