@@ -108,7 +108,8 @@ class Lib:
     def launch_count(self) -> int:
         return int(self.dll.ca_launch_count())
 
-    KERNEL_SLOTS = ("raw_ssd", "box_filters", "blockmin_argmin", "select_pass", "exact_redecision", "adam_grad", "adam_box3")
+    KERNEL_SLOTS = ("raw_ssd", "box_filters", "blockmin_argmin", "select_pass", "exact_redecision", "adam_grad", "adam_box3",
+                    "corr_fused")
 
     def kernel_timing(self, slots=()):
         """Bracket the launches of the named kernels (KERNEL_SLOTS) with CUDA events on the launch stream; () = off."""

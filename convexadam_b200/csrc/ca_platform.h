@@ -17,13 +17,16 @@
 #define CA_DYN_SMEM(T, name)                                        \
     extern __shared__ __align__(16) unsigned char ca_dyn_smem_raw[]; \
     T* name = reinterpret_cast<T*>(ca_dyn_smem_raw)
+#define CA_DYN_SMEM_ALIGNED(T, name, al)                                  \
+    extern __shared__ __align__(al) unsigned char ca_dyn_smem_raw_al[];   \
+    T* name = reinterpret_cast<T*>(ca_dyn_smem_raw_al)
 #endif
 
 #include "../../include/convexadam_b200.h"
 
 void ca_note_launch();   // counts kernel launches (ca_launch_count) -- the bench reports it
 // optional per-kernel timing with CUDA events on the launch stream (common.cu); slots:
-enum { CA_T_RAW = 0, CA_T_BOX = 1, CA_T_BLOCKMIN = 2, CA_T_SELECT = 3, CA_T_FIXUP = 4, CA_T_ADAM_GRAD = 5, CA_T_BOX3 = 6, CA_T_NSLOTS = 8 };
+enum { CA_T_RAW = 0, CA_T_BOX = 1, CA_T_BLOCKMIN = 2, CA_T_SELECT = 3, CA_T_FIXUP = 4, CA_T_ADAM_GRAD = 5, CA_T_BOX3 = 6, CA_T_FUSED = 7, CA_T_NSLOTS = 8 };
 void* ca_timing_begin(int slot, cudaStream_t st);
 void ca_timing_end(void* h, cudaStream_t st);
 
@@ -145,6 +148,29 @@ static __device__ __forceinline__ void ca_mbar_wait(unsigned long long* bar, uns
         "r"(parity)
         : "memory");
 }
+#endif
+
+// ---- mbarriers as producer/consumer hand-offs between warp groups (arrive / wait by different threads) ------------------
+// ca_mbar_* above are only ever used as "everybody waits for a copy" (CA_EMU: a block barrier); these carry the real
+// semantics in both builds.  CA_EMU keeps {pending arrivals, expected arrivals, phase} in the 64-bit word and spins by
+// yielding to the other fibers of the block; a copy completes at issue there, so expect_tx is a plain arrival.
+#if defined(CA_EMU)
+static inline void ca_mbarx_init(unsigned long long* bar, int count) { *bar = ((unsigned long long)count << 32) | ((unsigned long long)count << 1); }
+static inline void ca_mbarx_arrive(unsigned long long* bar) {
+    unsigned long long v = *bar;
+    unsigned pending = (unsigned)((v >> 1) & 0x7fffffffu), phase = (unsigned)(v & 1u), count = (unsigned)(v >> 32);
+    if (--pending == 0) { pending = count; phase ^= 1u; }
+    *bar = ((unsigned long long)count << 32) | ((unsigned long long)pending << 1) | phase;
+}
+static inline void ca_mbarx_expect_tx(unsigned long long* bar, unsigned bytes) { (void)bytes; ca_mbarx_arrive(bar); }
+static inline void ca_mbarx_wait(unsigned long long* bar, unsigned parity) { while ((unsigned)(*bar & 1u) == (parity & 1u)) emu::yield(); }
+#else
+static __device__ __forceinline__ void ca_mbarx_init(unsigned long long* bar, int count) { ca_mbar_init(bar, count); }
+static __device__ __forceinline__ void ca_mbarx_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ca_smem_u32(bar)) : "memory");
+}
+static __device__ __forceinline__ void ca_mbarx_expect_tx(unsigned long long* bar, unsigned bytes) { ca_mbar_expect_tx(bar, bytes); }
+static __device__ __forceinline__ void ca_mbarx_wait(unsigned long long* bar, unsigned parity) { ca_mbar_wait(bar, parity); }
 #endif
 
 // ---- packed fp32 pairs (sm_100: add/sub/mul/fma .rn.f32x2): IEEE round-to-nearest per lane, i.e. bit-identical to the

@@ -26,6 +26,9 @@
 int ca_launch_cost_argmin(const float* ssd, int64_t n, int L, const float* mesh, const float* soft, float coeff,
                           unsigned long long* keys, cudaStream_t st);
 int ca_launch_keys_to_i64(const unsigned long long* keys, int64_t n, int64_t* out, cudaStream_t st);
+// correlate_fused.cu: the whole stage in one kernel (certified mode); CA_ERR_UNSUPPORTED = take the two-kernel path
+int ca_launch_corr_fused(const float* fix, const float* mov, int C, int h, int w, int d, int pitch, int disp_hw, int xb, int xe,
+                         float* ssd, cudaStream_t st);
 
 // out (C, h+2p, w+2p, pitch) <- in (C,h,w,d), zero elsewhere (F.pad at utils.py:76 plus 16-byte row alignment)
 __global__ void __launch_bounds__(256) k_pad_features(const float* __restrict__ in, int C, int h, int w, int d, int p,
@@ -787,6 +790,23 @@ static int correlate_impl(bool fast, const float* fix, const float* mov, int C, 
     float* movp = (float*)(ws + p.off_mov);
     float* raw = (float*)(ws + p.off_raw);
     const int S = p.S, npairs = S * S;
+    if (fast) {
+        // One fused kernel (correlate_fused.cu) straight from the unpadded feature volumes: tensor-map TMA needs rows of a
+        // multiple of 4 floats on 16-byte aligned bases, anything else goes through a pitched copy first.
+        const float *ff = fix, *mm = mov;
+        const bool direct = p.dF == d && ((((uintptr_t)fix) | ((uintptr_t)mov)) & 15) == 0;
+        int rc = CA_OK;
+        if (!direct) {
+            const int64_t tf = (int64_t)C * h * w * p.dF;
+            const unsigned nb = (unsigned)ca_min((int)ca_divup(tf, 256), 148 * 16);
+            CA_LAUNCH(k_pad_features, dim3(nb), dim3(256), 0, st, fix, C, h, w, d, 0, p.dF, fixp);
+            CA_LAUNCH(k_pad_features, dim3(nb), dim3(256), 0, st, mov, C, h, w, d, 0, p.dF, movp);
+            CA_CHECK_LAUNCH("correlate/pitch");
+            ff = fixp; mm = movp;
+        }
+        rc = ca_launch_corr_fused(ff, mm, C, h, w, d, p.dF, disp_hw, x_begin, x_end, ssd, st);
+        if (rc != CA_ERR_UNSUPPORTED) return rc;
+    }
     {
         const int64_t tf = (int64_t)C * h * w * p.dF, tm = (int64_t)C * (h + 2 * disp_hw) * (w + 2 * disp_hw) * p.dP;
         // the fixed features are used in place when their rows already have the kernels' pitch and alignment

@@ -119,6 +119,7 @@ void* dyn_smem() {
     return (void*)((p + 63) & ~(uintptr_t)63);
 }
 void sync_block() { yield_as(WAIT_BLOCK); }
+void yield() { yield_as(READY); }
 void sync_warp() { yield_as(WAIT_WARP); }
 void* warp_scratch() { return &W.scratch[(W.cur / 32) * 32]; }
 int lane_id() { return W.cur % 32; }

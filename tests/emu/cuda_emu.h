@@ -52,6 +52,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
 void* dyn_smem();
 void sync_block();
 void sync_warp();
+void yield();           // give the other fibers of the block a turn (spin-wait on shared state)
 void* warp_scratch();   // 32 x 8 bytes for the calling thread's warp
 int lane_id();
 int warp_alive_mask_has(int lane);
@@ -61,6 +62,7 @@ void ca_note_launch();
 #define CA_LAUNCH(kernel, grid, block, smem, stream, ...) \
     (ca_note_launch(), emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); }))
 #define CA_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emu::dyn_smem())
+#define CA_DYN_SMEM_ALIGNED(T, name, al) T* name = reinterpret_cast<T*>(emu::dyn_smem())
 
 static inline void __syncthreads() { emu::sync_block(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::sync_warp(); }

@@ -309,16 +309,18 @@ def check_adam(lib, device, C=12, shape=(10, 12, 14), lam=1.25, steps=(1, 2, 7))
             continue
         p, m, v = T(p0, device), T(m0, device), T(v0, device)
         u, g = lib.adam_run(T(fix, device), T(mov, device), lam, p, m, v, k + 1, 1, want_grad=True)
-        # u = B^3 p: the fused separable kernels associate the 27x27x27 taps differently from torch's ordered sums
-        assert np.abs(N(u) - u_o).max() <= 2e-6 * max(1.0, np.abs(u_o).max()), f"adam u step {k + 1}: {np.abs(N(u) - u_o).max():.2e}"
+        # u = B^3 p: the fused separable kernels associate the 27x27x27 taps differently from torch's ordered sums.
+        # Bounds = ~2x what the B200 achieves (u 2.7e-7, grad 6.6e-7, p 1.3e-4 first / 2.2e-6 later, m 1.5e-11 relative;
+        # printed below, kept in profiles/r2_parity_achieved.txt)
+        assert np.abs(N(u) - u_o).max() <= 6e-7 * max(1.0, np.abs(u_o).max()), f"adam u step {k + 1}: {np.abs(N(u) - u_o).max():.2e}"
         gmax = np.abs(g_o).max()
-        assert np.abs(N(g) - g_o).max() <= 5e-6 * gmax, f"adam grad step {k + 1}: {np.abs(N(g) - g_o).max() / gmax:.2e}"
+        assert np.abs(N(g) - g_o).max() <= 1.4e-6 * gmax, f"adam grad step {k + 1}: {np.abs(N(g) - g_o).max() / gmax:.2e}"
         print(f"[adam vs oracle] step {k + 1}: u rel {np.abs(N(u) - u_o).max() / max(1.0, np.abs(u_o).max()):.2e}, grad rel "
               f"{np.abs(N(g) - g_o).max() / gmax:.2e}, p abs {np.abs(N(p) - st.p).max():.2e}, m rel "
               f"{np.abs(N(m) - st.m).max() / max(1.0, np.abs(st.m).max()):.2e}")
         # |dp| <= |dg| / eps (eps = 1e-8, lr = 1): the first step (v = 0) amplifies fp32 gradient noise
-        assert np.abs(N(p) - st.p).max() <= (2e-4 if k == 0 else 2e-5), f"adam p step {k + 1}: {np.abs(N(p) - st.p).max():.2e}"
-        assert np.abs(N(m) - st.m).max() <= 1e-6 * max(1.0, np.abs(st.m).max())
+        assert np.abs(N(p) - st.p).max() <= (2e-4 if k == 0 else 5e-6), f"adam p step {k + 1}: {np.abs(N(p) - st.p).max():.2e}"
+        assert np.abs(N(m) - st.m).max() <= 1e-9 * max(1.0, np.abs(st.m).max())
     # several iterations in one call == the same iterations one call at a time
     p0 = (r.randn(3, *shape) * 1.5).astype(np.float32)
     pa, ma, va = T(p0, device), T(np.zeros_like(p0), device), T(np.zeros_like(p0), device)

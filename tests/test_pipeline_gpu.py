@@ -13,9 +13,9 @@ KW_B = dict(mind_r=1, mind_d=2, lambda_weight=1.25, grid_sp=6, disp_hw=4, select
 # achieves on the B200 (printed by the test; profiles/r2_parity_achieved.txt): the analytic fused gradient sums the 8 corner
 # contributions in a different order from autograd's, and the first step (v = 0: |dp| = |dg| / (|g| + eps) with
 # |g| ~ 1e-7) amplifies that difference.
-TF_GRAD_REL = 5e-6
-TF_P_FIRST = 2e-4
-TF_P_LATER = 2e-5
+TF_GRAD_REL = 6e-7      # achieved 3.0e-7
+TF_P_FIRST = 2e-4       # achieved 1.28e-4 (first step, v = 0)
+TF_P_LATER = 2e-6       # achieved 4.8e-7 / 9.5e-7
 
 
 def api():
