@@ -215,85 +215,97 @@ __global__ void __launch_bounds__(256, 2) k_raw_ssd_staged(RawStagedArgs a) {
     const int ty = (int)threadIdx.y, z0 = 4 * (int)threadIdx.x;
     const int y = y0t + ty;
     const bool active = y < a.w;
+    // Interior rows only.  The 4+4 zero pad columns of a row (read by the box kernels without bounds checks) are written
+    // here by the row's edge threads; the halo ROWS (-2,-1,w,w+1) are never written: the fast box kernel does not copy
+    // them (its stages stay zero there) and the exact path zeroes them once per call (k_zero_raw_halo).  Round 1 wrote
+    // the halo rows from here too: those predicated stores were half of the kernel's executed instructions.
     const bool lpad = threadIdx.x == 0, rpad = threadIdx.x == blockDim.x - 1;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    // The chunk buffer's zero halo (rows -2,-1,w,w+1 and the 4+4 pad columns of every row, read by the box kernels without
-    // bounds checks) is written here, next to the data: the edge threads of a row add the pad quads, the first / last row
-    // tile adds the two halo rows above / below the volume.
-    const bool top = y0t == 0 && ty < 2, bottom = y0t + CA_RAW_TY >= a.w && ty < 2;
     const float* fs = sfix + ty * a.dF + z0;
-    float* slice0 = a.raw + (int64_t)blockIdx.z * a.rl.xPitch + 4 + z0;           // buffer row 0 of this x, column of z0
-    float* rp0 = slice0 + (int64_t)(y + 2) * a.rl.rowPitch;
+    float* rp0 = a.raw + (int64_t)blockIdx.z * a.rl.xPitch + 4 + z0 + (int64_t)(y + 2) * a.rl.rowPitch;
+    if (!active) return;
     for (int kWl = 0; kWl < a.NW; ++kWl) {
-        // the 4 voxels x S shifts as packed pairs: acc2[k][p] = voxels (2p, 2p+1) of shift k
-        float2 acc2[S][2];
+        float acc[S][4];
+        const float* ms = smov + (ty + kWl) * a.dP + z0;
+        if (FAST) {
+            // packed pairs of NEIGHBOURING LABELS of one voxel: (m[z+k] - f[z], m[z+k+1] - f[z]) is an aligned register pair of
+            // the loaded moving row whenever z+k is even, so voxel v pairs the labels (0,1),(2,3).. (v even) or (1,2),(3,4)..
+            // (v odd) and keeps one single label; the fixed value is a broadcast operand.  No operand shuffling.
+            float2 pr[4][S / 2];
+            float sg[4];
 #pragma unroll
-        for (int k = 0; k < S; ++k) acc2[k][0] = acc2[k][1] = make_float2(0.f, 0.f);
-        if (active) {
-            const float* ms = smov + (ty + kWl) * a.dP + z0;
+            for (int v = 0; v < 4; ++v) {
+                sg[v] = 0.f;
+#pragma unroll
+                for (int q = 0; q < S / 2; ++q) pr[v][q] = make_float2(0.f, 0.f);
+            }
+#pragma unroll 2
             for (int c = 0; c < a.C; ++c) {
                 const float4 f4 = *reinterpret_cast<const float4*>(fs + c * fch);
-                const float2 f2[2] = {make_float2(f4.x, f4.y), make_float2(f4.z, f4.w)};
-                float m[NM + 1];
+                const float f[4] = {f4.x, f4.y, f4.z, f4.w};
+                float m[NM];
 #pragma unroll
                 for (int j = 0; j < NM / 4; ++j) {
                     const float4 m4 = *reinterpret_cast<const float4*>(ms + c * mch + 4 * j);
                     m[4 * j + 0] = m4.x; m[4 * j + 1] = m4.y; m[4 * j + 2] = m4.z; m[4 * j + 3] = m4.w;
                 }
-                m[NM] = 0.f;
-                // pairs at even offsets come straight from the loaded quads, pairs at odd offsets from a copy shifted by one
-                float2 me[NM / 2], mo[NM / 2];
 #pragma unroll
-                for (int j = 0; j < NM / 2; ++j) { me[j] = make_float2(m[2 * j], m[2 * j + 1]); mo[j] = make_float2(m[2 * j + 1], m[2 * j + 2]); }
+                for (int v = 0; v < 4; ++v) {
+                    const float2 fv = make_float2(f[v], f[v]);
+                    const int par = v & 1;
+#pragma unroll
+                    for (int q = 0; q < S / 2; ++q) {
+                        const int i0 = v + 2 * q + par;
+                        const float2 df = ca_sub2(make_float2(m[i0], m[i0 + 1]), fv);
+                        pr[v][q] = ca_fma2(df, df, pr[v][q]);
+                    }
+                    const float ds = m[v + (par ? 0 : S - 1)] - f[v];
+                    sg[v] = __fmaf_rn(ds, ds, sg[v]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < S; ++k)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    if ((v & 1) == 0) acc[k][v] = k == S - 1 ? sg[v] : ((k & 1) ? pr[v][k >> 1].y : pr[v][k >> 1].x);
+                    else acc[k][v] = k == 0 ? sg[v] : (((k - 1) & 1) ? pr[v][(k - 1) >> 1].y : pr[v][(k - 1) >> 1].x);
+                }
+        } else {
+            // exact mode stays scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (even through an fma with a
+            // -0 addend), which it never does for the scalar _rn intrinsics
+#pragma unroll
+            for (int k = 0; k < S; ++k)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[k][i] = 0.f;
+            for (int c = 0; c < a.C; ++c) {
+                const float4 f4 = *reinterpret_cast<const float4*>(fs + c * fch);
+                const float f[4] = {f4.x, f4.y, f4.z, f4.w};
+                float m[NM];
+#pragma unroll
+                for (int j = 0; j < NM / 4; ++j) {
+                    const float4 m4 = *reinterpret_cast<const float4*>(ms + c * mch + 4 * j);
+                    m[4 * j + 0] = m4.x; m[4 * j + 1] = m4.y; m[4 * j + 2] = m4.z; m[4 * j + 3] = m4.w;
+                }
 #pragma unroll
                 for (int k = 0; k < S; ++k)
 #pragma unroll
-                    for (int pp = 0; pp < 2; ++pp) {
-                        const int j = 2 * pp + k;                       // first moving value of the pair
-                        const float2 mv = (j & 1) ? mo[j >> 1] : me[j >> 1];
-                        if (FAST) {
-                            const float2 df = ca_sub2(f2[pp], mv);
-                            acc2[k][pp] = ca_fma2(df, df, acc2[k][pp]);
-                        } else {
-                            // exact mode stays scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (even through
-                            // an fma with a -0 addend), which it never does for the scalar _rn intrinsics
-                            const float dx = __fsub_rn(f2[pp].x, mv.x), dy = __fsub_rn(f2[pp].y, mv.y);
-                            acc2[k][pp].x = __fadd_rn(acc2[k][pp].x, __fmul_rn(dx, dx));
-                            acc2[k][pp].y = __fadd_rn(acc2[k][pp].y, __fmul_rn(dy, dy));
-                        }
+                    for (int i = 0; i < 4; ++i) {
+                        const float df = __fsub_rn(f[i], m[i + k]);
+                        acc[k][i] = __fadd_rn(acc[k][i], __fmul_rn(df, df));
                     }
             }
         }
-        float acc[S][4];
-#pragma unroll
-        for (int k = 0; k < S; ++k) { acc[k][0] = acc2[k][0].x; acc[k][1] = acc2[k][0].y; acc[k][2] = acc2[k][1].x; acc[k][3] = acc2[k][1].y; }
-        const int64_t poff = (int64_t)(kWl * S + kH) * S * a.rl.plane;
+        float* rp = rp0 + (int64_t)(kWl * S + kH) * S * a.rl.plane;
 #pragma unroll
         for (int k = 0; k < S; ++k) {
-            const int64_t pk = poff + k * a.rl.plane;
-            if (active) {
-                float4 o;
-                o.x = (z0 + 0 < a.d) ? acc[k][0] : 0.f;
-                o.y = (z0 + 1 < a.d) ? acc[k][1] : 0.f;
-                o.z = (z0 + 2 < a.d) ? acc[k][2] : 0.f;
-                o.w = (z0 + 3 < a.d) ? acc[k][3] : 0.f;
-                float* rp = rp0 + pk;
-                ca_st_stream4(reinterpret_cast<float4*>(rp), o);
-                if (lpad) ca_st_stream4(reinterpret_cast<float4*>(rp - 4), zero4);
-                if (rpad) ca_st_stream4(reinterpret_cast<float4*>(rp + 4), zero4);
-            }
-            if (top) {
-                float* hp_ = slice0 + pk + (int64_t)ty * a.rl.rowPitch;
-                ca_st_stream4(reinterpret_cast<float4*>(hp_), zero4);
-                if (lpad) ca_st_stream4(reinterpret_cast<float4*>(hp_ - 4), zero4);
-                if (rpad) ca_st_stream4(reinterpret_cast<float4*>(hp_ + 4), zero4);
-            }
-            if (bottom) {
-                float* hp_ = slice0 + pk + (int64_t)(a.w + 2 + ty) * a.rl.rowPitch;
-                ca_st_stream4(reinterpret_cast<float4*>(hp_), zero4);
-                if (lpad) ca_st_stream4(reinterpret_cast<float4*>(hp_ - 4), zero4);
-                if (rpad) ca_st_stream4(reinterpret_cast<float4*>(hp_ + 4), zero4);
-            }
+            float4 o;
+            o.x = (z0 + 0 < a.d) ? acc[k][0] : 0.f;
+            o.y = (z0 + 1 < a.d) ? acc[k][1] : 0.f;
+            o.z = (z0 + 2 < a.d) ? acc[k][2] : 0.f;
+            o.w = (z0 + 3 < a.d) ? acc[k][3] : 0.f;
+            ca_st_stream4(reinterpret_cast<float4*>(rp + k * a.rl.plane), o);
+            if (lpad) ca_st_stream4(reinterpret_cast<float4*>(rp + k * a.rl.plane - 4), zero4);
+            if (rpad) ca_st_stream4(reinterpret_cast<float4*>(rp + k * a.rl.plane + 4), zero4);
         }
     }
 }
@@ -520,9 +532,12 @@ __global__ void __launch_bounds__(512, 1) k_box12_fast(BoxFastArgs a) {
     const int pl = (int)blockIdx.y;
     const int g = pl / a.S, kD = pl - g * a.S;
     const int64_t label = (int64_t)kD * a.S * a.S + a.chunk_start + g;
-    const int nrows = ca_min(RT, a.w + 4 - ty0);         // rows of the tile present in the chunk buffer
-    const unsigned copy_bytes = (unsigned)(nrows * pitch) * 4;
-    const float* src0 = a.raw + (int64_t)pl * a.rl.plane + (int64_t)ty0 * pitch;
+    // tile rows [ty0, ty0+RT) of the chunk buffer (row r <-> y = r-2); only the interior rows [2, w+2) are copied: the halo
+    // rows are not written by the staged raw kernel and stay zero in the stages
+    const int rfirst = ca_max(ty0, 2), rlast = ca_min(ty0 + RT, a.w + 2);
+    const unsigned copy_bytes = (unsigned)((rlast - rfirst) * pitch) * 4;
+    const int stage_off = (rfirst - ty0) * pitch;
+    const float* src0 = a.raw + (int64_t)pl * a.rl.plane + (int64_t)rfirst * pitch;
     // everything that is never copied or written stays zero: missing raw rows, first-box rows outside the volume, pads
     for (int i = tid; i < CA_BOXF_NST * stage_f + 2 * p1_f; i += nthr) sm[i] = 0.f;
     if (tid == 0)
@@ -531,7 +546,7 @@ __global__ void __launch_bounds__(512, 1) k_box12_fast(BoxFastArgs a) {
     if (tid == 0)
         for (int s = 0; s < CA_BOXF_NST && a.r0 + s < a.r1; ++s) {
             ca_mbar_expect_tx(&full[s], copy_bytes);
-            ca_bulk_g2s(sraw + s * stage_f, src0 + (int64_t)s * a.rl.xPitch, copy_bytes, &full[s]);
+            ca_bulk_g2s(sraw + s * stage_f + stage_off, src0 + (int64_t)s * a.rl.xPitch, copy_bytes, &full[s]);
         }
     const bool active1 = rp < a.RP;
     bool w1[2], w2[2];                                   // the thread's first-box rows / output rows exist
@@ -589,7 +604,7 @@ __global__ void __launch_bounds__(512, 1) k_box12_fast(BoxFastArgs a) {
         // every thread is done with stage st: refill it with plane X + NST
         if (tid == 0 && X + CA_BOXF_NST < a.r1) {
             ca_mbar_expect_tx(&full[st], copy_bytes);
-            ca_bulk_g2s(sraw + st * stage_f, src0 + (int64_t)(it + CA_BOXF_NST) * a.rl.xPitch, copy_bytes, &full[st]);
+            ca_bulk_g2s(sraw + st * stage_f + stage_off, src0 + (int64_t)(it + CA_BOXF_NST) * a.rl.xPitch, copy_bytes, &full[st]);
         }
         // ---- second box: box1 plane X-1 in, cost-volume plane X-2 out ----
         if (p1ok) {
@@ -816,7 +831,7 @@ static int correlate_impl(bool fast, const float* fix, const float* mov, int C, 
         CA_CHECK_LAUNCH("correlate/pad");
         // zero the halo rows / pad columns of the chunk buffer once; the raw kernels only ever write interiors
         // (the staged raw kernel writes the halo of its own planes; only the direct kernel needs it done up front)
-        if (!all_chunks_staged(p, C)) {
+        if (!fast || !all_chunks_staged(p, C)) {
             const int64_t nslices = (int64_t)p.G * p.S * (p.r1 - p.r0);
             CA_LAUNCH(k_zero_raw_halo, dim3((unsigned)(nslices < 148 * 32 ? nslices : 148 * 32)), dim3(128), 0, st, raw, nslices, w, p.rl.rowPitch);
             CA_CHECK_LAUNCH("correlate/zero_halo");

@@ -347,10 +347,12 @@ __global__ void __launch_bounds__((CorrFusedGeom<HW, TYO>::NT), 1)
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
 namespace {
-bool fused_enabled() {           // CA_CORR_FUSED=0: A/B switch back to the two-kernel path of correlate.cu
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("CA_CORR_FUSED"); v = (e && atoi(e) == 0) ? 0 : 1; }
-    return v == 1;
+// CA_CORR_FUSED=1 switches the certified mode to this kernel.  Off by default: at 192x160x256 it measures 7.8 ms per
+// direction against the two-kernel path's time (DESIGN.md 4.1 has the numbers and the reason: the kernel is bound by the
+// fp32 FMA lanes, and pays 1.5x the raw arithmetic for its halo).  Read on every call so that tests can toggle it.
+bool fused_enabled() {
+    const char* e = getenv("CA_CORR_FUSED");
+    return e && atoi(e) == 1;
 }
 
 template <int HW, int TYO>

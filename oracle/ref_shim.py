@@ -1,9 +1,11 @@
 """Import the UNMODIFIED reference (multimodallearning/convexAdam) in a container that lacks
 nibabel / SimpleITK.
 
-TEST INFRASTRUCTURE ONLY.  Used (a) by tests/golden/make_golden.py to generate the committed golden
-vectors and (b) by oracle validation scripts.  `/root/reference` does not exist on the GPU box, so
-nothing in the `-m gpu` tests, smoke() or bench.py imports this module.
+TEST / MEASUREMENT INFRASTRUCTURE ONLY.  Used (a) by tests/golden/make_golden*.py to generate the committed golden
+vectors, (b) by oracle validation scripts and (c) by bench.py's reference arm (`--impl reference`) and its
+`reference_torch_cuda` key, which time the reference's own code.  `/root/reference` does not exist on the GPU box:
+there the byte-for-byte copy staged by oracle/stage_reference.py under the git-ignored oracle/_ref/ is used.  Nothing in
+the `-m gpu` tests or smoke() imports this module.
 
 Protocol follows SURVEY.md §8(c): two stub modules in sys.modules, `/root/reference/src` on sys.path.
 """
@@ -11,7 +13,18 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("CONVEXADAM_REFERENCE", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")    # oracle/stage_reference.py (git-ignored copy)
+
+
+def _root():
+    """The reference where its sources lie, else the byte-for-byte copy staged under oracle/_ref/ (the GPU box)."""
+    for r in (os.environ.get("CONVEXADAM_REFERENCE"), "/root/reference", _STAGED):
+        if r and os.path.isdir(os.path.join(r, "src", "convexAdam")):
+            return r
+    return None
+
+
+REFERENCE_ROOT = _root() or "/root/reference"
 
 
 def available() -> bool:
