@@ -63,6 +63,22 @@ def extract_features(img_fixed, img_moving, mind_r, mind_d, use_mask, mask_fixed
 
 
 _COPY_STREAMS = {}
+_FP16_WARNED = False
+
+
+def _warn_fp16_once():
+    """The reference silently switches arithmetic with `dtype`; this package computes in fp32 either way and says so once.
+    (Issued through `warnings` with an explicit filter entry: the reference's blanket `filterwarnings("ignore")`, which
+    this module repeats at import, would otherwise swallow it.)"""
+    global _FP16_WARNED
+    if _FP16_WARNED:
+        return
+    _FP16_WARNED = True
+    with warnings.catch_warnings():
+        warnings.simplefilter("always")
+        warnings.warn("convexadam_b200: dtype=torch.float16 computes features and cost volume in float32 and rounds only the returned "
+                      "field through half (MIND.py:198-200); the reference's half-precision cost volume is not reproduced. "
+                      "Pass dtype=torch.float32 for the parity-pinned path.", RuntimeWarning, stacklevel=3)
 
 
 def _copy_stream(device):
@@ -99,10 +115,14 @@ def convex_adam_pt(
     same field (convexadam_b200/slab.py; for pairs whose cost volume does not fit one GPU).
 
     dtype: float32 computes and returns fp32 values (the reference's CPU policy, parity-pinned against it);
-    float16 (the reference's GPU default) currently keeps the cost volume in fp32 and rounds the returned field
-    through half exactly where the reference does (MIND.py:198-200)."""
+    float16 (the reference's GPU default) keeps features and cost volume in fp32 and rounds the returned field
+    through half exactly where the reference does (MIND.py:198-200): it does NOT reproduce the reference's half
+    arithmetic (MIND.py:58-59,118-119; utils.py:84-85,98-104), whose selections differ from the fp32 ones.  A
+    one-time warning says so; tests/test_reference_cuda_gpu.py measures the distance to the reference's own CUDA fp16 run."""
     device = _require_cuda(device if device is not None else _default_device())
     lib = get_lib()
+    if dtype == torch.float16:
+        _warn_fp16_once()
     img_fixed = validate_image(img_fixed).float()
     img_moving = validate_image(img_moving).float()
     if dtype not in (torch.float16, torch.float32):
