@@ -33,9 +33,13 @@
 
 #include <cstdlib>
 
+// 32 output voxels along D per tile, raw tile 2 + 32 + 2.  (Measured alternative: 28 outputs per tile make the raw tile
+// exactly 8 quads = four raw warps, one per warp scheduler, for TYO = 12: 21 % fewer cycles per step, but 25 % more tiles
+// to cover a 128-voxel row: 7.7 instead of 7.3 ms per direction.)
 #define CF_TZO 32   // output voxels along D per tile
 #define CF_ZR 36    // raw voxels along D per tile (2 + 32 + 2)
 #define CF_NQ 9     // z-quads per raw row
+#define CF_OQ 8     // z-quads per output row
 #define CF_NST 4    // channel groups in flight
 #define CF_CH 6     // channels per staged group
 
@@ -55,21 +59,37 @@ struct CorrFusedGeom {
     static constexpr int TYR = TYO + 4;                          // raw rows
     // TMA boxes start on 16-byte boundaries of the global rows: the fixed box starts 2 voxels before the raw range
     // (z0-4), the moving box MSH voxels before the first displaced voxel (z0-2-HW-MSH, MSH = 0 for hw = 2, 6)
-    static constexpr int FZ = 40;                                // fixed-tile row length
+    static constexpr int FZ = CF_ZR + 4;                         // fixed-tile row length
     static constexpr int MSH = ((-2 - HW) % 4 + 4) % 4;
     static constexpr int NM = (MSH + 4 + 2 * HW + 3) & ~3;       // moving values loaded per thread (aligned quads)
-    static constexpr int MZ = 32 + NM;                           // moving-tile row length
+    static constexpr int MZ = 4 * (CF_NQ - 1) + NM;              // moving-tile row length
     static constexpr int RG = TYO / 4;                           // owner row groups (4 rows each)
     static constexpr int RAW_ITEMS = TYR * CF_NQ;
-    static constexpr int OWN_ITEMS = S * 8 * RG;
+    static constexpr int OWN_ITEMS = S * CF_OQ * RG;
     static constexpr int RAW_WARPS = (RAW_ITEMS + 31) / 32, OWN_WARPS = (OWN_ITEMS + 31) / 32;
-    static constexpr int NT = 32 * (RAW_WARPS + OWN_WARPS);
+    static constexpr int NT = 32 * (RAW_WARPS + OWN_WARPS + 1);       // + the TMA producer warp
     static constexpr int EX_FLOATS = (S * TYR * CF_ZR + 31) & ~31;     // one exchange buffer
     static constexpr int FIX_CH = TYR * FZ, MOV_CH = TYR * MZ;         // floats per channel
     static constexpr int FIX_F = (CF_CH * FIX_CH + 31) & ~31, STAGE_F = FIX_F + ((CF_CH * MOV_CH + 31) & ~31);
     static constexpr unsigned STAGE_BYTES = (unsigned)(CF_CH * (FIX_CH + MOV_CH)) * 4u;
     static constexpr size_t SMEM = ((size_t)2 * EX_FLOATS + (size_t)CF_NST * STAGE_F) * sizeof(float) + 128;   // + barriers
 };
+
+#ifdef CF_PROFILE
+// debug build only (tools/build_cf_profile.sh): cycles of raw warp 0 / owner warp 0 per phase, summed over all CTAs
+__device__ unsigned long long cf_prof[8];
+#define CF_T(var) const long long var = clock64()
+#define CF_ACC(slot, t0, t1) prof[slot] += (unsigned long long)((t1) - (t0))
+extern "C" __attribute__((visibility("default"))) int ca_debug_cf_prof(unsigned long long* out, int reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(out, cf_prof, sizeof(z)) != cudaSuccess) return -1;
+    if (reset) cudaMemcpyToSymbol(cf_prof, z, sizeof(z));
+    return 0;
+}
+#else
+#define CF_T(var)
+#define CF_ACC(slot, t0, t1)
+#endif
 
 // barriers of one CTA: TMA stage s landed / stage s consumed by every raw warp; exchange buffer e written / read
 struct CfBarriers {
@@ -120,24 +140,29 @@ static __device__ __forceinline__ float cf_acc_get(const CfAcc<HW>& a, int v, in
     return k == 0 ? a.s[v] : (((k - 1) & 1) ? a.p[v][(k - 1) >> 1].y : a.p[v][(k - 1) >> 1].x);
 }
 
+// ---- producer role: one thread keeps CF_NST channel groups in flight ------------------------------------------------------
+// group g = (plane X - r0) * NCH + j  ->  channels [6j, 6j+6) of planes X (fixed) and X + kH - hw (moving); channels past C
+// are out of bounds of the tensor map and arrive as zeros (they add (0 - 0)^2)
 template <int HW, int TYO>
-static __device__ __forceinline__ void cf_raw_role(const CaTensorMap* tmF, const CaTensorMap* tmM, const CorrFusedArgs& a,
-                                                   float* ex, float* stages, CfBarriers& bar, int tid, int y0, int z0, int kH, int kW) {
+static __device__ __forceinline__ void cf_producer_role(const CaTensorMap* tmF, const CaTensorMap* tmM, const CorrFusedArgs& a,
+                                                        float* stages, CfBarriers& bar, int y0, int z0, int kH, int kW) {
     typedef CorrFusedGeom<HW, TYO> G;
-    constexpr int S = G::S, TYR = G::TYR, NM = G::NM, MZ = G::MZ, FZ = G::FZ, MSH = G::MSH;
-    const int lane = tid & 31;
-    const int NG = (a.r1 - a.r0) * a.NCH;                                  // channel groups of the whole march
-    // group g = (plane X - r0) * NCH + j  ->  channels [6j, 6j+6) of planes X (fixed) and X + kH - hw (moving); channels past
-    // C are out of bounds of the tensor map and arrive as zeros (they add (0 - 0)^2)
-    auto issue = [&](int g) {
+    const int NG = (a.r1 - a.r0) * a.NCH;
+    for (int g = 0; g < NG; ++g) {
         const int X = a.r0 + g / a.NCH, c0 = (g % a.NCH) * CF_CH, s = g % CF_NST;
+        if (g >= CF_NST) ca_mbarx_wait(&bar.st_free[s], (unsigned)(g / CF_NST - 1) & 1u);   // every raw warp has left its previous use
         float* st = stages + (size_t)s * G::STAGE_F;
         ca_mbarx_expect_tx(&bar.st_full[s], G::STAGE_BYTES);
         ca_tma_load_4d(st, tmF, z0 - 4, y0 - 2, X, c0, &bar.st_full[s]);
-        ca_tma_load_4d(st + G::FIX_F, tmM, z0 - 2 - HW - MSH, y0 - 2 + kW - HW, X + kH - HW, c0, &bar.st_full[s]);
-    };
-    if (tid == 0)
-        for (int g = 0; g < CF_NST && g < NG; ++g) issue(g);
+        ca_tma_load_4d(st + G::FIX_F, tmM, z0 - 2 - HW - G::MSH, y0 - 2 + kW - HW, X + kH - HW, c0, &bar.st_full[s]);
+    }
+}
+
+template <int HW, int TYO>
+static __device__ __forceinline__ void cf_raw_role(const CorrFusedArgs& a, float* ex, float* stages, CfBarriers& bar, int tid, int y0, int z0) {
+    typedef CorrFusedGeom<HW, TYO> G;
+    constexpr int S = G::S, TYR = G::TYR, NM = G::NM, MZ = G::MZ, FZ = G::FZ, MSH = G::MSH;
+    const int lane = tid & 31;
     const bool on = tid < G::RAW_ITEMS;
     const int rr = on ? tid / CF_NQ : 0, rq = on ? tid % CF_NQ : 0;
     bool rzok[4];
@@ -152,6 +177,9 @@ static __device__ __forceinline__ void cf_raw_role(const CaTensorMap* tmF, const
     }
     const int foff = rr * FZ + 4 * rq + 2, moff = rr * MZ + 4 * rq, eoff = rr * CF_ZR + 4 * rq;
     int g = 0;
+#ifdef CF_PROFILE
+    unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     for (int X = a.r0; X < a.r1; ++X) {
         const int it = X - a.r0;
         CfAcc<HW> acc;
@@ -165,7 +193,10 @@ static __device__ __forceinline__ void cf_raw_role(const CaTensorMap* tmF, const
             const int s = g % CF_NST;
             const float* fs = stages + (size_t)s * G::STAGE_F + foff;     // 8-byte aligned: two 64-bit loads
             const float* ms = stages + (size_t)s * G::STAGE_F + G::FIX_F + moff;
+            CF_T(c0);
             ca_mbarx_wait(&bar.st_full[s], (unsigned)(g / CF_NST) & 1u);
+            CF_T(c1);
+            CF_ACC(0, c0, c1);
             if (on) {
                 // all CF_CH channels of the group, fully unrolled: the loads of channel c+1 are issued before the arithmetic of c
                 float2 fa[2], fb[2];
@@ -206,18 +237,20 @@ static __device__ __forceinline__ void cf_raw_role(const CaTensorMap* tmF, const
                     }
                 }
             }
-            // this warp is done with stage s; thread 0 refills the stage of the PREVIOUS group (which every warp has long
-            // left) so that it never waits for the slowest warp of the current one
+            // this warp is done with stage s: the producer warp refills it once every raw warp has said so
             __syncwarp();
+            CF_T(c2);
+            CF_ACC(1, c1, c2);
             if (lane == 0) ca_mbarx_arrive(&bar.st_free[s]);
-            if (tid == 0 && g >= 1 && g - 1 + CF_NST < NG) {
-                ca_mbarx_wait(&bar.st_free[(g - 1) % CF_NST], (unsigned)((g - 1) / CF_NST) & 1u);
-                issue(g - 1 + CF_NST);
-            }
+            CF_T(c3);
+            CF_ACC(2, c2, c3);
         }
         // hand the raw tile of plane X to the owners through exchange buffer it & 1
         const int e = it & 1;
+        CF_T(c4);
         if (it >= 2) ca_mbarx_wait(&bar.ex_free[e], (unsigned)((it >> 1) - 1) & 1u);
+        CF_T(c5);
+        CF_ACC(3, c4, c5);
         if (on) {
             float* exw = ex + e * G::EX_FLOATS + eoff;
 #pragma unroll
@@ -232,7 +265,13 @@ static __device__ __forceinline__ void cf_raw_role(const CaTensorMap* tmF, const
         }
         __syncwarp();
         if (lane == 0) ca_mbarx_arrive(&bar.ex_full[e]);
+        CF_T(c6);
+        CF_ACC(4, c5, c6);
     }
+#ifdef CF_PROFILE
+    if (tid == 0)
+        for (int i = 0; i < 5; ++i) atomicAdd(&cf_prof[i], prof[i]);
+#endif
 }
 
 // ---- owner role: thread (label k, quad zq, 4 rows) of the owner warps ---------------------------------------------------
@@ -284,7 +323,7 @@ static __device__ __forceinline__ void cf_owner_role(const CorrFusedArgs& a, con
     constexpr int S = G::S, TYR = G::TYR;
     const int lane = otid & 31;
     const bool on = otid < G::OWN_ITEMS;
-    const int zq = otid & 7, rg = (otid >> 3) % G::RG, k = on ? (otid >> 3) / G::RG : 0;
+    const int zq = otid % CF_OQ, rg = (otid / CF_OQ) % G::RG, k = on ? (otid / CF_OQ) / G::RG : 0;
     const int oy = y0 + 4 * rg, oz = z0 + 4 * zq;
     float zm[6], ym[6];
 #pragma unroll
@@ -305,12 +344,18 @@ static __device__ __forceinline__ void cf_owner_role(const CorrFusedArgs& a, con
     float* outp = a.ssd + ((label * nx) * a.w + oy) * (int64_t)a.d + oz;     // plane xb of the thread's first row
     const int64_t outPitch = (int64_t)a.w * a.d;
     const int eoff = (k * TYR + 4 * rg) * CF_ZR + 4 * zq;
+#ifdef CF_PROFILE
+    unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     for (int X = a.r0; X <= a.xe + 1; ++X) {
         const int it = X - a.r0, e = it & 1;
         const bool have_raw = X < a.r1;
         const bool p1ok = X - 1 >= a.b0 && X - 1 < a.b1;
         const bool store = X - 2 >= a.xb;
+        CF_T(c0);
         if (have_raw) ca_mbarx_wait(&bar.ex_full[e], (unsigned)(it >> 1) & 1u);
+        CF_T(c1);
+        CF_ACC(5, c0, c1);
         const float* exr = ex + e * G::EX_FLOATS + eoff;
         if (it & 1) cf_owner_step<1, DALIGNED>(exr, have_raw, p1ok, store, hq, ha, zm, ym, outp, a.d, nrows, nz);
         else cf_owner_step<0, DALIGNED>(exr, have_raw, p1ok, store, hq, ha, zm, ym, outp, a.d, nrows, nz);
@@ -329,7 +374,7 @@ __global__ void __launch_bounds__((CorrFusedGeom<HW, TYO>::NT), 1)
     // tensor-map TMA writes need 128-byte aligned destinations: the dynamic window is declared with that alignment (and
     // nothing static precedes it -- the barriers live at its end), so every pointer below keeps its shared address space
     CA_DYN_SMEM_ALIGNED(float, sm, 128);
-    float* ex = sm;                                                       // [2][S][TYR][36]
+    float* ex = sm;                                                       // [2][S][TYR][CF_ZR]
     float* stages = sm + 2 * G::EX_FLOATS;                                // [NST][CH x (fixed tile | moving tile)]
     CfBarriers& bar = *reinterpret_cast<CfBarriers*>(stages + CF_NST * G::STAGE_F);
     const int tid = (int)threadIdx.x;
@@ -341,8 +386,9 @@ __global__ void __launch_bounds__((CorrFusedGeom<HW, TYO>::NT), 1)
         for (int e = 0; e < 2; ++e) { ca_mbarx_init(&bar.ex_full[e], G::RAW_WARPS); ca_mbarx_init(&bar.ex_free[e], G::OWN_WARPS); }
     }
     __syncthreads();
-    if (tid < 32 * G::RAW_WARPS) cf_raw_role<HW, TYO>(&tmF, &tmM, a, ex, stages, bar, tid, y0, z0, pair % G::S, pair / G::S);
-    else cf_owner_role<HW, TYO, DALIGNED>(a, ex, bar, tid - 32 * G::RAW_WARPS, y0, z0, pair);
+    if (tid < 32 * G::RAW_WARPS) cf_raw_role<HW, TYO>(a, ex, stages, bar, tid, y0, z0);
+    else if (tid < 32 * (G::RAW_WARPS + G::OWN_WARPS)) cf_owner_role<HW, TYO, DALIGNED>(a, ex, bar, tid - 32 * G::RAW_WARPS, y0, z0, pair);
+    else if (tid == 32 * (G::RAW_WARPS + G::OWN_WARPS)) cf_producer_role<HW, TYO>(&tmF, &tmM, a, stages, bar, y0, z0, pair % G::S, pair / G::S);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------

@@ -55,3 +55,11 @@ def test_random_small_shapes(lib):
 
 
 def test_field_mean(lib): kc.check_field_mean(lib, DEV)
+
+
+def test_certified_fused_kernel(lib, monkeypatch):
+    """The one-kernel form of ca_correlate_fast (csrc/correlate_fused.cu; opt-in through CA_CORR_FUSED=1): tiles that cross
+    the volume faces, several row / z tiles, d not a multiple of 4, every disp_hw the kernel is instantiated for."""
+    monkeypatch.setenv("CA_CORR_FUSED", "1")
+    kc.check_certified(lib, DEV, cases=((12, 4, 5, 8, 2), (3, 4, 5, 7, 1), (7, 3, 14, 35, 2), (4, 3, 4, 6, 4), (2, 2, 3, 5, 6)))
+    kc.check_certified(lib, DEV, cases=kc.random_small_shapes(55, 6), tie_case=False)

@@ -88,6 +88,24 @@ def test_certified(lib, dev):
     kc.check_certified(lib, dev, cases=((12, 10, 9, 16, 3), (16, 6, 7, 8, 1), (3, 5, 6, 9, 4), (12, 8, 6, 12, 6), (12, 7, 9, 10, 2)))
 
 
+@pytest.fixture
+def fused_correlate(monkeypatch):
+    """CA_CORR_FUSED=1: ca_correlate_fast runs as ONE kernel (csrc/correlate_fused.cu: tensor-map TMA staging, raw SSD, both
+    box filters and the H march fused; opt-in, read on every call)."""
+    monkeypatch.setenv("CA_CORR_FUSED", "1")
+
+
+def test_certified_fused_kernel(lib, dev, fused_correlate):
+    kc.check_certified(lib, dev, cases=((12, 10, 9, 16, 3), (16, 6, 7, 8, 1), (3, 5, 6, 9, 4), (12, 8, 6, 12, 6), (12, 7, 9, 10, 2),
+                                        (12, 9, 30, 70, 2), (5, 5, 14, 33, 5)))
+    kc.check_certified(lib, dev, cases=kc.random_small_shapes(77, 8, max_hw=6), tie_case=False)
+
+
+def test_full_size_fused_kernel_certified_equals_exact(lib, full_volume, fused_correlate):
+    """The fused kernel's volume at BASELINE config 2 size: inside the bound, and the same certified selections."""
+    test_full_size_certified_equals_exact(lib, full_volume)
+
+
 def test_correlate_rejects_bad_arguments(lib, dev):
     from convexadam_b200._native import NativeError
     f = torch.zeros(12, 4, 4, 4, device=dev)
