@@ -41,10 +41,17 @@ __global__ void __launch_bounds__(256) k_planar_to_cl(const float* __restrict__ 
         }
 }
 
-__global__ void __launch_bounds__(128, 5) k_adam_grad(const float* __restrict__ u, const float4* __restrict__ fixcl,
-                                                   const float4* __restrict__ movcl, int CG, AdamGeom g,
+// CGT > 0: the number of 4-channel groups is a compile-time constant (3 for the 12 MIND channels, 4 for 16 labels) and the
+// group loop is unrolled, so that all 8 * CGT corner gathers of a voxel are in flight together (the kernel is bound by the
+// latency of those L2 hits); CGT = 0: any channel count, one group at a time.
+template <int CGT, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_adam_grad(const float* __restrict__ u, const float4* __restrict__ fixcl,
+                                                   const float4* __restrict__ movcl, int CGrt, AdamGeom g,
                                                    const float* __restrict__ g0x, const float* __restrict__ g0y,
                                                    const float* __restrict__ g0z, float* __restrict__ gu) {
+    ca_grid_dep_launch();      // programmatic dependent launch: the next kernel of the iteration may be scheduled ...
+    ca_grid_dep_wait();        // ... and this one reads nothing before its predecessor (u = B^3 p) has completed
+    const int CG = CGT > 0 ? CGT : CGrt;
     const int ha = g.ha, wa = g.wa, da = g.da;
     const int n = g.hl * wa * da;                   // field arrays: window-local indexing
     const int z = (int)(blockIdx.x * blockDim.x + threadIdx.x);
@@ -116,7 +123,8 @@ __global__ void __launch_bounds__(128, 5) k_adam_grad(const float* __restrict__ 
     float gix = 0.f, giy = 0.f, giz = 0.f;
     // (an explicit register double buffer of the next group's gather was measured slower than one more resident CTA)
     float4 val[8], f;
-    for (int cg = 0; cg < CG; ++cg) {
+#pragma unroll
+    for (int cg = 0; cg < (CGT > 0 ? CGT : CG); ++cg) {
 #pragma unroll
         for (int t = 0; t < 8; ++t) val[t] = inb[t] ? __ldg(movcl + off[t] + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
         f = __ldg(fixcl + of * CG + cg);
@@ -143,6 +151,9 @@ __global__ void __launch_bounds__(128, 5) k_adam_grad(const float* __restrict__ 
     gu[o] = g.gscale * giz * g.gmul[0] + greg[0];
 }
 
+#ifndef CA_GRAD_MINB
+#define CA_GRAD_MINB 4
+#endif
 struct AdamScalars { float w_lerp, beta2, one_m_beta2, bc2_sqrt, eps, neg_step_size; };
 
 // torch.optim.Adam single-tensor step (adam.py:528-547), every op rounded as torch's kernels round it
@@ -187,6 +198,8 @@ static __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f,
 // T_H: grid = (ceil(w*nq / 128), H segments, 3 channels); a thread owns (row y, quad q) and the planes [xs, xe)
 template <int LX>
 __global__ void __launch_bounds__(128) k_box3_h(Box3Args a) {
+    ca_grid_dep_launch();
+    ca_grid_dep_wait();
     const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (t >= a.w * a.nq) return;
     const int xs = (int)blockIdx.y * LX, xe = ca_min(a.h, xs + LX);
@@ -218,6 +231,8 @@ __global__ void __launch_bounds__(128) k_box3_h(Box3Args a) {
 // T_W T_D on one plane: grid = (row tiles, h, 3 channels).  Shared memory: two buffers of (Ty + 6) rows x d floats.
 template <bool UPDATE>
 __global__ void __launch_bounds__(256) k_box3_p(Box3Args a) {
+    ca_grid_dep_launch();
+    ca_grid_dep_wait();
     CA_DYN_SMEM(float, sm);
     const int tid = (int)threadIdx.x, nthr = (int)blockDim.x;
     const int ty0 = (int)blockIdx.x * a.Ty;
@@ -330,7 +345,7 @@ static int box3_cubed(const float* in, float* tmp, float* out, int ha, int wa, i
     {
         const dim3 grid((unsigned)ca_divup((int64_t)wa * a.nq, 128), (unsigned)ca_divup(ha, CA_BOX3_LX), 3u);
         auto k = k_box3_h<CA_BOX3_LX>;
-        CA_LAUNCH(k, grid, dim3(128), 0, st, a);
+        CA_LAUNCH_PDL(k, grid, dim3(128), 0, st, a);
         CA_CHECK_LAUNCH("box3_h");
     }
     a.in = tmp; a.out = out;
@@ -341,8 +356,8 @@ static int box3_cubed(const float* in, float* tmp, float* out, int ha, int wa, i
     if (a.Ly < 4) a.Ly = ca_min(4, a.Ty);
     const size_t smem = (size_t)2 * (a.Ty + 6) * da * 4;
     const dim3 grid((unsigned)a.ntiles, (unsigned)ha, 3u);
-    if (upd) { auto k = k_box3_p<true>; CA_SMEM_OPTIN(k, CA_BOX3_SMEM + 6 * 4096); CA_LAUNCH(k, grid, dim3(256), smem, st, a); }
-    else { auto k = k_box3_p<false>; CA_SMEM_OPTIN(k, CA_BOX3_SMEM + 6 * 4096); CA_LAUNCH(k, grid, dim3(256), smem, st, a); }
+    if (upd) { auto k = k_box3_p<true>; CA_SMEM_OPTIN(k, CA_BOX3_SMEM + 6 * 4096); CA_LAUNCH_PDL(k, grid, dim3(256), smem, st, a); }
+    else { auto k = k_box3_p<false>; CA_SMEM_OPTIN(k, CA_BOX3_SMEM + 6 * 4096); CA_LAUNCH_PDL(k, grid, dim3(256), smem, st, a); }
     CA_CHECK_LAUNCH("box3_p");
     return CA_OK;
 }
@@ -411,8 +426,10 @@ extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int
         }
         const int bx = 32, by = 4, bz = 1;      // 32 x 4 voxels per CTA: neighbouring rows share corner gathers in L1
         void* tmg = ca_timing_begin(CA_T_ADAM_GRAD, st);
-        CA_LAUNCH(k_adam_grad, dim3((unsigned)((da + bx - 1) / bx), (unsigned)((wa + by - 1) / by), (unsigned)((hl + bz - 1) / bz)), dim3(bx, by, bz), 0, st, u_out, fixcl, movcl, CG,
-                  g, g0x, g0y, g0z, gu);
+        const dim3 ggrid((unsigned)((da + bx - 1) / bx), (unsigned)((wa + by - 1) / by), (unsigned)((hl + bz - 1) / bz)), gblock(bx, by, bz);
+        // (compile-time group counts with the loop unrolled -- all 24 gathers of a voxel in flight -- were measured slower: 9.5-10.6
+        // against 8.9 ms per 100 iterations; the kernel wants resident warps more than loads per warp)
+        CA_LAUNCH_PDL((k_adam_grad<0, 5>), ggrid, gblock, 0, st, (const float*)u_out, (const float4*)fixcl, (const float4*)movcl, CG, g, g0x, g0y, g0z, gu);
         ca_timing_end(tmg, st);
         CA_CHECK_LAUNCH("adam_grad");
         if (!fast) {

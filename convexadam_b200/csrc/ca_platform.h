@@ -14,6 +14,23 @@
 #include <cstdio>
 #define CA_LAUNCH(kernel, grid, block, smem, stream, ...) \
     (ca_note_launch(), kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__))
+// Programmatic dependent launch: the kernel is queued behind its predecessor on the stream but its CTAs may be scheduled
+// while the predecessor drains; it must call ca_grid_dep_wait() before touching anything the predecessor wrote (or reads).
+// Chains of short dependent kernels (the Adam loop: 5 launches of 8-50 us per iteration) lose their launch gaps this way.
+template <class... KArgs, class... Args>
+static inline cudaError_t ca_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#define CA_LAUNCH_PDL(kernel, grid, block, smem, stream, ...) \
+    (ca_note_launch(), (void)ca_launch_pdl(kernel, (grid), (block), (smem), (stream), __VA_ARGS__))
+static __device__ __forceinline__ void ca_grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+static __device__ __forceinline__ void ca_grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #define CA_DYN_SMEM(T, name)                                        \
     extern __shared__ __align__(16) unsigned char ca_dyn_smem_raw[]; \
     T* name = reinterpret_cast<T*>(ca_dyn_smem_raw)

@@ -61,6 +61,9 @@ int warp_alive_mask_has(int lane);
 void ca_note_launch();
 #define CA_LAUNCH(kernel, grid, block, smem, stream, ...) \
     (ca_note_launch(), emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); }))
+#define CA_LAUNCH_PDL CA_LAUNCH
+static inline void ca_grid_dep_wait() {}
+static inline void ca_grid_dep_launch() {}
 #define CA_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emu::dyn_smem())
 #define CA_DYN_SMEM_ALIGNED(T, name, al) T* name = reinterpret_cast<T*>(emu::dyn_smem())
 
