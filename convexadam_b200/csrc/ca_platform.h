@@ -120,6 +120,30 @@ static __device__ __forceinline__ float ca_ld_stream1(const float* p) {
     return *p;
 #endif
 }
+// 128-bit read-only loads with an L2 eviction priority (createpolicy + ld.global.nc.L2::cache_hint): `first` for data read
+// once per pass (it must not push the re-used working set out of L2), `last` for the working set itself
+#if defined(__CUDA_ARCH__)
+static __device__ __forceinline__ unsigned long long ca_l2_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+static __device__ __forceinline__ unsigned long long ca_l2_policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+static __device__ __forceinline__ float4 ca_ld_hint4(const float4* ptr, unsigned long long policy) {
+    float4 r;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(ptr), "l"(policy));
+    return r;
+}
+#else
+static inline unsigned long long ca_l2_policy_evict_first() { return 0; }
+static inline unsigned long long ca_l2_policy_evict_last() { return 0; }
+static inline float4 ca_ld_hint4(const float4* ptr, unsigned long long) { return *ptr; }
+#endif
+
 // streaming (write-once) 128-bit store: evict-first, the cost volume must not push the working set out of L2
 static __device__ __forceinline__ void ca_st_stream4(float4* p, const float4& v) {
 #if defined(__CUDA_ARCH__)
