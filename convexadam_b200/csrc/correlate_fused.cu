@@ -238,10 +238,9 @@ static __device__ __forceinline__ void cf_raw_role(const CorrFusedArgs& a, float
                 }
             }
             // this warp is done with stage s: the producer warp refills it once every raw warp has said so
-            __syncwarp();
             CF_T(c2);
             CF_ACC(1, c1, c2);
-            if (lane == 0) ca_mbarx_arrive(&bar.st_free[s]);
+            ca_mbarx_arrive(&bar.st_free[s]);               // every thread arrives for its own reads (release)
             CF_T(c3);
             CF_ACC(2, c2, c3);
         }
@@ -263,8 +262,7 @@ static __device__ __forceinline__ void cf_raw_role(const CorrFusedArgs& a, float
                 *reinterpret_cast<float4*>(exw + k * (TYR * CF_ZR)) = o;
             }
         }
-        __syncwarp();
-        if (lane == 0) ca_mbarx_arrive(&bar.ex_full[e]);
+        ca_mbarx_arrive(&bar.ex_full[e]);                   // every thread arrives for its own writes (release)
         CF_T(c6);
         CF_ACC(4, c5, c6);
     }
@@ -359,10 +357,7 @@ static __device__ __forceinline__ void cf_owner_role(const CorrFusedArgs& a, con
         const float* exr = ex + e * G::EX_FLOATS + eoff;
         if (it & 1) cf_owner_step<1, DALIGNED>(exr, have_raw, p1ok, store, hq, ha, zm, ym, outp, a.d, nrows, nz);
         else cf_owner_step<0, DALIGNED>(exr, have_raw, p1ok, store, hq, ha, zm, ym, outp, a.d, nrows, nz);
-        if (have_raw) {
-            __syncwarp();
-            if (lane == 0) ca_mbarx_arrive(&bar.ex_free[e]);
-        }
+        if (have_raw) ca_mbarx_arrive(&bar.ex_free[e]);     // every thread arrives for its own reads
         if (store) outp += outPitch;
     }
 }
@@ -382,8 +377,8 @@ __global__ void __launch_bounds__((CorrFusedGeom<HW, TYO>::NT), 1)
     const int y0 = ty * TYO, z0 = tz * CF_TZO;
     const int pair = (int)blockIdx.y;
     if (tid == 0) {
-        for (int s = 0; s < CF_NST; ++s) { ca_mbarx_init(&bar.st_full[s], 1); ca_mbarx_init(&bar.st_free[s], G::RAW_WARPS); }
-        for (int e = 0; e < 2; ++e) { ca_mbarx_init(&bar.ex_full[e], G::RAW_WARPS); ca_mbarx_init(&bar.ex_free[e], G::OWN_WARPS); }
+        for (int s = 0; s < CF_NST; ++s) { ca_mbarx_init(&bar.st_full[s], 1); ca_mbarx_init(&bar.st_free[s], 32 * G::RAW_WARPS); }
+        for (int e = 0; e < 2; ++e) { ca_mbarx_init(&bar.ex_full[e], 32 * G::RAW_WARPS); ca_mbarx_init(&bar.ex_free[e], 32 * G::OWN_WARPS); }
     }
     __syncthreads();
     if (tid < 32 * G::RAW_WARPS) cf_raw_role<HW, TYO>(a, ex, stages, bar, tid, y0, z0);

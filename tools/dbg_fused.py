@@ -9,6 +9,7 @@ shape = tuple(int(v) for v in sys.argv[1:5]) if len(sys.argv) > 4 else (12, 7, 2
 hw = int(sys.argv[5]) if len(sys.argv) > 5 else 2
 r = np.random.RandomState(0)
 fix = torch.from_numpy(r.rand(*shape).astype(np.float32)).to(dev); mov = torch.from_numpy(r.rand(*shape).astype(np.float32)).to(dev)
+os.environ.setdefault("CA_CORR_FUSED", "1")
 a, _ = lib.correlate(fix, mov, hw, fast=True)
 torch.cuda.synchronize()
 print("fused ok; max", float(a.max()))
