@@ -162,6 +162,10 @@ class Lib:
         k = (key, str(device))
         if k not in self._consts:
             self._consts[k] = tuple(x.to(device) for x in maker())
+            # first use only: the pageable host-to-device copies above are ordered on the creating stream alone, while the
+            # cached tensors are later read from any stream (pipelined batches, the two-stream convex stage)
+            if torch.device(device).type == "cuda":
+                torch.cuda.current_stream(device).synchronize()
         return self._consts[k]
 
     def identity_axes(self, h, w, d, device):

@@ -47,7 +47,13 @@ def coupled_convex(ssd, ssd_argmin, disp_mesh_t, grid_sp, shape):
     if S * S * S != L or S % 2 == 0:
         raise ValueError("coupled_convex: ssd.shape[0] must be (2*disp_hw+1)^3")
     dt = ssd.dtype
-    soft = lib.coupled_convex(_f32(ssd), ssd_argmin, _f32(disp_mesh_t).reshape(3, -1), (S - 1) // 2)
+    ssd32 = _f32(ssd)
+    # the kernels order (cost, label) pairs by the cost's bit pattern, which is the numerical order for non-negative floats
+    # only: SSD costs are non-negative by construction, anything else (or a NaN) is rejected here instead of mis-sorted
+    lo = ssd32.min()
+    if not bool(lo >= 0):
+        raise ValueError(f"coupled_convex: ssd must be non-negative (sum of squared differences); got min {float(lo)}")
+    soft = lib.coupled_convex(ssd32, ssd_argmin, _f32(disp_mesh_t).reshape(3, -1), (S - 1) // 2)
     return (soft if dt == torch.float32 else soft.to(dt)).unsqueeze(0)
 
 

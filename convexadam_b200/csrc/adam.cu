@@ -396,7 +396,9 @@ extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int
     CA_CHECK_ARG(C > 0 && C <= 128 && ha > 1 && wa > 1 && da > 1, "adam_run: bad dims (1..128 channels, each Adam-grid axis >= 2)");
     CA_CHECK_ARG(lo >= 0 && hi <= ha && lo < hi, "adam_run: bad window [%d, %d) of %d planes", lo, hi, ha);
     CA_CHECK_ARG(first_step >= 1 && niter >= 0, "adam_run: bad step range");
-    CA_CHECK_ARG((int64_t)ha * wa * da * ((C + 3) / 4) < (1ll << 31) && wa < 65536 && ha < 65536, "adam_run: grid too large");
+    // the kernels index the planar (3, n) fields and the (n, CG) feature groups with 32-bit integers
+    CA_CHECK_ARG((int64_t)ha * wa * da * ((C + 3) / 4) < (1ll << 31) && (int64_t)3 * ha * wa * da < (1ll << 31) && wa < 65536 && ha < 65536,
+                 "adam_run: grid too large");
     if (workspace_bytes < ca_adam_window_workspace_bytes(C, ha, wa, da, lo, hi)) {
         ca_set_error("adam_run: workspace too small");
         return CA_ERR_WORKSPACE;

@@ -105,10 +105,14 @@ __global__ void __launch_bounds__(256) k_keys_to_i64(const unsigned long long* _
     for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x)
         out[o] = (int64_t)(keys[o] & 0xffffffffull);
 }
-__global__ void __launch_bounds__(256) k_i64_to_keys(const int64_t* __restrict__ in, int64_t n,
+// caller-supplied labels (the public coupled_convex operator takes any int64 tensor): clamped into [0, L) so that the
+// pruned passes, which read ssd[label * n + v], can never leave the volume (the reference would raise an IndexError)
+__global__ void __launch_bounds__(256) k_i64_to_keys(const int64_t* __restrict__ in, int64_t n, int L,
                                                      unsigned long long* __restrict__ keys) {
-    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x)
-        keys[o] = (unsigned long long)in[o] & 0xffffffffull;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t l = in[o];
+        keys[o] = (unsigned long long)(l < 0 ? 0 : (l >= L ? L - 1 : l));
+    }
 }
 
 // ---- certified selection from an approximate cost volume -------------------------------------------------------------
@@ -121,6 +125,10 @@ __global__ void __launch_bounds__(256) k_i64_to_keys(const int64_t* __restrict__
 // hundred per million) are re-decided by k_cc_fixup, which evaluates the candidates' costs in the reference's exact
 // operation order straight from the feature volumes.  The selections -- and with them disp_soft -- are the
 // reference's bit for bit; only the cost volume itself is approximate.
+// (The relative bound assumes no term df^2 underflows to a subnormal or to zero -- underflow would add an absolute error
+// the band does not cover.  MIND descriptors cannot get there: every voxel has a channel equal to exp(0) = 1, differences
+// below 2^-63 do not occur between values in [0,1] quantised to 2^-24, and an exactly zero cost is exact in both
+// arithmetics.  Weighted one-hot label features (values 0 or ~10) cannot either; that path takes the exact volume anyway.)
 static __device__ __forceinline__ float ca_band_hi(float c) { return __fmul_ru(c, 1.0f + 0x1p-16f); }
 
 struct FixupArgs {
@@ -827,7 +835,7 @@ extern "C" int ca_coupled_convex(const float* ssd, const int64_t* argmin, const 
     const bool prune = cc_prune_enabled();
     int rc;
     // argmin == NULL: the plain argmin of utils.py:87 is taken here, in the same pass that builds the block minima
-    if (argmin) CA_LAUNCH(k_i64_to_keys, dim3(small_grid(n)), dim3(256), 0, st, argmin, n, keys);
+    if (argmin) CA_LAUNCH(k_i64_to_keys, dim3(small_grid(n)), dim3(256), 0, st, argmin, n, L, keys);
     float4* boxes = cc_boxes_of(bmin, n, S);
     if (prune) {
         if ((rc = ca_launch_blockmin_argmin(ssd, n, S, bmin, argmin ? nullptr : keys, st)) != CA_OK) return rc;
@@ -977,7 +985,7 @@ extern "C" int ca_cc_select(const float* ssd, int64_t n, int disp_hw, const floa
     unsigned long long* keys = (unsigned long long*)workspace;
     int rc;
     if (bmin && cc_prune_enabled()) {
-        CA_LAUNCH(k_i64_to_keys, dim3(small_grid(n)), dim3(256), 0, st, prev, n, keys);
+        CA_LAUNCH(k_i64_to_keys, dim3(small_grid(n)), dim3(256), 0, st, prev, n, S * S * S, keys);
         CA_CHECK_LAUNCH("cc_select/keys");
         float4* boxes = (float4*)(((uintptr_t)(keys + n) + 255) & ~(uintptr_t)255);
         if ((rc = ca_launch_mesh_boxes(mesh, S, boxes, st)) != CA_OK) return rc;
@@ -1059,7 +1067,7 @@ extern "C" int ca_cc_select_certified(const float* ssd, int64_t n, int disp_hw, 
         ca_set_error("cc_select_certified: memset failed");
         return CA_ERR_LAUNCH;
     }
-    CA_LAUNCH(k_i64_to_keys, dim3(small_grid(n)), dim3(256), 0, st, prev, n, c.keys);
+    CA_LAUNCH(k_i64_to_keys, dim3(small_grid(n)), dim3(256), 0, st, prev, n, S * S * S, c.keys);
     CA_CHECK_LAUNCH("cc_select_certified/keys");
     int rc;
     if ((rc = ca_launch_mesh_boxes(mesh, S, c.boxes, st)) != CA_OK) return rc;

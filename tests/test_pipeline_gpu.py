@@ -194,3 +194,41 @@ def test_translation_core_equals_reference_formula():
         assert np.abs(got - want_mean).max() <= 1e-9
         assert convex_adam_translation_arrays(fixed, moving, spacing, s, **kw) == want_xyz
     assert np.abs(want_mean - np.array([3.0, -2.0, 1.0])).max() < 0.5
+
+
+def test_apply_convex_integer_images_keep_their_dtype():
+    """scipy.ndimage.map_coordinates (reference apply_convex.py:21-23) returns the input's dtype: integer images are
+    interpolated in float64 and rounded back."""
+    from scipy.ndimage import map_coordinates
+    from convexadam_b200.apply_convex import apply_convex
+    rs = np.random.RandomState(3)
+    moving = rs.randint(-500, 1500, size=(12, 10, 14)).astype(np.int16)
+    disp = rs.randn(12, 10, 14, 3) * 1.7
+    ident = np.meshgrid(np.arange(12), np.arange(10), np.arange(14), indexing="ij")
+    want = map_coordinates(moving, np.stack([disp[..., k] + ident[k] for k in range(3)], 0), order=1)
+    got = apply_convex(disp, moving)
+    assert got.dtype == np.int16 and want.dtype == np.int16
+    assert np.abs(got.astype(np.int64) - want.astype(np.int64)).max() <= 1 and (got != want).mean() < 0.01
+
+
+def test_coupled_convex_operator_guards_caller_data():
+    """The public operator takes any tensors: labels outside [0, L) are clamped (no out-of-bounds read), a cost volume
+    with negative entries or NaNs is rejected (the kernels order costs by bit pattern)."""
+    import torch.nn.functional as F
+    from convexadam_b200.convex_adam_utils import coupled_convex
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1)
+    ssd = torch.rand(27, 5, 6, 8, generator=g).to(dev)
+    am = ssd.argmin(0)
+    mesh = F.affine_grid(torch.eye(3, 4).unsqueeze(0), (1, 1, 3, 3, 3), align_corners=True).permute(0, 4, 1, 2, 3).reshape(3, -1, 1).to(dev)
+    want = coupled_convex(ssd, am, mesh, 2, (10, 12, 16))
+    bad = am.clone()
+    bad[0, 0, 0] = 10 ** 9
+    bad[1, 1, 1] = -5
+    got = coupled_convex(ssd, bad, mesh, 2, (10, 12, 16))
+    torch.cuda.synchronize()
+    assert got.shape == want.shape and bool(torch.isfinite(got).all())
+    neg = ssd.clone()
+    neg[3, 2, 2, 2] = -1.0
+    with pytest.raises(ValueError):
+        coupled_convex(neg, am, mesh, 2, (10, 12, 16))
