@@ -382,7 +382,7 @@ def main():
     ach_corr = ab["correlate_per_direction"] / (t_corr * 1e-3) / 1e9 if t_corr > 0 else 0.0
     fused = "corr_fused" in ktimes
     corr_kernels = "k_corr_fused (one fused launch)" if fused else \
-        ("k_raw_ssd_staged + k_box12_fast" if mode == "certified" else "k_raw_ssd_staged + k_box12") + ", %d launches" % int(
+        ("k_raw_ssd_tmap + k_box12_fast" if mode == "certified" else "k_raw_ssd_staged + k_box12") + ", %d launches" % int(
             round((ktimes.get("raw_ssd", (0, 0))[1] + ktimes.get("box_filters", (0, 0))[1]) / steps / ndir))
     roof = {"kernel": "correlate stage of one direction (%s): features in, (L,h,w,d) cost volume out" % corr_kernels,
             "bound": "hbm", "achieved": ach_corr, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
@@ -399,7 +399,8 @@ def main():
               kernel_line("box_filters", "k_box12_fast (both 3x3x3 box filters, separable)" if mode == "certified" else
                           "k_box12 (both 3x3x3 box filters, reference summation order)", ndir * (ab["L"] * ab["n"] * 4), "hbm",
                           "bytes = the cost volume it writes; it also reads the raw-SSD planes (same size, not algorithmic)"),
-              kernel_line("raw_ssd", "k_raw_ssd_staged (SSD over 13 kD x 4 kW per CTA from bulk-copy staged tiles)",
+              kernel_line("raw_ssd", "k_raw_ssd_tmap (SSD over 13 kD x 4 kW per CTA; tiles staged by tensor-map TMA from the unpadded features)" if mode == "certified"
+                          else "k_raw_ssd_staged (SSD over 13 kD x 4 kW per CTA from bulk-copy staged tiles)",
                           ndir * (2 * 12 * ab["n"] * 4), "hbm",
                           "bytes = the two feature volumes it reads; it writes the raw-SSD planes (not algorithmic); bound by fp32 FMA lanes: 24 lane-ops per entry"),
               kernel_line("blockmin_argmin", "k_blockmin_argmin (argmin + block/slab minima, one streaming read of the volume)",

@@ -20,6 +20,7 @@
 // followed by a true division by 27 (avg_pool3d, count_include_pad) -- so that the argmin over labels is the
 // reference's argmin.  Every arithmetic op is an explicit _rn intrinsic: nvcc must not contract them to FMAs.
 #include "box_march.cuh"
+#include "ca_tma.cuh"
 
 #include <cstdlib>
 
@@ -304,6 +305,104 @@ __global__ void __launch_bounds__(256, 2) k_raw_ssd_staged(RawStagedArgs a) {
             o.z = (z0 + 2 < a.d) ? acc[k][2] : 0.f;
             o.w = (z0 + 3 < a.d) ? acc[k][3] : 0.f;
             ca_st_stream4(reinterpret_cast<float4*>(rp + k * a.rl.plane), o);
+            if (lpad) ca_st_stream4(reinterpret_cast<float4*>(rp + k * a.rl.plane - 4), zero4);
+            if (rpad) ca_st_stream4(reinterpret_cast<float4*>(rp + k * a.rl.plane + 4), zero4);
+        }
+    }
+}
+
+// ---- raw SSD staged by tensor-map TMA: the certified mode's default -----------------------------------------------------
+// Same tile, thread mapping and arithmetic as k_raw_ssd_staged<HW, true>, but the two tiles of a CTA arrive as ONE 4-D
+// tensor-map box each (cp.async.bulk.tensor.4d -> UTMALDG.4D) straight from the UNPADDED (C,h,w,d) feature volumes: the
+// fixed box (d, TY, 1, C) at (0, y0, x, 0) and the moving box (d + 2*hw rounded up, TY+NW-1, 1, C) at
+// (-hw-MSH, y0+kW0-hw, x+kH-hw, 0).  Elements outside the tensor are filled with zeros by the TMA unit -- the reference's
+// F.pad(mind_mov, hw) (utils.py:76) and the ragged last row tile at once -- so the zero-padded copy of the moving features
+// (k_pad_features: 68 MB written and re-read per direction at config 2) is gone.  A box must start on a 16-byte boundary of
+// the row, hence the MSH = (-hw) mod 4 extra leading voxels, skipped by a compile-time register offset.
+struct RawTmapArgs {
+    float* raw;
+    RawLayout rl;
+    int C, w, d, r0, kW0, NW;
+    int fix_f;          // floats of the fixed tile, rounded up to a 128-byte multiple (offset of the moving tile)
+    int mz;             // moving-tile row length
+};
+
+template <int HW>
+__global__ void __launch_bounds__(256, 2) k_raw_ssd_tmap(CA_TMAP_PARAM tmF, CA_TMAP_PARAM tmM, RawTmapArgs a) {
+    constexpr int S = 2 * HW + 1;
+    constexpr int MSH = (4 - HW % 4) % 4;
+    constexpr int NM = (MSH + 4 + 2 * HW + 3) & ~3;
+    CA_DYN_SMEM_ALIGNED(float, sm, 128);
+    const int tid = (int)threadIdx.y * (int)blockDim.x + (int)threadIdx.x;
+    const int kH = (int)blockIdx.x;
+    const int x = a.r0 + (int)blockIdx.z;
+    const int y0t = (int)blockIdx.y * CA_RAW_TY;
+    const int mrows = CA_RAW_TY + a.NW - 1;
+    const int fch = CA_RAW_TY * a.d, mch = mrows * a.mz;             // floats per channel in shared memory
+    float* sfix = sm;                                                // [C][TY][d]
+    float* smov = sm + a.fix_f;                                      // [C][TY+NW-1][mz]
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smov + (size_t)a.C * mch);
+    if (tid == 0) ca_mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        ca_mbar_expect_tx(bar, (unsigned)(a.C * (fch + mch)) * 4u);
+        ca_tma_load_4d(sfix, &tmF, 0, y0t, x, 0, bar);
+        ca_tma_load_4d(smov, &tmM, -HW - MSH, y0t + a.kW0 - HW, x + kH - HW, 0, bar);
+    }
+    ca_mbar_wait(bar, 0);
+    const int ty = (int)threadIdx.y, z0 = 4 * (int)threadIdx.x;
+    const int y = y0t + ty;
+    if (y >= a.w) return;
+    const bool lpad = threadIdx.x == 0, rpad = threadIdx.x == blockDim.x - 1;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* fs = sfix + ty * a.d + z0;
+    float* rp0 = a.raw + (int64_t)blockIdx.z * a.rl.xPitch + 4 + z0 + (int64_t)(y + 2) * a.rl.rowPitch;
+    for (int kWl = 0; kWl < a.NW; ++kWl) {
+        const float* ms = smov + (ty + kWl) * a.mz + z0;
+        // packed pairs of neighbouring labels of one voxel (see k_raw_ssd_staged): first moving index of voxel v, label k
+        // is MSH + v + k
+        float2 pr[4][S / 2];
+        float sg[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            sg[v] = 0.f;
+#pragma unroll
+            for (int q = 0; q < S / 2; ++q) pr[v][q] = make_float2(0.f, 0.f);
+        }
+#pragma unroll 2
+        for (int c = 0; c < a.C; ++c) {
+            const float4 f4 = *reinterpret_cast<const float4*>(fs + c * fch);
+            const float f[4] = {f4.x, f4.y, f4.z, f4.w};
+            float m[NM];
+#pragma unroll
+            for (int j = 0; j < NM / 4; ++j) {
+                const float4 m4 = *reinterpret_cast<const float4*>(ms + c * mch + 4 * j);
+                m[4 * j + 0] = m4.x; m[4 * j + 1] = m4.y; m[4 * j + 2] = m4.z; m[4 * j + 3] = m4.w;
+            }
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float2 fv = make_float2(f[v], f[v]);
+                const int par = (MSH + v) & 1;
+#pragma unroll
+                for (int q = 0; q < S / 2; ++q) {
+                    const int i0 = MSH + v + 2 * q + par;
+                    const float2 df = ca_sub2(make_float2(m[i0], m[i0 + 1]), fv);
+                    pr[v][q] = ca_fma2(df, df, pr[v][q]);
+                }
+                const float ds = m[MSH + v + (par ? 0 : S - 1)] - f[v];
+                sg[v] = __fmaf_rn(ds, ds, sg[v]);
+            }
+        }
+        float* rp = rp0 + (int64_t)(kWl * S + kH) * S * a.rl.plane;
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+            float o[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                if (((MSH + v) & 1) == 0) o[v] = k == S - 1 ? sg[v] : ((k & 1) ? pr[v][k >> 1].y : pr[v][k >> 1].x);
+                else o[v] = k == 0 ? sg[v] : (((k - 1) & 1) ? pr[v][(k - 1) >> 1].y : pr[v][(k - 1) >> 1].x);
+            }
+            ca_st_stream4(reinterpret_cast<float4*>(rp + k * a.rl.plane), make_float4(o[0], o[1], o[2], o[3]));
             if (lpad) ca_st_stream4(reinterpret_cast<float4*>(rp + k * a.rl.plane - 4), zero4);
             if (rpad) ca_st_stream4(reinterpret_cast<float4*>(rp + k * a.rl.plane + 4), zero4);
         }
@@ -757,6 +856,47 @@ bool launch_raw_staged(bool fast, const float* fixp, const float* movp, int C, i
     }();
     return true;
 }
+
+// geometry of the tensor-map raw kernel for NW kW groups per chunk; false: shape outside its range (d a multiple of 4,
+// boxes of at most 256 elements per dimension, two CTAs per SM)
+static bool tmap_geometry(int C, int d, int hw, int NW, int* fix_f, int* mz, size_t* smem) {
+    const int msh = (4 - hw % 4) % 4, nm = (msh + 4 + 2 * hw + 3) & ~3;
+    *mz = d - 4 + nm;
+    *fix_f = (C * CA_RAW_TY * d + 31) & ~31;
+    *smem = ((size_t)*fix_f + (size_t)C * (CA_RAW_TY + NW - 1) * *mz) * sizeof(float) + 128;
+    return (d & 3) == 0 && d <= 240 && *mz <= 256 && C <= 256 && *smem <= 110 * 1024 && (d / 4) * CA_RAW_TY <= 256;
+}
+static bool use_tmap() {         // CA_RAW_TMAP=0: A/B switch back to the bulk-copy staged kernel on the zero-padded copy
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("CA_RAW_TMAP"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v == 1;
+}
+// true when every chunk of the plan goes through the tensor-map kernel (certified mode, unpadded features in place)
+static bool all_chunks_tmap(const CorrPlan& p, int C, int d, int hw, const float* fix, const float* mov) {
+    int ff, mz; size_t sm;
+    return use_tmap() && use_staged() && p.G % p.S == 0 && ((((uintptr_t)fix) | ((uintptr_t)mov)) & 15) == 0 &&
+           tmap_geometry(C, d, hw, p.G / p.S, &ff, &mz, &sm);
+}
+
+template <int HW>
+int launch_raw_tmap(const float* fix, const float* mov, int C, int h, int w, int d, int kW0, int NW, const CorrPlan& p, float* raw,
+                    cudaStream_t st) {
+    constexpr int S = 2 * HW + 1;
+    RawTmapArgs a;
+    size_t smem;
+    if (!tmap_geometry(C, d, HW, NW, &a.fix_f, &a.mz, &smem)) return CA_ERR_UNSUPPORTED;
+    a.raw = raw; a.rl = p.rl; a.C = C; a.w = w; a.d = d; a.r0 = p.r0; a.kW0 = kW0; a.NW = NW;
+    CaTensorMap tmF, tmM;
+    int rc = ca_tmap_make(&tmF, fix, d, w, h, C, d, d, CA_RAW_TY, C);
+    if (rc != CA_OK) return rc;
+    rc = ca_tmap_make(&tmM, mov, d, w, h, C, d, a.mz, CA_RAW_TY + NW - 1, C);
+    if (rc != CA_OK) return rc;
+    const dim3 grid((unsigned)S, (unsigned)((w + CA_RAW_TY - 1) / CA_RAW_TY), (unsigned)(p.r1 - p.r0)), block((unsigned)(d / 4), CA_RAW_TY);
+    auto k = k_raw_ssd_tmap<HW>;
+    CA_SMEM_OPTIN(k, 110 * 1024);
+    CA_LAUNCH(k, grid, block, smem, st, tmF, tmM, a);
+    return CA_OK;
+}
 }  // namespace
 
 extern "C" size_t ca_correlate_slab_workspace_bytes(int C, int h, int w, int d, int disp_hw, int x_begin, int x_end) {
@@ -822,7 +962,10 @@ static int correlate_impl(bool fast, const float* fix, const float* mov, int C, 
         rc = ca_launch_corr_fused(ff, mm, C, h, w, d, p.dF, disp_hw, x_begin, x_end, ssd, st);
         if (rc != CA_ERR_UNSUPPORTED) return rc;
     }
-    {
+    // certified mode, rows of a multiple of 4 voxels: the raw kernel stages its tiles by tensor-map TMA straight from the
+    // caller's feature volumes (out-of-bounds zero fill = F.pad): no padded copy, no halo zeroing
+    const bool tmap = fast && all_chunks_tmap(p, C, d, disp_hw, fix, mov);
+    if (!tmap) {
         const int64_t tf = (int64_t)C * h * w * p.dF, tm = (int64_t)C * (h + 2 * disp_hw) * (w + 2 * disp_hw) * p.dP;
         // the fixed features are used in place when their rows already have the kernels' pitch and alignment
         if (p.dF == d && (((uintptr_t)fix) & 15) == 0) fixp = const_cast<float*>(fix);
@@ -847,7 +990,19 @@ static int correlate_impl(bool fast, const float* fix, const float* mov, int C, 
         void* tm = ca_timing_begin(CA_T_RAW, st);
         bool staged = false;
         int src = CA_OK;
-        if (use_staged() && cs % S == 0 && g % S == 0) {
+        if (tmap) {
+            switch (disp_hw) {
+                case 1: src = launch_raw_tmap<1>(fix, mov, C, h, w, d, cs / S, g / S, p, raw, st); break;
+                case 2: src = launch_raw_tmap<2>(fix, mov, C, h, w, d, cs / S, g / S, p, raw, st); break;
+                case 3: src = launch_raw_tmap<3>(fix, mov, C, h, w, d, cs / S, g / S, p, raw, st); break;
+                case 4: src = launch_raw_tmap<4>(fix, mov, C, h, w, d, cs / S, g / S, p, raw, st); break;
+                case 5: src = launch_raw_tmap<5>(fix, mov, C, h, w, d, cs / S, g / S, p, raw, st); break;
+                case 6: src = launch_raw_tmap<6>(fix, mov, C, h, w, d, cs / S, g / S, p, raw, st); break;
+                case 7: src = launch_raw_tmap<7>(fix, mov, C, h, w, d, cs / S, g / S, p, raw, st); break;
+                default: src = launch_raw_tmap<8>(fix, mov, C, h, w, d, cs / S, g / S, p, raw, st); break;
+            }
+            staged = true;
+        } else if (use_staged() && cs % S == 0 && g % S == 0) {
             switch (disp_hw) {
                 case 1: staged = launch_raw_staged<1>(fast, fixp, movp, C, h, w, d, cs / S, g / S, p, raw, st, &src); break;
                 case 2: staged = launch_raw_staged<2>(fast, fixp, movp, C, h, w, d, cs / S, g / S, p, raw, st, &src); break;
