@@ -583,7 +583,9 @@ __global__ void __launch_bounds__(512, 1) k_box12(Box12Args a) {
 // pad columns included) are requested with ONE bulk asynchronous copy (cp.async.bulk + mbarrier) into a ring of NST
 // shared-memory stages while plane X is being filtered, and every tap -- the +-1 neighbours along D included -- is a
 // shared-memory read of a zero-padded row: no shuffles, no boundary selects, no address arithmetic per row.
+#ifndef CA_BOXF_NST
 #define CA_BOXF_NST 4
+#endif
 struct BoxFastArgs {
     const float* raw;
     float* ssd;

@@ -6,7 +6,7 @@ PART=${2:-all}
 mkdir -p $OUT
 if [ "$PART" = "all" ] || [ "$PART" = "1" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches_bench.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > $OUT/bench_under_ncu.log 2>&1; echo "list rc=$?"
-for k in k_box12_fast k_raw_ssd_staged k_blockmin_argmin; do
+for k in k_box12_fast k_raw_ssd_tmap k_blockmin_argmin; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 0 -c 1 -f -o $OUT/prof_$k python tools/profile_corr.py --fast --cc > /dev/null 2>&1; echo "$k rc=$?"
 done
 CA_CORR_FUSED=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_corr_fused -s 0 -c 1 -f -o $OUT/prof_k_corr_fused python tools/profile_corr.py --fast > /dev/null 2>&1; echo "fused rc=$?"
