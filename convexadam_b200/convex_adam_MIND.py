@@ -147,9 +147,9 @@ def convex_adam_pt(
             moving_ready = side.record_event()
             moving_dev.record_stream(main)
         if use_mask:
-            import nibabel as nib
-            mask_fixed = torch.from_numpy(nib.load(path_fixed_mask).get_fdata()).float()
-            mask_moving = torch.from_numpy(nib.load(path_moving_mask).get_fdata()).float()
+            load, _ = _nifti_io()
+            mask_fixed = torch.from_numpy(np.asarray(load(path_fixed_mask)[0])).float()
+            mask_moving = torch.from_numpy(np.asarray(load(path_moving_mask)[0])).float()
             fixed_dev = _fill_outside_mask(fixed_dev, mask_fixed, device)
             moving_dev = _fill_outside_mask(moving_dev, mask_moving, device)
         if split_over is not None and split_over is not False:
@@ -184,18 +184,40 @@ def convex_adam(
     result_path="./",
     verbose: bool = False,
 ) -> None:
-    """File-in / disp.nii.gz-out wrapper (reference MIND.py:205-248).  Needs nibabel."""
-    import nibabel as nib
-
-    img_fixed = torch.from_numpy(nib.load(path_img_fixed).get_fdata()).float()
-    img_moving = torch.from_numpy(nib.load(path_img_moving).get_fdata()).float()
+    """File-in / disp.nii.gz-out wrapper (reference MIND.py:205-248): NIfTI images in, `result_path/disp.nii.gz` out with
+    the fixed image's affine.  Uses nibabel when it is installed, else this package's own NIfTI-1 reader / writer."""
+    load, save = _nifti_io()
+    fixed_data, affine = load(path_img_fixed)
+    img_fixed = torch.from_numpy(np.asarray(fixed_data)).float()
+    img_moving = torch.from_numpy(np.asarray(load(path_img_moving)[0])).float()
     displacements = convex_adam_pt(img_fixed=img_fixed, img_moving=img_moving, mind_r=mind_r, mind_d=mind_d,
                                    lambda_weight=lambda_weight, grid_sp=grid_sp, disp_hw=disp_hw,
                                    selected_niter=selected_niter, selected_smooth=selected_smooth,
                                    grid_sp_adam=grid_sp_adam, ic=ic, use_mask=use_mask, path_fixed_mask=path_fixed_mask,
                                    path_moving_mask=path_moving_mask, verbose=verbose)
-    affine = nib.load(path_img_fixed).affine
-    nib.save(nib.Nifti1Image(displacements, affine), os.path.join(result_path, "disp.nii.gz"))
+    save(os.path.join(result_path, "disp.nii.gz"), displacements, affine)
+
+
+def _nifti_io():
+    """(load(path) -> (float64 data, affine), save(path, data, affine)): nibabel if present, else convexadam_b200.lite_io."""
+    try:
+        import nibabel as nib
+
+        def load(path):
+            img = nib.load(path)
+            return img.get_fdata(), img.affine
+
+        def save(path, data, affine):
+            nib.save(nib.Nifti1Image(data, affine), path)
+    except ImportError:
+        from . import lite_io
+
+        def load(path):
+            data, affine = lite_io.read_nifti(path)
+            return np.asarray(data, np.float64), affine
+
+        save = lite_io.write_nifti
+    return load, save
 
 
 def _main():

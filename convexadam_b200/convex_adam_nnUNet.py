@@ -95,15 +95,16 @@ def convex_adam_pt(pred_fixed, pred_moving, lambda_weight=1.25, grid_sp=6, disp_
 
 def convex_adam(path_pred_fixed, path_pred_moving, lambda_weight, grid_sp, disp_hw, selected_niter, selected_smooth,
                 grid_sp_adam=2, ic=True, result_path="./"):
-    """Reference signature (nnUNet.py:41-50): reads two label maps, writes result_path/disp.nii.gz.  Needs nibabel."""
-    import nibabel as nib
-
-    pred_fixed = torch.from_numpy(nib.load(path_pred_fixed).get_fdata()).float()
-    pred_moving = torch.from_numpy(nib.load(path_pred_moving).get_fdata()).float()
+    """Reference signature (nnUNet.py:41-50): reads two label maps, writes result_path/disp.nii.gz (nibabel when installed,
+    else this package's own NIfTI-1 reader / writer)."""
+    from .convex_adam_MIND import _nifti_io
+    load, save = _nifti_io()
+    fixed_data, affine = load(path_pred_fixed)
+    pred_fixed = torch.from_numpy(np.asarray(fixed_data)).float()
+    pred_moving = torch.from_numpy(np.asarray(load(path_pred_moving)[0])).float()
     displacements = convex_adam_pt(pred_fixed, pred_moving, lambda_weight, grid_sp, disp_hw, selected_niter,
                                    selected_smooth, grid_sp_adam, ic)
-    affine = nib.load(path_pred_fixed).affine
-    nib.save(nib.Nifti1Image(displacements, affine), os.path.join(result_path, "disp.nii.gz"))
+    save(os.path.join(result_path, "disp.nii.gz"), displacements, affine)
 
 
 def _main():
