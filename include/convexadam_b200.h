@@ -127,7 +127,11 @@ CA_API int ca_coupled_convex(const float* ssd, const int64_t* argmin, const floa
  * order from the feature volumes (fix, mov: the same (C,h,w,d) arrays given to ca_correlate_fast).  The selections and
  * disp_soft are therefore bit-identical to ca_correlate + ca_coupled_convex; only the volume is approximate.
  * sel_out: optional (7,h,w,d) int64 -- plane 0 the argmin of utils.py:87, planes 1..6 the six passes.
- * flagged_out: optional 7 int32 on the device, the number of voxels that needed the exact re-decision in each. */
+ * flagged_out: optional 7 int32 on the device, the number of voxels that needed the exact re-decision in each.
+ * Implementation of ca_correlate_fast: per chunk of (kH,kW) pairs a raw-SSD kernel staged by tensor-map TMA straight from
+ * the caller's unpadded feature volumes (out-of-bounds zero fill = the reference's F.pad, utils.py:76) and a separable
+ * box-filter kernel; the environment variable CA_CORR_FUSED=1 selects the one-kernel form of the stage
+ * (csrc/correlate_fused.cu: a third of the DRAM traffic, same bound on every entry, same certified selections). */
 CA_API int ca_correlate_fast(const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, float* ssd,
                       void* workspace, size_t workspace_bytes, ca_stream_t stream);
 CA_API size_t ca_coupled_convex_certified_workspace_bytes(int h, int w, int d, int disp_hw);
