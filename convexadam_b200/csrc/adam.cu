@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(128, MINB) k_adam_grad(const float* __restrict
 }
 
 #ifndef CA_GRAD_MINB
-#define CA_GRAD_MINB 4
+#define CA_GRAD_MINB 5
 #endif
 struct AdamScalars { float w_lerp, beta2, one_m_beta2, bc2_sqrt, eps, neg_step_size; };
 
@@ -450,7 +450,7 @@ extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int
         const dim3 ggrid((unsigned)((da + bx - 1) / bx), (unsigned)((wa + by - 1) / by), (unsigned)((hl + bz - 1) / bz)), gblock(bx, by, bz);
         // (compile-time group counts with the loop unrolled -- all 24 gathers of a voxel in flight -- were measured slower: 9.5-10.6
         // against 8.9 ms per 100 iterations; the kernel wants resident warps more than loads per warp)
-        CA_LAUNCH_PDL((k_adam_grad<0, 5>), ggrid, gblock, 0, st, (const float*)u_out, (const float4*)fixcl, (const float4*)movcl, CG, g, g0x, g0y, g0z, gu);
+        CA_LAUNCH_PDL((k_adam_grad<0, CA_GRAD_MINB>), ggrid, gblock, 0, st, (const float*)u_out, (const float4*)fixcl, (const float4*)movcl, CG, g, g0x, g0y, g0z, gu);
         ca_timing_end(tmg, st);
         CA_CHECK_LAUNCH("adam_grad");
         if (!fast) {
