@@ -317,6 +317,24 @@ def main():
     value_h2d = {"value": world * steps / (max_over_ranks(e0.elapsed_time(e1)) / 1e3), "unit": "pairs/s",
                  "h2d_bytes_per_step": int(2 * fixed.numel() * 4)}
 
+    # ---- optional mode: the two directions of the convex stage on two CUDA streams (CONVEXADAM_B200_OVERLAP=1; needs a second
+    # cost volume; off by default because per-kernel timings of concurrently running kernels stop meaning anything) ----
+    value_overlap = None
+    if not args.no_extras:
+        P2 = pipeline.Params(selected_niter=args.niter, overlap="1", **prm)
+        for _ in range(2):
+            pipeline.register_mind(fixed_dev, moving_dev, P2, lib, ssd_buf)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            field = pipeline.register_mind(fixed_dev, moving_dev, P2, lib, ssd_buf)
+        e1.record()
+        barrier()
+        value_overlap = {"value": world * steps / (max_over_ranks(e0.elapsed_time(e1)) / 1e3), "unit": "pairs/s",
+                         "note": "forward and backward direction of the convex stage issued on two streams (opt-in)"}
+        pipeline._VOL2.clear()
+        torch.cuda.empty_cache()
+
     # ---- end to end through the public API (host buffers in, host array out) ----
     e2e = None
     if not args.no_e2e:
@@ -423,6 +441,7 @@ def main():
                    "l2": "the 8.6 GB cost volume (>> 126 MB L2) is rewritten and re-read every step; no explicit flush"},
         "stages_ms": stages,
         "value_t0_t1": value_h2d,
+        "value_two_stream_directions": value_overlap,
         "roofline": roof,
         "roofline_other_kernels": [k for k in others if k],
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "e2e_pipelined": piped,
