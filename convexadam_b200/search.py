@@ -46,3 +46,58 @@ def convex_fields(img_fixed, img_moving, settings, mind_r=1, mind_d=2, ic=True, 
             else:
                 out.append(disp)
     return out
+
+
+def adam_fields(img_fixed, img_moving, adam_settings, snapshots=(80,), grid_sp=6, disp_hw=4, selected_smooth=0, mind_r=1, mind_d=2,
+                ic=True, device=None, to_host=True):
+    """The Adam stage for a list of settings on top of ONE convex stage (second half).
+
+    The reference's Adam search (self_configuring/adam_run_withconfig_shiftSpline.py:159-264) restarts from the stored
+    convex field for every (grid_sp_adam, ..., lambda_weight) setting, recomputes the features each time and evaluates the
+    field at several iteration counts of one run (iterations 60, 80, 100, 120 there).  Here MIND runs once per image, the
+    convex stage once, the features are pooled once per distinct grid_sp_adam, and each run is continued from snapshot to
+    snapshot (`ca_adam_run` is resumable: the state (p, m, v) and the step index carry over).
+
+    adam_settings: iterable of (grid_sp_adam, lambda_weight); snapshots: increasing iteration counts.
+    Returns {(grid_sp_adam, lambda_weight, niter): field}; every field is bit-identical to
+    `convex_adam_pt(..., grid_sp_adam=gsa, lambda_weight=lam, selected_niter=niter)`.  (The search's spline / Gaussian
+    regularisers, convexAdam_hyper_util.py:454-488, are not built: the regulariser is the reference's B^3, MIND.py:166.)"""
+    lib = get_lib()
+    dev = torch.device(device if device is not None else "cuda")
+    fixed = torch.as_tensor(img_fixed).float()
+    moving = torch.as_tensor(img_moving).float()
+    if fixed.dim() != 3 or fixed.shape != moving.shape:
+        raise ValueError("img_fixed and img_moving must be 3-D volumes of the same shape")
+    snapshots = [int(n) for n in snapshots]
+    if not snapshots or snapshots != sorted(set(snapshots)) or snapshots[0] < 1:
+        raise ValueError("snapshots must be increasing iteration counts >= 1")
+    H, W, D = fixed.shape
+    out = {}
+    with torch.cuda.device(dev):
+        full_f, _ = lib.mindssc_pooled(fixed.to(dev).contiguous(), mind_r, mind_d, 1)
+        full_m, _ = lib.mindssc_pooled(moving.to(dev).contiguous(), mind_r, mind_d, 1)
+        pooled = {}
+
+        def feats(gs):
+            if gs not in pooled:
+                pooled[gs] = (full_f if gs == 1 else lib.avgpool3d(full_f, gs, gs), full_m if gs == 1 else lib.avgpool3d(full_m, gs, gs))
+            return pooled[gs]
+
+        fs, ms = feats(int(grid_sp))
+        base = pipeline.Params(mind_r, mind_d, 1.0, int(grid_sp), int(disp_hw), snapshots[-1], int(selected_smooth), 2, ic)
+        disp0 = pipeline.convex_stage(lib, fs, ms, (H, W, D), base)
+        for gsa, lam in adam_settings:
+            gsa, lam = int(gsa), float(lam)
+            if lam <= 0:
+                raise ValueError("adam_fields: lambda_weight must be > 0 (lambda_weight = 0 skips the Adam stage: use convex_fields)")
+            fa, ma = feats(gsa)
+            prm = pipeline.Params(mind_r, mind_d, lam, int(grid_sp), int(disp_hw), snapshots[-1], int(selected_smooth), gsa, ic)
+            p = pipeline.adam_start(lib, disp0, fa.shape[1:], prm)
+            m, v = torch.zeros_like(p), torch.zeros_like(p)
+            done = 0
+            for n in snapshots:
+                u = lib.adam_run(fa, ma, lam, p, m, v, done + 1, n - done)
+                done = n
+                disp = pipeline.adam_finish(lib, u, (H, W, D), prm)
+                out[(gsa, lam, n)] = lib.pack_field(disp).cpu().numpy() if to_host else disp
+    return out

@@ -232,3 +232,18 @@ def test_coupled_convex_operator_guards_caller_data():
     neg[3, 2, 2, 2] = -1.0
     with pytest.raises(ValueError):
         coupled_convex(neg, am, mesh, 2, (10, 12, 16))
+
+
+def test_adam_sweep_equals_individual_calls():
+    """convexadam_b200.search.adam_fields (one convex stage, features pooled once per grid_sp_adam, each Adam run continued
+    from snapshot to snapshot) == one convex_adam_pt call per (grid_sp_adam, lambda_weight, niter), bit for bit."""
+    from convexadam_b200.search import adam_fields
+    from convexadam_b200.synth import make_pair
+    fixed, moving = make_pair((48, 42, 54), seed=8, disp_scale=0.1)
+    settings = [(2, 1.25), (1, 0.5), (3, 2.0)]
+    got = adam_fields(fixed, moving, settings, snapshots=(3, 6, 10), grid_sp=3, disp_hw=3)
+    assert len(got) == 9
+    for (gsa, lam, n), g in got.items():
+        want = api()(fixed, moving, mind_r=1, mind_d=2, lambda_weight=lam, grid_sp=3, disp_hw=3, selected_niter=n,
+                     selected_smooth=0, grid_sp_adam=gsa, ic=True, dtype=torch.float32)
+        assert g.shape == want.shape and (g == want).all(), (gsa, lam, n)
