@@ -57,6 +57,9 @@ _SIGS = {
     "ca_apply_convex": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "ca_field_mean_workspace_bytes": (_sz, []),
     "ca_field_mean": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _sz, _vp]),
+    "ca_mask_erode": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "ca_nearest_inside_workspace_bytes": (_sz, [_i, _i, _i]),
+    "ca_nearest_inside": (_i, [_vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
 }
 EXPORTS = tuple(_SIGS)
 ABI_VERSION = 1
@@ -391,6 +394,24 @@ class Lib:
         self._chk(self.dll.ca_trilinear(self._p(x), Cn, ih, iw, idd, self._p(out), size[0], size[1], size[2], post_mul,
                                        self._stream(x)))
         return out
+
+    def mask_erode(self, mask):
+        """(avg3(mask) > 0.9).float() with the replicate-padded 3x3x3 mean of MIND.py:38-42; mask (H,W,D) float32."""
+        mask = self._t(mask)
+        H, W, D = mask.shape
+        out = torch.empty_like(mask)
+        self._chk(self.dll.ca_mask_erode(self._p(mask), H, W, D, self._p(out), self._stream(mask)))
+        return out
+
+    def nearest_inside(self, inside):
+        """(3,h,w,d) int32 coordinates of the nearest voxel with inside != 0 (scipy's distance_transform_edt indices)."""
+        inside = self._t(inside)
+        h, w, d = inside.shape
+        idx = torch.empty((3, h, w, d), dtype=torch.int32, device=inside.device)
+        nb = self.dll.ca_nearest_inside_workspace_bytes(h, w, d)
+        ws = self._ws(nb, inside)
+        self._chk(self.dll.ca_nearest_inside(self._p(inside), h, w, d, self._p(idx), self._p(ws), nb, self._stream(inside)))
+        return idx
 
     def adam_run(self, fix, mov, lambda_weight, p, m, v, first_step, niter, want_grad=False):
         fix = self._t(fix)

@@ -32,22 +32,24 @@ def _require_cuda(device):
 
 
 def _fill_outside_mask(img, mask, device):
-    """use_mask branch of the reference (MIND.py:36-54): erode the mask, fill the outside with the nearest inside
-    value found on a 2x subsampled grid (scipy EDT on the host), keep the inside.  Host-side, outside the kernels
-    (out of scope for the CUDA path)."""
-    import torch.nn as nn
-    import torch.nn.functional as F
-    from scipy.ndimage import distance_transform_edt as edt
-
+    """use_mask branch of the reference (MIND.py:36-54): erode the mask (`avg3(mask) > 0.9`), give every voxel of the 2x
+    subsampled grid the intensity of the nearest voxel inside the eroded mask (the reference: scipy's distance transform
+    on the host; here ca_nearest_inside, the same feature transform on the device, equidistant choices included),
+    upsample trilinearly and keep the original intensities inside the mask.  Like the reference this needs even H, W, D."""
+    lib = get_lib()
     H, W, D = img.shape[-3:]
-    avg3 = nn.Sequential(nn.ReplicationPad3d(1), nn.AvgPool3d(3, stride=1)).to(device)
-    m = (avg3(mask.view(1, 1, H, W, D).to(device)) > 0.9).float()
-    _, idx = edt((m[0, 0, ::2, ::2, ::2] == 0).squeeze().cpu().numpy(), return_indices=True)
-    idx = torch.from_numpy(idx).to(device)
-    sub = img[::2, ::2, ::2].to(device).reshape(-1)[idx[0] * D // 2 * W // 2 + idx[1] * D // 2 + idx[2]]
-    filled = F.interpolate(sub.unsqueeze(0).unsqueeze(0), scale_factor=2, mode="trilinear")
-    filled.view(-1)[m.view(-1) != 0] = img.to(device).reshape(-1)[m.view(-1) != 0]
-    return filled[0, 0].contiguous()
+    img = img.reshape(H, W, D).to(device).float().contiguous()
+    m = lib.mask_erode(mask.reshape(H, W, D).to(device).float().contiguous())
+    m_sub = m[::2, ::2, ::2].contiguous()
+    idx = lib.nearest_inside(m_sub).long()
+    h2, w2, d2 = m_sub.shape
+    # the reference's flat index into the subsampled image: idx[0]*D//2*W//2 + idx[1]*D//2 + idx[2]  (MIND.py:44)
+    flat = idx[0] * D // 2 * W // 2 + idx[1] * D // 2 + idx[2]
+    sub = img[::2, ::2, ::2].reshape(-1)[flat].reshape(1, h2, w2, d2).contiguous()
+    filled = lib.trilinear(sub, (2 * h2, 2 * w2, 2 * d2))[0]                 # F.interpolate(scale_factor=2, mode='trilinear')
+    if filled.shape != img.shape:
+        raise RuntimeError(f"use_mask needs even image dimensions (got {tuple(img.shape)}): the reference fails on the same line")
+    return torch.where(m != 0, img, filled).contiguous()
 
 
 def extract_features(img_fixed, img_moving, mind_r, mind_d, use_mask, mask_fixed, mask_moving,

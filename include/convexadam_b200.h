@@ -17,6 +17,7 @@
  *   ca_pack_field          dtype rounding + np.stack(...,3)  convex_adam_MIND.py:198-202
  *   ca_apply_convex        map_coordinates warp              apply_convex.py:13-24
  *   ca_field_mean          np.mean(field[mask], axis=0)      convex_adam_translation.py:88-96
+ *   ca_mask_erode, ca_nearest_inside   mask erosion + EDT indices (use_mask)   convex_adam_MIND.py:36-54
  *
  * Conventions: every pointer is a DEVICE pointer to a contiguous array owned by the caller;
  * no function allocates, none synchronises, all work is enqueued on `stream` (a cudaStream_t); the functions are
@@ -232,6 +233,16 @@ CA_API int ca_apply_convex(const double* disp, const void* moving, int moving_is
 CA_API size_t ca_field_mean_workspace_bytes(void);
 CA_API int ca_field_mean(const float* field, const unsigned char* mask, int64_t n, int round_half, double* out4, void* workspace,
                   size_t workspace_bytes, ca_stream_t stream);
+
+/* ---- use_mask pre-processing of extract_features (convex_adam_MIND.py:36-54) ------------------------------------------------
+ * ca_mask_erode: out = (avg3(mask) > 0.9) as 0/1 floats, avg3 = ReplicationPad3d(1) + AvgPool3d(3, stride 1) (MIND.py:38-42).
+ * ca_nearest_inside: idx (3,h,w,d) int32 = for every voxel the coordinates of the nearest voxel with inside != 0 --
+ * scipy.ndimage.distance_transform_edt(inside == 0, return_indices=True)[1] (MIND.py:43), including scipy's choice among
+ * equidistant voxels (the reference calls scipy on the host here; this is the same feature transform on the device). */
+CA_API int ca_mask_erode(const float* mask, int H, int W, int D, float* out, ca_stream_t stream);
+CA_API size_t ca_nearest_inside_workspace_bytes(int h, int w, int d);
+CA_API int ca_nearest_inside(const float* inside, int h, int w, int d, int32_t* idx, void* workspace, size_t workspace_bytes,
+                      ca_stream_t stream);
 
 #ifdef __cplusplus
 }

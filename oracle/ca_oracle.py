@@ -294,3 +294,26 @@ def translation_from_field(field, spacing_zyx, seg=None):
     t = field[np.asarray(seg) > 0].mean(axis=0) if seg is not None else field.mean(axis=(0, 1, 2))
     spacing = np.asarray(spacing_zyx, np.float64)
     return t, tuple(list((np.round(t / spacing, decimals=0) * spacing)[::-1]))
+
+
+def fill_outside_mask(img, mask):
+    """The use_mask pre-processing of extract_features (reference convex_adam_MIND.py:36-54) for one image, restated with
+    numpy and -- like the reference itself -- scipy's distance transform: erode the mask with the replicate-padded 3x3x3
+    mean (> 0.9), nearest inside voxel on the 2x subsampled grid, trilinear 2x upsampling, original intensities inside.
+    Returns (filled image, eroded mask, EDT indices (3,h,w,d))."""
+    from scipy.ndimage import distance_transform_edt as edt
+    img = np.ascontiguousarray(img, np.float32)
+    mask = np.ascontiguousarray(mask, np.float32)
+    H, W, D = img.shape
+    padded = np.pad(mask, 1, mode="edge")
+    s = np.zeros_like(mask)
+    for dx in range(3):                 # torch avg_pool3d: ascending (dH, dW, dD) fp32 sum, then a true division
+        for dy in range(3):
+            for dz in range(3):
+                s = s + padded[dx:dx + H, dy:dy + W, dz:dz + D]
+    m = ((s / np.float32(27)) > np.float32(0.9)).astype(np.float32)
+    _, idx = edt(m[::2, ::2, ::2] == 0, return_indices=True)
+    sub = img[::2, ::2, ::2].reshape(-1)[idx[0] * D // 2 * W // 2 + idx[1] * D // 2 + idx[2]]
+    h2, w2, d2 = sub.shape
+    filled = trilinear(sub[None].astype(np.float32), (2 * h2, 2 * w2, 2 * d2))[0]
+    return np.where(m != 0, img, filled), m, idx.astype(np.int32)

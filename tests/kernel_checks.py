@@ -397,3 +397,50 @@ def check_field_mean(lib, device, shape=(9, 10, 11)):
     assert (got == 0).all()
     got = N(lib.field_mean(T(f, device), round_half=True))
     assert np.abs(got[:3] - f.astype(np.float16).astype(np.float64).reshape(3, -1).mean(1)).max() <= 1e-12
+
+
+def check_mask_fill(lib, device, shapes=((12, 10, 14), (8, 16, 6), (20, 18, 22))):
+    """ca_mask_erode / ca_nearest_inside (the use_mask pre-processing, MIND.py:36-54) against scipy's feature transform:
+    the eroded mask and EVERY index bit-equal -- the grids are small integer lattices full of equidistant candidates, so the
+    choice among them is exercised everywhere -- including blocky masks, a single inside voxel and an empty mask."""
+    from scipy.ndimage import distance_transform_edt as edt
+    r = rng(120)
+    for si, (H, W, D) in enumerate(shapes):
+        img = (r.rand(H, W, D) * 1000).astype(np.float32)
+        masks = []
+        blob = np.zeros((H, W, D), np.float32)
+        blob[H // 4:3 * H // 4 + 1, W // 5:4 * W // 5, D // 3:D - 2] = 1
+        masks.append(blob)
+        masks.append((r.rand(H, W, D) > 0.35).astype(np.float32))            # speckle: erosion leaves scattered voxels
+        two = np.zeros((H, W, D), np.float32)
+        two[1:5, 1:5, 1:5] = 1
+        two[H - 5:H - 1, W - 5:W - 1, D - 5:D - 1] = 1                        # two symmetric blocks: planes of exact ties
+        masks.append(two)
+        masks.append(np.ones((H, W, D), np.float32))
+        for mi, mask in enumerate(masks):
+            want, m_o, idx_o = orc.fill_outside_mask(img, mask)
+            m = lib.mask_erode(T(mask, device))
+            assert_bits_equal(N(m), m_o, f"eroded mask {si}/{mi}")
+            idx_t = lib.nearest_inside(m[::2, ::2, ::2].contiguous())
+            idx = N(idx_t)
+            assert (idx == idx_o).all(), f"nearest-inside indices {si}/{mi}: {(idx != idx_o).any(0).sum()} voxels differ from scipy"
+            if (idx[0] >= 0).all():
+                # the whole fill as convex_adam_MIND._fill_outside_mask composes it: gather, 2x trilinear, select
+                it = T(img, device)
+                lin = idx_t.long()
+                flat = lin[0] * D // 2 * W // 2 + lin[1] * D // 2 + lin[2]
+                sub = it[::2, ::2, ::2].reshape(-1)[flat].reshape((1,) + tuple(idx.shape[1:])).contiguous()
+                filled = lib.trilinear(sub, (H, W, D))[0]
+                got = torch.where(m != 0, it, filled)
+                assert_bits_equal(N(got), want, f"filled image {si}/{mi}")
+    # raw feature transform on random sets, many ties, degenerate extents
+    for shape in ((1, 1, 9), (7, 1, 5), (6, 9, 4), (11, 12, 13)):
+        for dens in (0.02, 0.2, 0.7):
+            inside = (r.rand(*shape) < dens).astype(np.float32)
+            if inside.sum() == 0:
+                inside.reshape(-1)[r.randint(inside.size)] = 1
+            _, want = edt(inside == 0, return_indices=True)
+            got = N(lib.nearest_inside(T(inside, device)))
+            assert (got == want).all(), f"feature transform {shape} density {dens}"
+    none = N(lib.nearest_inside(T(np.zeros((4, 5, 6), np.float32), device)))
+    assert (none == edt(np.ones((4, 5, 6), bool), return_indices=True)[1]).all() and (none[0] == -1).all()

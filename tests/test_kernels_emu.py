@@ -63,3 +63,6 @@ def test_certified_fused_kernel(lib, monkeypatch):
     monkeypatch.setenv("CA_CORR_FUSED", "1")
     kc.check_certified(lib, DEV, cases=((12, 4, 5, 8, 2), (3, 4, 5, 7, 1), (7, 3, 14, 35, 2), (4, 3, 4, 6, 4), (2, 2, 3, 5, 6)))
     kc.check_certified(lib, DEV, cases=kc.random_small_shapes(55, 6), tie_case=False)
+
+
+def test_mask_fill(lib): kc.check_mask_fill(lib, DEV)

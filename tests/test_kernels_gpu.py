@@ -236,3 +236,6 @@ def test_full_size_certified_equals_exact(lib, full_volume):
     fl = flagged.cpu().numpy()
     print(f"full size: max relative deviation of the fast volume {worst:.3e}; voxels re-decided exactly per selection {fl.tolist()} of {am.numel()}")
     assert fl.sum() > 0 and fl.max() < am.numel() // 50
+
+
+def test_mask_fill(lib, dev): kc.check_mask_fill(lib, dev, shapes=((12, 10, 14), (8, 16, 6), (20, 18, 22), (48, 40, 64)))

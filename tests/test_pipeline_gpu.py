@@ -247,3 +247,29 @@ def test_adam_sweep_equals_individual_calls():
         want = api()(fixed, moving, mind_r=1, mind_d=2, lambda_weight=lam, grid_sp=3, disp_hw=3, selected_niter=n,
                      selected_smooth=0, grid_sp_adam=gsa, ic=True, dtype=torch.float32)
         assert g.shape == want.shape and (g == want).all(), (gsa, lam, n)
+
+
+def test_use_mask_path_vs_oracle(tmp_path):
+    """convex_adam_pt(use_mask=True, path_*_mask=...): masks read from NIfTI files, eroded, the outside filled with the
+    nearest inside intensity (device feature transform == scipy's, MIND.py:36-54), then the usual path -- against the
+    oracle run on the oracle's filled images."""
+    from convexadam_b200 import lite_io
+    from convexadam_b200.synth import make_pair
+    from oracle import ca_oracle as orc
+    fixed, moving = make_pair((40, 36, 44), seed=13, disp_scale=0.1)
+    zz, yy, xx = np.meshgrid(np.arange(40), np.arange(36), np.arange(44), indexing="ij")
+    mask_f = (((zz - 20) / 15.0) ** 2 + ((yy - 18) / 13.0) ** 2 + ((xx - 22) / 17.0) ** 2 < 1).astype(np.float32)
+    mask_m = (((zz - 19) / 14.0) ** 2 + ((yy - 17) / 14.0) ** 2 + ((xx - 23) / 16.0) ** 2 < 1).astype(np.float32)
+    lite_io.write_nifti(tmp_path / "mf.nii.gz", mask_f, np.eye(4))
+    lite_io.write_nifti(tmp_path / "mm.nii.gz", mask_m, np.eye(4))
+    kw = dict(mind_r=1, mind_d=2, lambda_weight=1.25, grid_sp=2, disp_hw=3, selected_niter=4, selected_smooth=0, grid_sp_adam=2, ic=True)
+    got = api()(fixed, moving, use_mask=True, path_fixed_mask=str(tmp_path / "mf.nii.gz"), path_moving_mask=str(tmp_path / "mm.nii.gz"),
+                dtype=torch.float32, **kw)
+    ff, _, _ = orc.fill_outside_mask(fixed.numpy(), mask_f)
+    fm, _, _ = orc.fill_outside_mask(moving.numpy(), mask_m)
+    want = orc.convex_adam_pt(ff, fm, 1, 2, 1.25, 2, 3, 4, 0, 2, True)
+    err = float(np.abs(got - want).max())
+    print(f"[cuda] use_mask path vs oracle: L_inf = {err:.3e} voxel")
+    assert err <= 1e-4
+    plain = api()(fixed, moving, dtype=torch.float32, **kw)
+    assert np.abs(got - plain).max() > 1e-3          # the masks do change the result
