@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libconvexadam_b200.so")
-SOURCES = ["common.cu", "pool.cu", "mind.cu", "correlate.cu", "correlate_fused.cu", "coupled.cu", "field.cu", "adam.cu", "mask.cu"]
+SOURCES = ["common.cu", "pool.cu", "mind.cu", "correlate.cu", "correlate_fused.cu", "correlate_pipe.cu", "coupled.cu", "field.cu", "adam.cu", "mask.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--fmad=true",            # every order-sensitive op is an explicit _rn intrinsic; the rest may fuse

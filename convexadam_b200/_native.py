@@ -112,7 +112,7 @@ class Lib:
         return int(self.dll.ca_launch_count())
 
     KERNEL_SLOTS = ("raw_ssd", "box_filters", "blockmin_argmin", "select_pass", "exact_redecision", "adam_grad", "adam_box3",
-                    "corr_fused")
+                    "corr_fused", "corr_pipe")
 
     def kernel_timing(self, slots=()):
         """Bracket the launches of the named kernels (KERNEL_SLOTS) with CUDA events on the launch stream; () = off."""
@@ -123,7 +123,7 @@ class Lib:
 
     def kernel_times(self):
         """{slot: (total ms, launches)} of everything recorded since kernel_timing(); synchronise first."""
-        n = 8
+        n = len(self.KERNEL_SLOTS)
         ms, cnt = (C.c_double * n)(), (_i * n)()
         rc = self.dll.ca_kernel_times(ms, cnt, n)
         if rc < 0:

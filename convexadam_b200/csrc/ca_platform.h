@@ -43,7 +43,7 @@ static __device__ __forceinline__ void ca_grid_dep_launch() { asm volatile("grid
 
 void ca_note_launch();   // counts kernel launches (ca_launch_count) -- the bench reports it
 // optional per-kernel timing with CUDA events on the launch stream (common.cu); slots:
-enum { CA_T_RAW = 0, CA_T_BOX = 1, CA_T_BLOCKMIN = 2, CA_T_SELECT = 3, CA_T_FIXUP = 4, CA_T_ADAM_GRAD = 5, CA_T_BOX3 = 6, CA_T_FUSED = 7, CA_T_NSLOTS = 8 };
+enum { CA_T_RAW = 0, CA_T_BOX = 1, CA_T_BLOCKMIN = 2, CA_T_SELECT = 3, CA_T_FIXUP = 4, CA_T_ADAM_GRAD = 5, CA_T_BOX3 = 6, CA_T_FUSED = 7, CA_T_PIPE = 8, CA_T_NSLOTS = 9 };
 void* ca_timing_begin(int slot, cudaStream_t st);
 void ca_timing_end(void* h, cudaStream_t st);
 

@@ -30,6 +30,10 @@ int ca_launch_keys_to_i64(const unsigned long long* keys, int64_t n, int64_t* ou
 // correlate_fused.cu: the whole stage in one kernel (certified mode); CA_ERR_UNSUPPORTED = take the two-kernel path
 int ca_launch_corr_fused(const float* fix, const float* mov, int C, int h, int w, int d, int pitch, int disp_hw, int xb, int xe,
                          float* ssd, cudaStream_t st);
+// correlate_pipe.cu: producer / consumer CTAs of one launch exchanging the raw planes through a ring in L2 (certified mode);
+// `ws` = scratch for the ring and its counters; CA_ERR_UNSUPPORTED = take the two-kernel path
+int ca_launch_corr_pipe(const float* fix, const float* mov, int C, int h, int w, int d, int disp_hw, int xb, int xe, float* ssd,
+                        void* ws, size_t ws_bytes, cudaStream_t st);
 
 // out (C, h+2p, w+2p, pitch) <- in (C,h,w,d), zero elsewhere (F.pad at utils.py:76 plus 16-byte row alignment)
 __global__ void __launch_bounds__(256) k_pad_features(const float* __restrict__ in, int C, int h, int w, int d, int p,
@@ -963,6 +967,11 @@ static int correlate_impl(bool fast, const float* fix, const float* mov, int C, 
         }
         rc = ca_launch_corr_fused(ff, mm, C, h, w, d, p.dF, disp_hw, x_begin, x_end, ssd, st);
         if (rc != CA_ERR_UNSUPPORTED) return rc;
+        // default: one launch of producer / consumer CTAs, raw planes through a ring in L2 (the chunk buffer's space)
+        if (direct) {
+            rc = ca_launch_corr_pipe(fix, mov, C, h, w, d, disp_hw, x_begin, x_end, ssd, ws + p.off_raw, workspace_bytes - p.off_raw, st);
+            if (rc != CA_ERR_UNSUPPORTED) return rc;
+        }
     }
     // certified mode, rows of a multiple of 4 voxels: the raw kernel stages its tiles by tensor-map TMA straight from the
     // caller's feature volumes (out-of-bounds zero fill = F.pad): no padded copy, no halo zeroing

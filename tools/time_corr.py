@@ -35,7 +35,8 @@ def timeit(fn, n=reps):
     return e0.elapsed_time(e1) / n, r
 
 
-knobs = " ".join(f"{k}={os.environ[k]}" for k in ("CA_RAW_MINB", "CA_BOX_THREADS", "CA_CORR_CHUNK") if k in os.environ)
+knobs = " ".join(f"{k}={os.environ[k]}" for k in ("CA_RAW_MINB", "CA_BOX_THREADS", "CA_CORR_CHUNK", "CA_CORR_PIPE", "CA_PIPE_NW",
+                                                  "CA_PIPE_R", "CA_CORR_FUSED") if k in os.environ)
 t_fast, _ = timeit(lambda: lib.correlate(fs, ms_, 6, out=ssd, fast=True))
 t_cert, _ = timeit(lambda: lib.coupled_convex_certified(ssd, fs, ms_, mesh, 6))
 line = f"[{knobs}] certified: correlate_fast/dir {t_fast:.3f} ms, coupled_certified/dir {t_cert:.3f} ms"
@@ -43,4 +44,8 @@ if "--exact" in sys.argv:
     t_ex, _ = timeit(lambda: lib.correlate(fs, ms_, 6, out=ssd, want_argmin=False))
     t_cc, _ = timeit(lambda: lib.coupled_convex(ssd, None, mesh, 6))
     line += f" | exact: correlate/dir {t_ex:.3f} ms, coupled/dir {t_cc:.3f} ms"
+try:
+    line += f" | pipe hand-off error flag {lib.dll.ca_debug_corr_pipe_error(1)}"
+except AttributeError:
+    pass
 print(line)
