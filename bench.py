@@ -285,7 +285,7 @@ def main():
     timer = StageTimer(torch)
     pipeline.TIMER = timer
     # CUDA events around the launches of the convex stage's main kernels, recorded by the library on its launch stream
-    lib.kernel_timing(("raw_ssd", "box_filters", "corr_fused", "blockmin_argmin", "select_pass", "exact_redecision", "adam_grad"))
+    lib.kernel_timing(("raw_ssd", "box_filters", "corr_fused", "corr_pipe", "blockmin_argmin", "select_pass", "exact_redecision", "adam_grad"))
     n0 = lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -399,7 +399,8 @@ def main():
     t_corr = stages.get("correlate", 0.0) / ndir
     ach_corr = ab["correlate_per_direction"] / (t_corr * 1e-3) / 1e9 if t_corr > 0 else 0.0
     fused = "corr_fused" in ktimes
-    corr_kernels = "k_corr_fused (one fused launch)" if fused else \
+    piped = "corr_pipe" in ktimes
+    corr_kernels = "k_corr_fused (one fused launch)" if fused else "k_corr_pipe (one launch of producer / consumer CTAs)" if piped else \
         ("k_raw_ssd_tmap + k_box12_fast" if mode == "certified" else "k_raw_ssd_staged + k_box12") + ", %d launches" % int(
             round((ktimes.get("raw_ssd", (0, 0))[1] + ktimes.get("box_filters", (0, 0))[1]) / steps / ndir))
     roof = {"kernel": "correlate stage of one direction (%s): features in, (L,h,w,d) cost volume out" % corr_kernels,
@@ -409,11 +410,13 @@ def main():
             "share_of_step": ndir * t_corr / step_ms,
             "note": "algorithmic bytes = SURVEY 8(d) bytes_corr per direction: both coarse feature volumes read once, the cost volume "
                     "written once (+ int64 argmin); 'launch' = one direction of the stage",
-            "traffic": committed_traffic(mode, fused, shape)}
+            "traffic": committed_traffic("pipe" if piped else mode, fused, shape)}
     # per-kernel extras, each against the SURVEY 8(d) bytes it is responsible for (the raw-SSD planes between the two kernels
     # of the stage are NOT algorithmic bytes: they are the traffic the fused kernel removes)
     others = [kernel_line("corr_fused", "k_corr_fused (raw SSD + both box filters + H march, tensor-map TMA)",
                           ndir * ab["correlate_per_direction"], "hbm", "writes the cost volume once; features are L2 hits"),
+              kernel_line("corr_pipe", "k_corr_pipe (producer / consumer CTAs, raw SSD planes through a ring in L2)",
+                          ndir * ab["correlate_per_direction"], "hbm", "writes the cost volume once; the raw planes stay in L2"),
               kernel_line("box_filters", "k_box12_fast (both 3x3x3 box filters, separable)" if mode == "certified" else
                           "k_box12 (both 3x3x3 box filters, reference summation order)", ndir * (ab["L"] * ab["n"] * 4), "hbm",
                           "bytes = the cost volume it writes; it also reads the raw-SSD planes (same size, not algorithmic)"),

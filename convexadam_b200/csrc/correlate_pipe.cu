@@ -10,23 +10,26 @@
 // [0, n)).  Written out, (T r)(i) = r(i-2) + 2 r(i-1) + c(i) r(i) + 2 r(i+1) + r(i+2) on the zero-extended r, with the centre
 // weight c(i) = 3 - [i = 0] - [i = n-1]: the truncation only removes the first-box value that sits outside the volume.
 //
-// Work decomposition.  The labels are processed in chunks of one H shift kH x NW (<= 4) W shifts x all S = 2*hw+1 D shifts.
-// Every CTA draws a ticket (one atomic) and the ticket decides what it is:
-//   consumer (label, tile of 16 rows): lives for the whole chunk.  Marches along H (the axis the reference loops over,
-//             utils.py:83): a loader thread waits until the producers have finished plane X, fetches the tile's 20 rows
-//             of the ring with ONE bulk asynchronous copy (cp.async.bulk + mbarrier, CP_NST planes in flight) and hands
-//             the ring slot back; the compute threads apply T_D to the 20 rows (5 row quads each, through a second
-//             shared-memory plane), T_W for their 4 rows x 4 voxels, T_H with the last four in-plane results held in
-//             registers, and stream plane X-2 into `ssd`.
+// Work decomposition.  The labels are processed in chunks of one H shift kH x NW (<= 4) W shifts x all S = 2*hw+1 D shifts,
+// the H axis in blocks of PB planes.  Every CTA draws a ticket (one atomic) and the ticket decides what it is:
 //   producer (plane x, 4 rows): the raw-SSD arithmetic of k_raw_ssd_tmap -- fixed tile and moving tile with its
 //             displacement neighbourhood by tensor-map TMA from the unpadded features (out-of-bounds zero fill = F.pad,
 //             utils.py:76), 4 voxels x S shifts per thread as packed pairs of neighbouring labels -- stored into the
-//             ring slot of plane x once the consumers have released it.
-// Tickets are handed out in the order [consumers of chunk c][producers of chunk c, plane by plane][consumers of c+1]...
-// A CTA only ever waits for CTAs with smaller tickets (which hold an SM slot already or are done) or, as a consumer,
-// for the producers of its own chunk, for which slots remain because a chunk has fewer consumers than 0.6 x the CTA
-// slots of the GPU: no deadlock, whatever order the hardware starts CTAs in.  Two launches of this kernel must not share
-// the GPU, though (their consumers together could fill every slot): the host serialises them with an event.
+//             ring slot of plane x once the consumers of the plane that held the slot before are done.
+//   consumer (label, tile of 16 rows, block of PB planes): a loader thread waits until the producers have finished the
+//             block's PB+4 planes and fetches the tile's 20 rows of each with ONE bulk asynchronous copy (cp.async.bulk +
+//             mbarrier, CP_NST planes in flight); the compute threads apply T_D to the 20 rows (through a second
+//             shared-memory plane), T_W for their 4 rows x 4 voxels, T_H along the block with the last four in-plane
+//             results held in registers (the march along H, the axis the reference loops over, utils.py:83), and stream
+//             the block's PB planes into `ssd`.  The 4 halo planes of a block are filtered in-plane twice (by two
+//             blocks): (PB+4)/PB of the consumers' in-plane arithmetic, nothing of the raw SSD is recomputed.
+// Tickets are handed out, per chunk, in the order [producers of the planes block 0 needs][consumers of block 0]
+// [producers of the further planes block 1 needs][consumers of block 1]...  With a ring of R >= PB + 4 planes a CTA only
+// ever waits for CTAs with SMALLER tickets -- which hold an SM slot already or are done -- so there is no deadlock whatever
+// order the hardware starts CTAs in, however many launches share the GPU, and every CTA is short-lived: the hardware
+// scheduler balances the load.  (Measured and rejected: interleaving the consumers of block b-1 with the producers of block
+// b ticket by ticket, so that both roles share every SM at any time: the producers then wait for ring slots twice as long,
+// 10.0 instead of 8.4 ms per direction at the same ring depth.)
 //
 // Arithmetic: FMA channel sum, 5-tap sums, one multiplication by 1/729 -- at most C + 14 roundings per entry on sums of
 // non-negative terms, i.e. within the same bound as the two-kernel fast path (coupled.cu, "certified selection").  The
@@ -34,7 +37,6 @@
 #include "ca_tma.cuh"
 
 #include <cstdlib>
-#include <mutex>
 #ifdef CA_EMU
 #include <sched.h>
 #endif
@@ -43,14 +45,15 @@
 #define CP_TYC 16        // consumer: output rows per tile (4 row groups of 4 rows)
 #define CP_TR 20         // consumer: ring rows per tile (2 + 16 + 2)
 #define CP_NST 4         // consumer: planes in flight
-#define CP_RMAX 16       // ring depth (planes) the workspace is sized for
+#define CP_RMAX 40       // ring depth (planes) the workspace is sized for
+#define CP_MAXB 256      // H blocks per chunk
 #define CP_MAXG 17       // kW groups (S <= 17)
-#define CP_EMU_SLOTS 48  // CA_EMU: OS threads of the launch = CTAs alive at once
 
 struct CorrPipeArgs {
     float* ring;
     float* ssd;
-    unsigned* ctr;            // [0] ticket, [1] unused, [2, 2+nseq) producers done per plane, [2+nseq, 2+2 nseq) consumers done
+    unsigned* ctr;            // [0] ticket, [1] unused, [2, 2+nseq) producer tiles done per plane, then consumers done per (chunk, block)
+    int PB, nb;               // planes per H block, blocks
     int C, h, w, d;
     int xb, xe, r0, r1, nx;   // output planes [xb, xe); raw planes [r0, r1) = [xb-2, xe+2) clipped to the volume; nx = r1 - r0
     int nq, ncomp, ldr;       // quads per row, compute threads (4 nq), first thread of the loader warp
@@ -64,6 +67,7 @@ struct CorrPipeArgs {
     int ng;                   // kW groups
     int nw[CP_MAXG], kw0[CP_MAXG];
     unsigned tstart[CP_MAXG + 1];   // first ticket of group g
+    int ringRows;             // rows of one label in a ring slot: 16 ntC + 4 (every tile copies 20 whole rows)
     unsigned spin_limit;
 };
 
@@ -190,11 +194,16 @@ static __device__ __forceinline__ void cp_producer(const CaTensorMap* tmF, const
         ca_mbarx_expect_tx(tile_bar, (unsigned)(a.C * (fch + mch)) * 4u);
         ca_tma_load_4d(sfix, tmF, 0, y0t, x, 0, tile_bar);
         ca_tma_load_4d(smov, tmM, -HW - MSH, y0t + kW0 - HW, x + kH - HW, 0, tile_bar);
-        // the ring slot of this plane held plane seq-R: every consumer of THAT plane's chunk must have fetched it
+        // the ring slot of this plane held plane seq-R: the (at most two) consumer blocks that read THAT plane must be done
         if (seq >= (unsigned)a.R) {
             const unsigned old = seq - (unsigned)a.R;
-            const int og = (int)(old / (unsigned)a.nx) / S;
-            cp_poll(a.ctr + 2 + a.nseq + old, (unsigned)(a.nw[og] * S * a.ntC), a.spin_limit);
+            const int oc = (int)(old / (unsigned)a.nx);                       // its chunk
+            const int q = a.r0 + (int)(old - (unsigned)oc * (unsigned)a.nx);   // its plane
+            const int b_last = ca_min(a.nb - 1, (q - a.xb + 2) / a.PB);
+            const unsigned target = (unsigned)(a.nw[oc / S] * S * a.ntC);
+            const unsigned* cd = a.ctr + 2 + a.nseq + oc * a.nb;
+            if (b_last > 0) cp_poll(cd + b_last - 1, target, a.spin_limit);
+            cp_poll(cd + b_last, target, a.spin_limit);
         }
         CPP_T(p1);
         CPP_ACC(6, p0, p1);
@@ -268,12 +277,11 @@ static __device__ __forceinline__ void cp_producer(const CaTensorMap* tmF, const
         CPP_T(p5);
         if (tid == 0) CPP_ACC(1, p2, p5);
     }
-    // the CTA barrier orders every thread's ring stores before thread 0's release (cumulative): one fence per CTA, not one
-    // per thread (a gpu-scope fence also invalidates L1)
+    // the CTA barrier orders every thread's ring stores before thread 0's release-increment (cumulative): one release per
+    // CTA, no fence per thread (a gpu-scope fence also invalidates L1)
     __syncthreads();
     if (tid == 0) {
         CPP_T(p5b);
-        cp_threadfence();
         cp_signal(a.ctr + 2 + seq);
         CPP_T(p6);
         CPP_ACC(3, p5b, p6);
@@ -323,15 +331,15 @@ struct CpConsumerThread {
     unsigned cmask;           // compute lanes of the thread's warp
     bool elect;               // first lane of its warp: arrives on the barriers for the warp
     bool prof;                // CP_PROFILE: the thread that reports
+    int rs, re, ob, oe;       // the item's block: raw planes [rs, re) in, cost-volume planes [ob, oe) out
 };
 
-// one plane step.  Phase A (T_D of the ring rows into the T_D buffer) runs one plane AHEAD of phase B (T_W out of the T_D
-// buffer, T_H, store): step X does A(X+1) and B(X) between the same pair of barriers, so the two phases overlap in the
-// instruction stream.  PH = (X - r0) mod 4 is the register slot that holds the in-plane result of plane X-4.
+// Phase A (T_D of the ring rows into the T_D buffer) runs one plane AHEAD of phase B (T_W out of the T_D buffer, T_H,
+// store): step X does A(X+1) and B(X) between the same pair of barriers, so the two phases overlap in the instruction stream.
 static __device__ __forceinline__ void cp_phase_a(int X, const CorrPipeArgs& a, const CpConsumerThread& t, unsigned long long* full,
                                                   unsigned long long* empty) {
-    if (X >= a.r1) return;
-    const int i = X - a.r0, st = i % CP_NST;
+    if (X >= t.re) return;
+    const int i = X - t.rs, st = i % CP_NST;
     const int db = (i & 1) * CP_TR * a.d;
     CPP_T(c0);
     ca_mbarx_wait(&full[st], (unsigned)(i / CP_NST) & 1u);
@@ -346,18 +354,19 @@ static __device__ __forceinline__ void cp_phase_a(int X, const CorrPipeArgs& a, 
     if (t.prof) { CPP_ACC(8, c0, c1); CPP_ACC(9, c1, c2); CPP_CNT(12); }
 }
 
+// one plane step; PH = (X - rs) mod 4 is the register slot that holds the in-plane result of plane X-4
 template <int PH>
 static __device__ __forceinline__ void cp_consumer_step(int X, const CorrPipeArgs& a, CpConsumerThread& t, unsigned long long* full,
                                                         unsigned long long* empty, unsigned long long* dbar, float2 (&hs)[4][4][2]) {
-    if (X > a.xe + 1) return;
+    if (X > t.oe + 1) return;
     const float2 two = make_float2(2.f, 2.f);
-    const bool have = X < a.r1;
-    const int i = X - a.r0;
+    const bool have = X < t.re;
+    const int i = X - t.rs;
     const int db = (i & 1) * CP_TR * a.d;
     cp_phase_a(X + 1, a, t, full, empty);
     CPP_T(c4);
     const int xo = X - 2;
-    const bool store = xo >= a.xb;
+    const bool store = xo >= t.ob;
     const float wx = 3.f - (xo == 0 ? 1.f : 0.f) - (xo == a.h - 1 ? 1.f : 0.f);
     const float c729 = 1.0f / 729.0f;
     const float2 wx2 = make_float2(wx, wx), c2 = make_float2(c729, c729);
@@ -405,64 +414,49 @@ static __device__ __forceinline__ void cp_consumer_step(int X, const CorrPipeArg
     if (store) t.out += t.outPitch;
     CPP_T(c5);
     // A(X+1) is complete and B(X) has read its T_D plane: the next step may overwrite the latter and read the former
-    if (X + 1 < a.r1) cp_compute_barrier(dbar, (unsigned)(i + 1) & 1u, a.ncomp, t.cmask, t.elect);
+    if (X + 1 < t.re) cp_compute_barrier(dbar, (unsigned)(i + 1) & 1u, a.ncomp, t.cmask, t.elect);
     CPP_T(c6);
     if (t.prof) { CPP_ACC(11, c4, c5); CPP_ACC(10, c5, c6); }
 }
 
 template <int HW>
 static __device__ __forceinline__ void cp_consumer(const CorrPipeArgs& a, float* sm, unsigned long long* bars, int tid, int chunk, int g,
-                                                   int kH, int col) {
+                                                   int kH, int blk, int col) {
     constexpr int S = 2 * HW + 1;
     const int j = col / a.ntC, tile = col - j * a.ntC;              // label of the chunk, row tile
     const int kWl = j / S, kD = j - kWl * S;
     const int64_t label = (int64_t)kD * S * S + (int64_t)(a.kw0[g] + kWl) * S + kH;
     const int ty0 = tile * CP_TYC;
+    // the item's block of H planes
+    const int ob = a.xb + blk * a.PB, oe = ca_min(ob + a.PB, a.xe);
+    const int rs = ca_max(a.r0, ob - 2), re = ca_min(a.r1, oe + 2);
     unsigned long long* full = bars;
     unsigned long long* empty = bars + CP_NST;
     unsigned long long* dbar = bars + 2 * CP_NST;
-    // rows that are never copied (beyond the ring's w+4 rows) stay zero
-    for (int i = tid; i < CP_NST * a.stage_f; i += (int)blockDim.x) sm[i] = 0.f;
     if (tid == 0) {
         const int ncw = (a.ncomp + 31) / 32;             // compute warps: one arrival each
         for (int s = 0; s < CP_NST; ++s) { ca_mbarx_init(&full[s], 1); ca_mbarx_init(&empty[s], ncw); }
         ca_mbarx_init(dbar, ncw);
     }
     __syncthreads();
-    const int nraw = a.r1 - a.r0;
+    const int nraw = re - rs;
     CPP_T(q0);
     if (tid == a.ldr) {
-        // ring rows [ty0, ty0+20) of the label <-> y = ty0-2 .. ty0+17; rows 0,1,w+2,w+3 and the pad columns are zero
-        const int nrows = ca_min(CP_TR, a.w + 4 - ty0);
-        const unsigned bytes = (unsigned)(nrows * a.pitch) * 4u;
+        // ring rows [ty0, ty0+20) of the label <-> y = ty0-2 .. ty0+17; rows 0, 1 and >= w+2 and the pad columns are zero
+        const unsigned bytes = (unsigned)(CP_TR * a.pitch) * 4u;
         const long long off = (long long)j * a.labelPlane + (long long)ty0 * a.pitch;
-        const unsigned seq0 = (unsigned)chunk * (unsigned)a.nx;
-        int ready = 0;                                  // planes [0, ready) are known to be complete in the ring
+        const unsigned seq0 = (unsigned)chunk * (unsigned)a.nx + (unsigned)(rs - a.r0);
+        int ready = 0;                                  // planes [0, ready) of the block are known to be complete in the ring
         for (int i = 0; i < nraw; ++i) {
             const int st = i % CP_NST;
-            CPP_T(l0);
             if (i >= CP_NST) ca_mbarx_wait(&empty[st], (unsigned)(i / CP_NST - 1) & 1u);
-            CPP_T(l1);
             const unsigned seq = seq0 + (unsigned)i;
             if (i >= ready) {
                 ready = i + cp_poll_prefix(a.ctr + 2 + seq, ca_min(8, nraw - i), (unsigned)a.ntP, a.spin_limit);
                 cp_fence_async();
             }
-            CPP_T(l2);
             ca_mbarx_expect_tx(&full[st], bytes);
             ca_bulk_g2s(sm + st * a.stage_f, a.ring + (long long)(seq % (unsigned)a.R) * a.slotFloats + off, bytes, &full[st]);
-            CPP_T(l3);
-            const int ii = i - (CP_NST - 1);
-            if (ii >= 0) {      // that plane has landed: hand its ring slot back
-                ca_mbarx_wait(&full[ii % CP_NST], (unsigned)(ii / CP_NST) & 1u);
-                cp_signal_relaxed(a.ctr + 2 + a.nseq + seq0 + (unsigned)ii);
-            }
-            CPP_T(l4);
-            CPP_ACC(16, l0, l1); CPP_ACC(17, l1, l2); CPP_ACC(18, l2, l3); CPP_ACC(19, l3, l4);
-        }
-        for (int ii = ca_max(0, nraw - (CP_NST - 1)); ii < nraw; ++ii) {
-            ca_mbarx_wait(&full[ii % CP_NST], (unsigned)(ii / CP_NST) & 1u);
-            cp_signal_relaxed(a.ctr + 2 + a.nseq + seq0 + (unsigned)ii);
         }
     }
     if (tid < a.ncomp) {
@@ -481,15 +475,16 @@ static __device__ __forceinline__ void cp_consumer(const CorrPipeArgs& a, float*
         t.wz3 = z0 + 3 == a.d - 1 ? 2.f : 3.f;
         t.yb = ty0 + 4 * rg;
         t.nrows = ca_clamp(a.w - t.yb, 0, 4);
-        t.out = a.ssd + ((label * (a.xe - a.xb)) * a.w + (t.nrows > 0 ? t.yb : 0)) * (int64_t)a.d + z0;
+        t.rs = rs; t.re = re; t.ob = ob; t.oe = oe;
+        t.out = a.ssd + ((label * (a.xe - a.xb) + (ob - a.xb)) * a.w + (t.nrows > 0 ? t.yb : 0)) * (int64_t)a.d + z0;
         float2 hs[4][4][2];
 #pragma unroll
         for (int s = 0; s < 4; ++s)
 #pragma unroll
             for (int o = 0; o < 4; ++o) hs[s][o][0] = hs[s][o][1] = make_float2(0.f, 0.f);
-        cp_phase_a(a.r0, a, t, full, empty);
+        cp_phase_a(rs, a, t, full, empty);
         cp_compute_barrier(dbar, 0u, a.ncomp, t.cmask, t.elect);
-        for (int X = a.r0; X <= a.xe + 1; X += 4) {
+        for (int X = rs; X <= oe + 1; X += 4) {
             cp_consumer_step<0>(X, a, t, full, empty, dbar, hs);
             cp_consumer_step<1>(X + 1, a, t, full, empty, dbar, hs);
             cp_consumer_step<2>(X + 2, a, t, full, empty, dbar, hs);
@@ -497,6 +492,10 @@ static __device__ __forceinline__ void cp_consumer(const CorrPipeArgs& a, float*
         }
         CPP_T(q1);
         if (tid == 0) { CPP_ACC(13, q0, q1); CPP_CNT(14); }
+        // every plane of the block has been fetched and used by every compute thread: the item is done with the ring
+        // (barrier number nraw of the compute threads: the prologue's and one per step that had a plane to prepare)
+        cp_compute_barrier(dbar, (unsigned)nraw & 1u, a.ncomp, t.cmask, t.elect);
+        if (tid == 0) cp_signal_relaxed(a.ctr + 2 + a.nseq + chunk * a.nb + blk);
     }
 }
 
@@ -518,26 +517,44 @@ __global__ void CP_REGCAP k_corr_pipe(CA_TMAP_PARAM tmF, CA_TMAP_PARAM tmM, Corr
     const unsigned t = s_ticket;
     int g = 0;
     while (g + 1 < a.ng && t >= a.tstart[g + 1]) ++g;
-    const unsigned ncons = (unsigned)(a.nw[g] * S * a.ntC);
-    const unsigned per_chunk = ncons + (unsigned)(a.nx * a.ntP);
+    const unsigned ncols = (unsigned)(a.nw[g] * S * a.ntC);
+    const unsigned per_chunk = (unsigned)(a.nx * a.ntP) + (unsigned)a.nb * ncols;
     const unsigned u = t - a.tstart[g];
     const int kH = (int)(u / per_chunk);
-    const unsigned r = u - (unsigned)kH * per_chunk;
+    unsigned r = u - (unsigned)kH * per_chunk;
     const int chunk = g * S + kH;
-#ifndef CP_NO_CONSUMER
-    if (r < ncons) { cp_consumer<HW>(a, sm, bars, tid, chunk, g, kH, (int)r); return; }
-#endif
+    // within the chunk: [producers of the planes block 0 needs][consumers of block 0][producers of the further planes block 1
+    // needs][consumers of block 1] ...
+    int pe_prev = a.r0;
+    for (int b = 0; b < a.nb; ++b) {
+        const int pe = b == a.nb - 1 ? a.r1 : ca_min(a.r1, a.xb + (b + 1) * a.PB + 2);
+        const unsigned np = (unsigned)((pe - pe_prev) * a.ntP);
+        if (r < np) {
 #ifndef CP_NO_PRODUCER
-    if (r >= ncons) cp_producer<HW>(&tmF, &tmM, a, sm, bars, tid, chunk, g, kH, (int)(r - ncons));
+            cp_producer<HW>(&tmF, &tmM, a, sm, bars, tid, chunk, g, kH, (pe_prev - a.r0) * a.ntP + (int)r);
 #endif
+            return;
+        }
+        r -= np;
+        if (r < ncols) {
+#ifndef CP_NO_CONSUMER
+            cp_consumer<HW>(a, sm, bars, tid, chunk, g, kH, b, (int)r);
+#endif
+            return;
+        }
+        r -= ncols;
+        pe_prev = pe;
+    }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
 namespace {
-// CA_CORR_PIPE=0 switches the certified mode back to the two-kernel path (read on every call so that tests can toggle it)
+// CA_CORR_PIPE=1 switches the certified mode to this kernel (read on every call so that tests can toggle it).  Off by
+// default: at 192x160x256 it measures 6.8 ms per direction against 6.3 ms for the two-kernel path, with 1.6x instead of 3.1x
+// the algorithmic DRAM traffic (DESIGN.md 4.1 has the numbers and the reason).
 bool pipe_enabled() {
     const char* e = getenv("CA_CORR_PIPE");
-    return !(e && atoi(e) == 0);
+    return e && atoi(e) == 1;
 }
 int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
@@ -547,7 +564,7 @@ size_t cp_align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct PipeGeom {
     int nq, ncomp, ldr, nt;
-    int ntP, ntC, pitch, labelPlane;
+    int ntP, ntC, pitch, ringRows, labelPlane;
     int fix_f, mz;
     size_t smem_cons;
 };
@@ -557,8 +574,9 @@ bool pipe_geom(int C, int w, int d, int hw, PipeGeom* g) {
     if (g->nt > CP_MAXT) return false;
     g->ntP = (w + CP_TY - 1) / CP_TY; g->ntC = (w + CP_TYC - 1) / CP_TYC;
     g->pitch = d + 8;
-    if ((int64_t)(w + 4) * g->pitch >= (1ll << 28)) return false;
-    g->labelPlane = (w + 4) * g->pitch;
+    g->ringRows = CP_TYC * g->ntC + 4;
+    if ((int64_t)g->ringRows * g->pitch >= (1ll << 28)) return false;
+    g->labelPlane = g->ringRows * g->pitch;
     const int msh = (4 - hw % 4) % 4, nm = (msh + 4 + 2 * hw + 3) & ~3;
     g->mz = d - 4 + nm;
     if (g->mz > 256) return false;
@@ -571,11 +589,6 @@ size_t pipe_smem(const PipeGeom& g, int C, int NW) {
     return (prod > g.smem_cons ? prod : g.smem_cons) + 128;
 }
 
-std::mutex g_pipe_mu;
-#ifndef CA_EMU
-cudaEvent_t g_pipe_done[64] = {};
-#endif
-
 template <int HW>
 int launch_pipe(const float* fix, const float* mov, int C, int h, int w, int d, int xb, int xe, float* ssd, void* ws, size_t ws_bytes,
                 cudaStream_t st) {
@@ -583,60 +596,50 @@ int launch_pipe(const float* fix, const float* mov, int C, int h, int w, int d, 
     PipeGeom pg;
     if (!pipe_geom(C, w, d, HW, &pg)) return CA_ERR_UNSUPPORTED;
     auto k = k_corr_pipe<HW>;
-    // CTA slots of the GPU for the largest NW whose tiles fit, then the largest NW whose consumers leave room for producers
-    int NW = 0, slots = 0;
-    size_t smem = 0;
-    const int nw_cap = ca_min(ca_max(env_int("CA_PIPE_NW", 4), 1), 4);
-    for (int cand = ca_min(nw_cap, S); cand >= 1; --cand) {
-        const size_t sm_c = pipe_smem(pg, C, cand);
-        if (sm_c > 110 * 1024) continue;
-#ifdef CA_EMU
-        const int sl = CP_EMU_SLOTS;
-#else
-        CA_SMEM_OPTIN(k, 110 * 1024);
-        int occ = 0, dev = 0, nsm = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, pg.nt, sm_c) != cudaSuccess) {
-            (void)cudaGetLastError();
-            return CA_ERR_UNSUPPORTED;
-        }
-        const int sl = occ * nsm;
-#endif
-        if ((int64_t)cand * S * pg.ntC * 10 <= (int64_t)sl * 6) { NW = cand; slots = sl; smem = sm_c; break; }
-    }
-    if (NW == 0) return CA_ERR_UNSUPPORTED;
-    (void)slots;
+    // kW values per chunk: the moving tile of a producer holds CP_TY + NW - 1 rows
+    int NW = ca_min(ca_min(ca_max(env_int("CA_PIPE_NW", 4), 1), 4), S);
+    while (NW > 1 && pipe_smem(pg, C, NW) > 75 * 1024) --NW;            // three CTAs per SM
+    const size_t smem = pipe_smem(pg, C, NW);
+    if (smem > 110 * 1024) return CA_ERR_UNSUPPORTED;
     CorrPipeArgs a;
     a.ssd = ssd; a.C = C; a.h = h; a.w = w; a.d = d;
     a.xb = xb; a.xe = xe;
     a.r0 = ca_max(0, xb - 2); a.r1 = ca_min(h, xe + 2); a.nx = a.r1 - a.r0;
     a.nq = pg.nq; a.ncomp = pg.ncomp; a.ldr = pg.ldr;
-    a.ntP = pg.ntP; a.ntC = pg.ntC; a.pitch = pg.pitch; a.labelPlane = pg.labelPlane;
+    a.ntP = pg.ntP; a.ntC = pg.ntC; a.pitch = pg.pitch; a.ringRows = pg.ringRows; a.labelPlane = pg.labelPlane;
     a.fix_f = pg.fix_f; a.mz = pg.mz; a.mrows = CP_TY + NW - 1;
     a.stage_f = CP_TR * pg.pitch;
     a.slotFloats = (long long)NW * S * pg.labelPlane;
-    // kW groups of (almost) equal size
+    // Ring depth R and block length PB.  A producer of plane p waits for the consumers of the blocks that read plane p-R; their
+    // tickets are smaller than its own only if R >= PB + 4 (a block reads PB + 4 planes): that is what rules out deadlock.
+    // Default: two blocks with their halo planes, so that the producers of block b+1 seldom wait for the consumers of block b.
+    const size_t slot_bytes = (size_t)a.slotFloats * sizeof(float);
+    a.PB = ca_min(ca_max(env_int("CA_PIPE_PB", 12), 4), 60);
     a.ng = (S + NW - 1) / NW;
+    const int nchunks = a.ng * S;
+    a.nseq = nchunks * a.nx;
+    const size_t ctr_bytes = cp_align256((size_t)(2 + (size_t)a.nseq + (size_t)nchunks * (size_t)(xe - xb)) * sizeof(unsigned));
+    if (ws_bytes < ctr_bytes + 12 * slot_bytes) return CA_ERR_UNSUPPORTED;
+    const int r_cap = ca_min(ca_max(env_int("CA_PIPE_R", 2 * a.PB + 8), 12), CP_RMAX);
+    a.R = (int)ca_min((int64_t)r_cap, (int64_t)((ws_bytes - ctr_bytes) / slot_bytes));
+    if (a.PB > a.R - 4) a.PB = a.R - 4;
+    a.nb = (xe - xb + a.PB - 1) / a.PB;
+    if (a.nb > CP_MAXB) return CA_ERR_UNSUPPORTED;
+    // kW groups of (almost) equal size
     unsigned tick = 0;
     for (int g = 0, k0 = 0; g < a.ng; ++g) {
         const int n = S / a.ng + (g < S % a.ng ? 1 : 0);
         a.nw[g] = n; a.kw0[g] = k0; k0 += n;
         a.tstart[g] = tick;
-        const uint64_t per_chunk = (uint64_t)n * S * pg.ntC + (uint64_t)a.nx * pg.ntP;
+        const uint64_t per_chunk = (uint64_t)a.nx * pg.ntP + (uint64_t)a.nb * n * S * pg.ntC;
         if ((uint64_t)tick + per_chunk * S >= (1ull << 31)) return CA_ERR_UNSUPPORTED;
         tick += (unsigned)(per_chunk * S);
     }
     a.tstart[a.ng] = tick;
-    a.nseq = a.ng * S * a.nx;
-    const size_t ctr_bytes = cp_align256((size_t)(2 + 2 * (size_t)a.nseq) * sizeof(unsigned));
-    const size_t slot_bytes = (size_t)a.slotFloats * sizeof(float);
-    if (ws_bytes < ctr_bytes + 2 * slot_bytes) return CA_ERR_UNSUPPORTED;
-    const int r_cap = ca_min(ca_max(env_int("CA_PIPE_R", CP_RMAX), 2), 64);
-    a.R = (int)ca_min((int64_t)r_cap, (int64_t)((ws_bytes - ctr_bytes) / slot_bytes));
     a.ctr = (unsigned*)ws;
     a.ring = (float*)((char*)ws + ctr_bytes);
 #ifdef CA_EMU
-    a.spin_limit = 1u << 26;
+    a.spin_limit = 1u << 20;
 #else
     a.spin_limit = 1u << 23;     // x (64 ns sleep + an L2 round trip) = a few seconds
 #endif
@@ -652,26 +655,8 @@ int launch_pipe(const float* fix, const float* mov, int C, int h, int w, int d, 
         return CA_ERR_LAUNCH;
     }
     const dim3 grid(tick), block((unsigned)pg.nt);
-    {
-        // two launches of this kernel must not share the GPU (see the header): chain them with an event per device
-        std::lock_guard<std::mutex> lock(g_pipe_mu);
-#ifdef CA_EMU
-        emu::launch_wide(grid, block, smem, CP_EMU_SLOTS, [&]() { k(tmF, tmM, a); });
-        ca_note_launch();
-#else
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaEvent_t& ev = g_pipe_done[dev & 63];
-        if (!ev) {
-            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { ca_set_error("correlate (pipe): event"); return CA_ERR_LAUNCH; }
-        } else {
-            cudaStreamWaitEvent(st, ev, 0);
-        }
-        CA_SMEM_OPTIN(k, 110 * 1024);
-        CA_LAUNCH(k, grid, block, smem, st, tmF, tmM, a);
-        cudaEventRecord(ev, st);
-#endif
-    }
+    CA_SMEM_OPTIN(k, 110 * 1024);
+    CA_LAUNCH(k, grid, block, smem, st, tmF, tmM, a);
     ca_timing_end(tmg, st);
     CA_CHECK_LAUNCH("correlate/pipe");
     return CA_OK;
@@ -683,7 +668,7 @@ size_t ca_corr_pipe_workspace_bytes(int C, int h, int w, int d, int disp_hw) {
     PipeGeom pg;
     if (!pipe_geom(C, w, d, disp_hw, &pg)) return 0;
     const int S = 2 * disp_hw + 1;
-    const size_t nseq = (size_t)S * S * (size_t)h;       // >= ng * S * nx
+    const size_t nseq = (size_t)S * S * (size_t)h;       // >= nchunks * nx and >= nchunks * nb
     return cp_align256((2 + 2 * nseq) * sizeof(unsigned)) + (size_t)CP_RMAX * 4 * S * pg.labelPlane * sizeof(float) + 256;
 }
 

@@ -114,23 +114,6 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
     }
 }
 
-void launch_wide(dim3 grid, dim3 block, size_t smem, int nthreads, const std::function<void()>& body) {
-    const long nb = (long)grid.x * grid.y * grid.z;
-    if (nb == 0) return;
-    omp_set_dynamic(0);
-#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
-    for (long b = 0; b < nb; ++b) {
-        if (omp_get_num_threads() < nthreads && nb > omp_get_num_threads()) {
-            fprintf(stderr, "emu: launch_wide got %d of %d threads\n", omp_get_num_threads(), nthreads);
-            abort();
-        }
-        gridDim = grid;
-        blockDim = block;
-        blockIdx = uint3{(unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((long)grid.x * grid.y))};
-        run_block(block, smem, body);
-    }
-}
-
 void* dyn_smem() {
     uintptr_t p = (uintptr_t)W.dyn.data();
     return (void*)((p + 63) & ~(uintptr_t)63);

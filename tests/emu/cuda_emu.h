@@ -49,8 +49,6 @@ template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAtt
 
 namespace emu {
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
-// the same with `nthreads` OS threads, i.e. that many blocks alive at once (kernels whose blocks wait for each other)
-void launch_wide(dim3 grid, dim3 block, size_t smem, int nthreads, const std::function<void()>& body);
 void* dyn_smem();
 void sync_block();
 void sync_warp();

@@ -65,4 +65,24 @@ def test_certified_fused_kernel(lib, monkeypatch):
     kc.check_certified(lib, DEV, cases=kc.random_small_shapes(55, 6), tie_case=False)
 
 
+def test_certified_pipe_kernel(lib, monkeypatch):
+    """The producer / consumer form of ca_correlate_fast (csrc/correlate_pipe.cu; opt-in through CA_CORR_PIPE=1): CTAs of one
+    launch that wait for each other through global counters (blocks of the emulation run on several OS threads), several
+    row tiles and H blocks, small rings."""
+    import ctypes
+    fn = lib.dll.ca_debug_corr_pipe_error
+    fn.restype, fn.argtypes = ctypes.c_int, [ctypes.c_int]
+    monkeypatch.setenv("CA_CORR_PIPE", "1")
+    fn(1)
+    kc.check_certified(lib, DEV, cases=((12, 4, 5, 8, 2), (7, 3, 14, 36, 2), (5, 9, 35, 20, 3), (3, 21, 7, 8, 2), (3, 30, 20, 16, 1)))
+    for knobs in ({"CA_PIPE_PB": "4", "CA_PIPE_R": "12"}, {"CA_PIPE_PB": "9", "CA_PIPE_R": "13", "CA_PIPE_NW": "1"},
+                  {"CA_PIPE_PB": "60", "CA_PIPE_NW": "3"}):
+        for k, v in knobs.items():
+            monkeypatch.setenv(k, v)
+        kc.check_certified(lib, DEV, cases=((7, 3, 14, 36, 2), (3, 21, 7, 8, 2)), tie_case=False)
+        for k in knobs:
+            monkeypatch.delenv(k)
+    assert fn(1) == 0, "a hand-off wait of the producer / consumer kernel gave up"
+
+
 def test_mask_fill(lib): kc.check_mask_fill(lib, DEV)

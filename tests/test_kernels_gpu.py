@@ -106,6 +106,48 @@ def test_full_size_fused_kernel_certified_equals_exact(lib, full_volume, fused_c
     test_full_size_certified_equals_exact(lib, full_volume)
 
 
+@pytest.fixture
+def pipe_correlate(monkeypatch):
+    """CA_CORR_PIPE=1: ca_correlate_fast runs as ONE launch of producer / consumer CTAs that hand the raw SSD planes over through
+    a ring in L2 (csrc/correlate_pipe.cu; opt-in, read on every call)."""
+    monkeypatch.setenv("CA_CORR_PIPE", "1")
+
+
+def _pipe_error_flag(lib):
+    import ctypes
+    fn = lib.dll.ca_debug_corr_pipe_error
+    fn.restype, fn.argtypes = ctypes.c_int, [ctypes.c_int]
+    return fn(1)
+
+
+def test_certified_pipe_kernel(lib, dev, pipe_correlate):
+    """Shapes with several row tiles, several H blocks, ragged last tiles and every ring / block / chunk knob: rows of a multiple
+    of 4 voxels go through the kernel, the others fall back to the two-kernel path (same checks)."""
+    _pipe_error_flag(lib)
+    n0 = lib.launch_count()
+    kc.check_certified(lib, dev, cases=((12, 10, 9, 16, 3), (16, 6, 7, 8, 1), (3, 30, 6, 12, 4), (12, 8, 6, 12, 6), (12, 40, 35, 64, 2),
+                                        (12, 9, 30, 72, 2), (5, 5, 14, 36, 5), (4, 26, 50, 20, 1)))
+    assert lib.launch_count() > n0
+    assert _pipe_error_flag(lib) == 0, "a hand-off wait of the producer / consumer kernel gave up"
+
+
+@pytest.mark.parametrize("knobs", [{"CA_PIPE_PB": "4", "CA_PIPE_R": "12"}, {"CA_PIPE_PB": "9", "CA_PIPE_R": "13", "CA_PIPE_NW": "1"},
+                                   {"CA_PIPE_PB": "60", "CA_PIPE_NW": "3"}, {"CA_PIPE_PB": "8", "CA_PIPE_NW": "2", "CA_PIPE_R": "40"}])
+def test_certified_pipe_kernel_knobs(lib, dev, pipe_correlate, monkeypatch, knobs):
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    _pipe_error_flag(lib)
+    kc.check_certified(lib, dev, cases=((12, 40, 35, 64, 2), (6, 21, 18, 24, 3)), tie_case=False)
+    assert _pipe_error_flag(lib) == 0
+
+
+def test_full_size_pipe_kernel_certified_equals_exact(lib, full_volume, pipe_correlate):
+    """The producer / consumer kernel's volume at BASELINE config 2 size: inside the bound, and the same certified selections."""
+    _pipe_error_flag(lib)
+    test_full_size_certified_equals_exact(lib, full_volume)
+    assert _pipe_error_flag(lib) == 0
+
+
 def test_correlate_rejects_bad_arguments(lib, dev):
     from convexadam_b200._native import NativeError
     f = torch.zeros(12, 4, 4, 4, device=dev)

@@ -36,7 +36,7 @@ def timeit(fn, n=reps):
 
 
 knobs = " ".join(f"{k}={os.environ[k]}" for k in ("CA_RAW_MINB", "CA_BOX_THREADS", "CA_CORR_CHUNK", "CA_CORR_PIPE", "CA_PIPE_NW",
-                                                  "CA_PIPE_R", "CA_CORR_FUSED") if k in os.environ)
+                                                  "CA_PIPE_R", "CA_PIPE_PB", "CA_CORR_FUSED") if k in os.environ)
 t_fast, _ = timeit(lambda: lib.correlate(fs, ms_, 6, out=ssd, fast=True))
 t_cert, _ = timeit(lambda: lib.coupled_convex_certified(ssd, fs, ms_, mesh, 6))
 line = f"[{knobs}] certified: correlate_fast/dir {t_fast:.3f} ms, coupled_certified/dir {t_cert:.3f} ms"
