@@ -510,41 +510,40 @@ __global__ void CP_REGCAP k_corr_pipe(CA_TMAP_PARAM tmF, CA_TMAP_PARAM tmM, Corr
     constexpr int S = 2 * HW + 1;
     CA_DYN_SMEM_ALIGNED(float, sm, 128);
     __shared__ unsigned long long bars[2 * CP_NST + 1];
-    __shared__ unsigned s_ticket;
+    __shared__ int s_job[6];      // chunk, kW group, kH, role (0 producer / 1 consumer / -1 none), block, item
     const int tid = (int)threadIdx.x;
-    if (tid == 0) s_ticket = cp_ticket(a.ctr);
-    __syncthreads();
-    const unsigned t = s_ticket;
-    int g = 0;
-    while (g + 1 < a.ng && t >= a.tstart[g + 1]) ++g;
-    const unsigned ncols = (unsigned)(a.nw[g] * S * a.ntC);
-    const unsigned per_chunk = (unsigned)(a.nx * a.ntP) + (unsigned)a.nb * ncols;
-    const unsigned u = t - a.tstart[g];
-    const int kH = (int)(u / per_chunk);
-    unsigned r = u - (unsigned)kH * per_chunk;
-    const int chunk = g * S + kH;
-    // within the chunk: [producers of the planes block 0 needs][consumers of block 0][producers of the further planes block 1
-    // needs][consumers of block 1] ...
-    int pe_prev = a.r0;
-    for (int b = 0; b < a.nb; ++b) {
-        const int pe = b == a.nb - 1 ? a.r1 : ca_min(a.r1, a.xb + (b + 1) * a.PB + 2);
-        const unsigned np = (unsigned)((pe - pe_prev) * a.ntP);
-        if (r < np) {
-#ifndef CP_NO_PRODUCER
-            cp_producer<HW>(&tmF, &tmM, a, sm, bars, tid, chunk, g, kH, (pe_prev - a.r0) * a.ntP + (int)r);
-#endif
-            return;
+    if (tid == 0) {
+        // thread 0 draws the ticket and decodes it for the CTA (divisions and a loop over the H blocks: not 160 times)
+        const unsigned t = cp_ticket(a.ctr);
+        int g = 0;
+        while (g + 1 < a.ng && t >= a.tstart[g + 1]) ++g;
+        const unsigned ncols = (unsigned)(a.nw[g] * S * a.ntC);
+        const unsigned per_chunk = (unsigned)(a.nx * a.ntP) + (unsigned)a.nb * ncols;
+        const unsigned u = t - a.tstart[g];
+        const int kH = (int)(u / per_chunk);
+        unsigned r = u - (unsigned)kH * per_chunk;
+        s_job[0] = g * S + kH; s_job[1] = g; s_job[2] = kH; s_job[3] = -1;
+        // within the chunk: [producers of the planes block 0 needs][consumers of block 0][producers of the further planes
+        // block 1 needs][consumers of block 1] ...
+        int pe_prev = a.r0;
+        for (int b = 0; b < a.nb; ++b) {
+            const int pe = b == a.nb - 1 ? a.r1 : ca_min(a.r1, a.xb + (b + 1) * a.PB + 2);
+            const unsigned np = (unsigned)((pe - pe_prev) * a.ntP);
+            if (r < np) { s_job[3] = 0; s_job[4] = b; s_job[5] = (pe_prev - a.r0) * a.ntP + (int)r; break; }
+            r -= np;
+            if (r < ncols) { s_job[3] = 1; s_job[4] = b; s_job[5] = (int)r; break; }
+            r -= ncols;
+            pe_prev = pe;
         }
-        r -= np;
-        if (r < ncols) {
-#ifndef CP_NO_CONSUMER
-            cp_consumer<HW>(a, sm, bars, tid, chunk, g, kH, b, (int)r);
-#endif
-            return;
-        }
-        r -= ncols;
-        pe_prev = pe;
     }
+    __syncthreads();
+    const int chunk = s_job[0], g = s_job[1], kH = s_job[2], role = s_job[3], blk = s_job[4], item = s_job[5];
+#ifndef CP_NO_PRODUCER
+    if (role == 0) cp_producer<HW>(&tmF, &tmM, a, sm, bars, tid, chunk, g, kH, item);
+#endif
+#ifndef CP_NO_CONSUMER
+    if (role == 1) cp_consumer<HW>(a, sm, bars, tid, chunk, g, kH, blk, item);
+#endif
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
