@@ -23,6 +23,9 @@
 //             results held in registers (the march along H, the axis the reference loops over, utils.py:83), and stream
 //             the block's PB planes into `ssd`.  The 4 halo planes of a block are filtered in-plane twice (by two
 //             blocks): (PB+4)/PB of the consumers' in-plane arithmetic, nothing of the raw SSD is recomputed.
+// When a row of the volume is exactly one warp of quads (d = 128) the producers apply T_D themselves, with the two voxels
+// either side of a thread's quad taken from the neighbouring lanes by warp shuffles; the consumers then skip their T_D phase
+// and its shared-memory plane and keep six planes in flight instead of four (6.8 -> 6.5 ms per direction at config 2).
 // Tickets are handed out, per chunk, in the order [producers of the planes block 0 needs][consumers of block 0]
 // [producers of the further planes block 1 needs][consumers of block 1]...  With a ring of R >= PB + 4 planes a CTA only
 // ever waits for CTAs with SMALLER tickets -- which hold an SM slot already or are done -- so there is no deadlock whatever
@@ -44,7 +47,9 @@
 #define CP_TY 4          // producer: rows per item
 #define CP_TYC 16        // consumer: output rows per tile (4 row groups of 4 rows)
 #define CP_TR 20         // consumer: ring rows per tile (2 + 16 + 2)
-#define CP_NST 4         // consumer: planes in flight
+#define CP_NST 4         // consumer: planes in flight (its own T_D phase, two T_D planes next to the stages)
+#define CP_NST_TDP 6     // ... when the producers filter along D (no T_D planes)
+#define CP_NSTMAX 6
 #define CP_RMAX 40       // ring depth (planes) the workspace is sized for
 #define CP_MAXB 256      // H blocks per chunk
 #define CP_MAXG 17       // kW groups (S <= 17)
@@ -62,6 +67,7 @@ struct CorrPipeArgs {
     int labelPlane;           // (w + 4) * pitch floats: rows y = -2 .. w+1 of one label
     long long slotFloats;     // NWmax * S * labelPlane: one plane of a chunk
     int fix_f, mz, mrows;     // producer shared memory: offset of the moving tile, its row length and rows
+    int fhalf, mhalf;         // ... floats between the two channel halves of the fixed / moving tile (128-byte multiples)
     int stage_f;              // consumer shared memory: floats per stage = CP_TR * pitch
     int nseq;                 // planes of all chunks: nchunks * nx
     int ng;                   // kW groups
@@ -172,7 +178,7 @@ static __device__ __forceinline__ int cp_poll_prefix(const unsigned* p, int n, u
 }
 
 // ---- producer: raw SSD of 4 rows of plane x for one kH, NWc values of kW and all S values of kD -------------------------
-template <int HW>
+template <int HW, bool TDP>
 static __device__ __forceinline__ void cp_producer(const CaTensorMap* tmF, const CaTensorMap* tmM, const CorrPipeArgs& a, float* sm,
                                                    unsigned long long* bars, int tid, int chunk, int g, int kH, int item) {
     constexpr int S = 2 * HW + 1;
@@ -185,15 +191,22 @@ static __device__ __forceinline__ void cp_producer(const CaTensorMap* tmF, const
     float* sfix = sm;                                                // [C][TY][d]
     float* smov = sm + a.fix_f;                                      // [C][mrows][mz]
     const int fch = CP_TY * a.d, mch = a.mrows * a.mz;
+    // the tiles arrive in two halves of the channels (two tensor-map boxes each): the arithmetic starts on the first half
+    // while the second is still in flight
     unsigned long long* tile_bar = &bars[0];
     unsigned long long* slot_bar = &bars[1];
-    if (tid == 0) { ca_mbarx_init(tile_bar, 1); ca_mbarx_init(slot_bar, 1); }
+    unsigned long long* tile_bar2 = &bars[2];
+    const int Ch = (a.C + 1) / 2;
+    if (tid == 0) { ca_mbarx_init(tile_bar, 1); ca_mbarx_init(slot_bar, 1); ca_mbarx_init(tile_bar2, 1); }
     __syncthreads();
     CPP_T(p0);
     if (tid == a.ldr) {
-        ca_mbarx_expect_tx(tile_bar, (unsigned)(a.C * (fch + mch)) * 4u);
+        ca_mbarx_expect_tx(tile_bar, (unsigned)(Ch * (fch + mch)) * 4u);
         ca_tma_load_4d(sfix, tmF, 0, y0t, x, 0, tile_bar);
         ca_tma_load_4d(smov, tmM, -HW - MSH, y0t + kW0 - HW, x + kH - HW, 0, tile_bar);
+        ca_mbarx_expect_tx(tile_bar2, (unsigned)(Ch * (fch + mch)) * 4u);
+        ca_tma_load_4d(sfix + a.fhalf, tmF, 0, y0t, x, Ch, tile_bar2);
+        ca_tma_load_4d(smov + a.mhalf, tmM, -HW - MSH, y0t + kW0 - HW, x + kH - HW, Ch, tile_bar2);
         // the ring slot of this plane held plane seq-R: the (at most two) consumer blocks that read THAT plane must be done
         if (seq >= (unsigned)a.R) {
             const unsigned old = seq - (unsigned)a.R;
@@ -216,10 +229,10 @@ static __device__ __forceinline__ void cp_producer(const CaTensorMap* tmF, const
         ca_mbarx_wait(tile_bar, 0);
         CPP_T(p2);
         if (tid == 0) CPP_ACC(0, p0, p2);
-        const float* fs = sfix + ty * a.d + z0;
+        const float* fs0 = sfix + ty * a.d + z0;
         float* rp0 = a.ring + (long long)(seq % (unsigned)a.R) * a.slotFloats + (long long)(y + 2) * a.pitch + 4 + z0;
         for (int kWl = 0; kWl < NWc; ++kWl) {
-            const float* ms = smov + (ty + kWl) * a.mz + z0;
+            const float* ms0 = smov + (ty + kWl) * a.mz + z0;
             // packed pairs of neighbouring labels of one voxel (see k_raw_ssd_staged): first moving index of voxel v, label k
             // is MSH + v + k
             float2 pr[4][S / 2];
@@ -230,37 +243,42 @@ static __device__ __forceinline__ void cp_producer(const CaTensorMap* tmF, const
 #pragma unroll
                 for (int q = 0; q < S / 2; ++q) pr[v][q] = make_float2(0.f, 0.f);
             }
+            auto accumulate = [&](const float* fs, const float* ms, int nch) {
 #pragma unroll 2
-            for (int c = 0; c < a.C; ++c) {
-                const float4 f4 = *reinterpret_cast<const float4*>(fs + c * fch);
-                const float f[4] = {f4.x, f4.y, f4.z, f4.w};
-                float m[NM];
+                for (int c = 0; c < nch; ++c) {
+                    const float4 f4 = *reinterpret_cast<const float4*>(fs + c * fch);
+                    const float f[4] = {f4.x, f4.y, f4.z, f4.w};
+                    float m[NM];
 #pragma unroll
-                for (int j = 0; j < NM / 4; ++j) {
-                    const float4 m4 = *reinterpret_cast<const float4*>(ms + c * mch + 4 * j);
-                    m[4 * j + 0] = m4.x; m[4 * j + 1] = m4.y; m[4 * j + 2] = m4.z; m[4 * j + 3] = m4.w;
-                }
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const float2 fv = make_float2(f[v], f[v]);
-                    const int par = (MSH + v) & 1;
-#pragma unroll
-                    for (int q = 0; q < S / 2; ++q) {
-                        const int i0 = MSH + v + 2 * q + par;
-                        const float2 df = ca_sub2(make_float2(m[i0], m[i0 + 1]), fv);
-                        pr[v][q] = ca_fma2(df, df, pr[v][q]);
+                    for (int j = 0; j < NM / 4; ++j) {
+                        const float4 m4 = *reinterpret_cast<const float4*>(ms + c * mch + 4 * j);
+                        m[4 * j + 0] = m4.x; m[4 * j + 1] = m4.y; m[4 * j + 2] = m4.z; m[4 * j + 3] = m4.w;
                     }
-                    const float ds = m[MSH + v + (par ? 0 : S - 1)] - f[v];
-                    sg[v] = __fmaf_rn(ds, ds, sg[v]);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float2 fv = make_float2(f[v], f[v]);
+                        const int par = (MSH + v) & 1;
+#pragma unroll
+                        for (int q = 0; q < S / 2; ++q) {
+                            const int i0 = MSH + v + 2 * q + par;
+                            const float2 df = ca_sub2(make_float2(m[i0], m[i0 + 1]), fv);
+                            pr[v][q] = ca_fma2(df, df, pr[v][q]);
+                        }
+                        const float ds = m[MSH + v + (par ? 0 : S - 1)] - f[v];
+                        sg[v] = __fmaf_rn(ds, ds, sg[v]);
+                    }
                 }
-            }
+            };
+            accumulate(fs0, ms0, Ch);
+            if (kWl == 0) ca_mbarx_wait(tile_bar2, 0);
+            accumulate(fs0 + a.fhalf, ms0 + a.mhalf, a.C - Ch);
             if (kWl == 0) {
                 CPP_T(p3);
                 ca_mbarx_wait(slot_bar, 0);
                 CPP_T(p4);
                 if (tid == 0) CPP_ACC(2, p3, p4);
             }
-            if (active) {
+            {
                 float* rp = rp0 + (long long)(kWl * S) * a.labelPlane;
 #pragma unroll
                 for (int k = 0; k < S; ++k) {
@@ -270,7 +288,23 @@ static __device__ __forceinline__ void cp_producer(const CaTensorMap* tmF, const
                         if (((MSH + v) & 1) == 0) o[v] = k == S - 1 ? sg[v] : ((k & 1) ? pr[v][k >> 1].y : pr[v][k >> 1].x);
                         else o[v] = k == 0 ? sg[v] : (((k - 1) & 1) ? pr[v][(k - 1) >> 1].y : pr[v][(k - 1) >> 1].x);
                     }
-                    cp_st4(rp + (long long)k * a.labelPlane, make_float4(o[0], o[1], o[2], o[3]));
+                    if (TDP) {
+                        // T_D here: a row is exactly one warp (32 quads), so the two voxels either side of the thread's quad come
+                        // from the neighbouring lanes (zero beyond the row ends = the zero padding); same operations in the same
+                        // order as cp_td, which the consumers then skip
+                        float l2 = __shfl_up_sync(0xffffffffu, o[2], 1), l3 = __shfl_up_sync(0xffffffffu, o[3], 1);
+                        float r0 = __shfl_down_sync(0xffffffffu, o[0], 1), r1 = __shfl_down_sync(0xffffffffu, o[1], 1);
+                        if (tx == 0) { l2 = 0.f; l3 = 0.f; }
+                        if (tx == a.nq - 1) { r0 = 0.f; r1 = 0.f; }
+                        const float2 two = make_float2(2.f, 2.f);
+                        const float2 ae01 = ca_add2(make_float2(l2, l3), make_float2(o[2], o[3]));
+                        const float2 ae23 = ca_add2(make_float2(o[0], o[1]), make_float2(r0, r1));
+                        const float b0 = l3 + o[1], b1 = o[0] + o[2], b2 = o[1] + o[3], b3 = o[2] + r0;
+                        const float2 d01 = ca_fma2(make_float2(tx == 0 ? 2.f : 3.f, 3.f), make_float2(o[0], o[1]), ca_fma2(two, make_float2(b0, b1), ae01));
+                        const float2 d23 = ca_fma2(make_float2(3.f, tx == a.nq - 1 ? 2.f : 3.f), make_float2(o[2], o[3]), ca_fma2(two, make_float2(b2, b3), ae23));
+                        o[0] = d01.x; o[1] = d01.y; o[2] = d23.x; o[3] = d23.y;
+                    }
+                    if (active) cp_st4(rp + (long long)k * a.labelPlane, make_float4(o[0], o[1], o[2], o[3]));
                 }
             }
         }
@@ -355,15 +389,27 @@ static __device__ __forceinline__ void cp_phase_a(int X, const CorrPipeArgs& a, 
 }
 
 // one plane step; PH = (X - rs) mod 4 is the register slot that holds the in-plane result of plane X-4
-template <int PH>
+template <int PH, bool TDP>
 static __device__ __forceinline__ void cp_consumer_step(int X, const CorrPipeArgs& a, CpConsumerThread& t, unsigned long long* full,
                                                         unsigned long long* empty, unsigned long long* dbar, float2 (&hs)[4][4][2]) {
     if (X > t.oe + 1) return;
     const float2 two = make_float2(2.f, 2.f);
     const bool have = X < t.re;
     const int i = X - t.rs;
-    const int db = (i & 1) * CP_TR * a.d;
-    cp_phase_a(X + 1, a, t, full, empty);
+    // TDP: the ring holds T_D values already (the producers filtered along D): phase B reads the stage itself
+    constexpr int NST = TDP ? CP_NST_TDP : CP_NST;
+    const int db = TDP ? (i % NST) * a.stage_f : (i & 1) * CP_TR * a.d;
+    const int dpitch = TDP ? a.pitch : a.d;
+    if (TDP) {
+        if (have) {
+            CPP_T(c0);
+            ca_mbarx_wait(&full[i % NST], (unsigned)(i / NST) & 1u);
+            CPP_T(c1);
+            if (t.prof) { CPP_ACC(8, c0, c1); CPP_CNT(12); }
+        }
+    } else {
+        cp_phase_a(X + 1, a, t, full, empty);
+    }
     CPP_T(c4);
     const int xo = X - 2;
     const bool store = xo >= t.ob;
@@ -377,7 +423,7 @@ static __device__ __forceinline__ void cp_consumer_step(int X, const CorrPipeArg
     for (int j = 0; j < 8; ++j) {
         float2 D[2];
         if (have) {
-            const float4 v = *reinterpret_cast<const float4*>(t.dB + db + j * a.d);
+            const float4 v = *reinterpret_cast<const float4*>(t.dB + db + j * dpitch);
             D[0] = make_float2(v.x, v.y); D[1] = make_float2(v.z, v.w);
         } else {
             D[0] = D[1] = make_float2(0.f, 0.f);
@@ -413,13 +459,20 @@ static __device__ __forceinline__ void cp_consumer_step(int X, const CorrPipeArg
     }
     if (store) t.out += t.outPitch;
     CPP_T(c5);
-    // A(X+1) is complete and B(X) has read its T_D plane: the next step may overwrite the latter and read the former
-    if (X + 1 < t.re) cp_compute_barrier(dbar, (unsigned)(i + 1) & 1u, a.ncomp, t.cmask, t.elect);
+    if (TDP) {
+        if (have) {     // the stage has been read
+            __syncwarp(t.cmask);
+            if (t.elect) ca_mbarx_arrive(&empty[i % NST]);
+        }
+    } else {
+        // A(X+1) is complete and B(X) has read its T_D plane: the next step may overwrite the latter and read the former
+        if (X + 1 < t.re) cp_compute_barrier(dbar, (unsigned)(i + 1) & 1u, a.ncomp, t.cmask, t.elect);
+    }
     CPP_T(c6);
     if (t.prof) { CPP_ACC(11, c4, c5); CPP_ACC(10, c5, c6); }
 }
 
-template <int HW>
+template <int HW, bool TDP>
 static __device__ __forceinline__ void cp_consumer(const CorrPipeArgs& a, float* sm, unsigned long long* bars, int tid, int chunk, int g,
                                                    int kH, int blk, int col) {
     constexpr int S = 2 * HW + 1;
@@ -431,11 +484,12 @@ static __device__ __forceinline__ void cp_consumer(const CorrPipeArgs& a, float*
     const int ob = a.xb + blk * a.PB, oe = ca_min(ob + a.PB, a.xe);
     const int rs = ca_max(a.r0, ob - 2), re = ca_min(a.r1, oe + 2);
     unsigned long long* full = bars;
-    unsigned long long* empty = bars + CP_NST;
-    unsigned long long* dbar = bars + 2 * CP_NST;
+    constexpr int NST = TDP ? CP_NST_TDP : CP_NST;
+    unsigned long long* empty = bars + CP_NSTMAX;
+    unsigned long long* dbar = bars + 2 * CP_NSTMAX;
     if (tid == 0) {
         const int ncw = (a.ncomp + 31) / 32;             // compute warps: one arrival each
-        for (int s = 0; s < CP_NST; ++s) { ca_mbarx_init(&full[s], 1); ca_mbarx_init(&empty[s], ncw); }
+        for (int s = 0; s < NST; ++s) { ca_mbarx_init(&full[s], 1); ca_mbarx_init(&empty[s], ncw); }
         ca_mbarx_init(dbar, ncw);
     }
     __syncthreads();
@@ -448,8 +502,8 @@ static __device__ __forceinline__ void cp_consumer(const CorrPipeArgs& a, float*
         const unsigned seq0 = (unsigned)chunk * (unsigned)a.nx + (unsigned)(rs - a.r0);
         int ready = 0;                                  // planes [0, ready) of the block are known to be complete in the ring
         for (int i = 0; i < nraw; ++i) {
-            const int st = i % CP_NST;
-            if (i >= CP_NST) ca_mbarx_wait(&empty[st], (unsigned)(i / CP_NST - 1) & 1u);
+            const int st = i % NST;
+            if (i >= NST) ca_mbarx_wait(&empty[st], (unsigned)(i / NST - 1) & 1u);
             const unsigned seq = seq0 + (unsigned)i;
             if (i >= ready) {
                 ready = i + cp_poll_prefix(a.ctr + 2 + seq, ca_min(8, nraw - i), (unsigned)a.ntP, a.spin_limit);
@@ -463,10 +517,10 @@ static __device__ __forceinline__ void cp_consumer(const CorrPipeArgs& a, float*
         const int q = tid % a.nq, rg = tid / a.nq;
         const int z0 = 4 * q;
         CpConsumerThread t;
-        float* dbuf = sm + CP_NST * a.stage_f;                          // [2][CP_TR][d]: the T_D rows of the plane in work
+        float* dbuf = sm + NST * a.stage_f;                          // [2][CP_TR][d]: the T_D rows of the plane in work
         t.stageA = sm + (5 * rg) * a.pitch + 4 + z0;
         t.dA = dbuf + (5 * rg) * a.d + z0;
-        t.dB = dbuf + (4 * rg) * a.d + z0;
+        t.dB = TDP ? sm + (4 * rg) * a.pitch + 4 + z0 : dbuf + (4 * rg) * a.d + z0;
         t.outPitch = (int64_t)a.w * a.d;
         t.prof = tid == 0;
         t.elect = (tid & 31) == 0;
@@ -482,19 +536,21 @@ static __device__ __forceinline__ void cp_consumer(const CorrPipeArgs& a, float*
         for (int s = 0; s < 4; ++s)
 #pragma unroll
             for (int o = 0; o < 4; ++o) hs[s][o][0] = hs[s][o][1] = make_float2(0.f, 0.f);
-        cp_phase_a(rs, a, t, full, empty);
-        cp_compute_barrier(dbar, 0u, a.ncomp, t.cmask, t.elect);
+        if (!TDP) {
+            cp_phase_a(rs, a, t, full, empty);
+            cp_compute_barrier(dbar, 0u, a.ncomp, t.cmask, t.elect);
+        }
         for (int X = rs; X <= oe + 1; X += 4) {
-            cp_consumer_step<0>(X, a, t, full, empty, dbar, hs);
-            cp_consumer_step<1>(X + 1, a, t, full, empty, dbar, hs);
-            cp_consumer_step<2>(X + 2, a, t, full, empty, dbar, hs);
-            cp_consumer_step<3>(X + 3, a, t, full, empty, dbar, hs);
+            cp_consumer_step<0, TDP>(X, a, t, full, empty, dbar, hs);
+            cp_consumer_step<1, TDP>(X + 1, a, t, full, empty, dbar, hs);
+            cp_consumer_step<2, TDP>(X + 2, a, t, full, empty, dbar, hs);
+            cp_consumer_step<3, TDP>(X + 3, a, t, full, empty, dbar, hs);
         }
         CPP_T(q1);
         if (tid == 0) { CPP_ACC(13, q0, q1); CPP_CNT(14); }
         // every plane of the block has been fetched and used by every compute thread: the item is done with the ring
         // (barrier number nraw of the compute threads: the prologue's and one per step that had a plane to prepare)
-        cp_compute_barrier(dbar, (unsigned)nraw & 1u, a.ncomp, t.cmask, t.elect);
+        cp_compute_barrier(dbar, TDP ? 0u : (unsigned)nraw & 1u, a.ncomp, t.cmask, t.elect);
         if (tid == 0) cp_signal_relaxed(a.ctr + 2 + a.nseq + chunk * a.nb + blk);
     }
 }
@@ -505,11 +561,11 @@ static __device__ __forceinline__ void cp_consumer(const CorrPipeArgs& a, float*
 #elif !defined(CP_REGCAP)
 #define CP_REGCAP __maxnreg__(128)      // 3 CTAs of 160 threads per SM at d = 128
 #endif
-template <int HW>
+template <int HW, bool TDP>
 __global__ void CP_REGCAP k_corr_pipe(CA_TMAP_PARAM tmF, CA_TMAP_PARAM tmM, CorrPipeArgs a) {
     constexpr int S = 2 * HW + 1;
     CA_DYN_SMEM_ALIGNED(float, sm, 128);
-    __shared__ unsigned long long bars[2 * CP_NST + 1];
+    __shared__ unsigned long long bars[2 * CP_NSTMAX + 1];
     __shared__ int s_job[6];      // chunk, kW group, kH, role (0 producer / 1 consumer / -1 none), block, item
     const int tid = (int)threadIdx.x;
     if (tid == 0) {
@@ -539,18 +595,18 @@ __global__ void CP_REGCAP k_corr_pipe(CA_TMAP_PARAM tmF, CA_TMAP_PARAM tmM, Corr
     __syncthreads();
     const int chunk = s_job[0], g = s_job[1], kH = s_job[2], role = s_job[3], blk = s_job[4], item = s_job[5];
 #ifndef CP_NO_PRODUCER
-    if (role == 0) cp_producer<HW>(&tmF, &tmM, a, sm, bars, tid, chunk, g, kH, item);
+    if (role == 0) cp_producer<HW, TDP>(&tmF, &tmM, a, sm, bars, tid, chunk, g, kH, item);
 #endif
 #ifndef CP_NO_CONSUMER
-    if (role == 1) cp_consumer<HW>(a, sm, bars, tid, chunk, g, kH, blk, item);
+    if (role == 1) cp_consumer<HW, TDP>(a, sm, bars, tid, chunk, g, kH, blk, item);
 #endif
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
 namespace {
 // CA_CORR_PIPE=1 switches the certified mode to this kernel (read on every call so that tests can toggle it).  Off by
-// default: at 192x160x256 it measures 6.8 ms per direction against 6.3 ms for the two-kernel path, with 1.6x instead of 3.1x
-// the algorithmic DRAM traffic (DESIGN.md 4.1 has the numbers and the reason).
+// default: at 192x160x256 it measures 6.4 ms per direction against 6.3 ms for the two-kernel path, with 1.6-2.5x instead of
+// 3.1x the algorithmic DRAM traffic (DESIGN.md 4.1 has the numbers and the reason).
 bool pipe_enabled() {
     const char* e = getenv("CA_CORR_PIPE");
     return e && atoi(e) == 1;
@@ -564,8 +620,8 @@ size_t cp_align256(size_t v) { return (v + 255) & ~(size_t)255; }
 struct PipeGeom {
     int nq, ncomp, ldr, nt;
     int ntP, ntC, pitch, ringRows, labelPlane;
-    int fix_f, mz;
-    size_t smem_cons;
+    int fix_f, fhalf, mz;
+    size_t smem_cons, smem_cons_tdp;
 };
 bool pipe_geom(int C, int w, int d, int hw, PipeGeom* g) {
     if ((d & 3) || d > 240 || d < 4 || C > 24 || hw < 1 || hw > 8) return false;
@@ -579,13 +635,17 @@ bool pipe_geom(int C, int w, int d, int hw, PipeGeom* g) {
     const int msh = (4 - hw % 4) % 4, nm = (msh + 4 + 2 * hw + 3) & ~3;
     g->mz = d - 4 + nm;
     if (g->mz > 256) return false;
-    g->fix_f = (C * CP_TY * d + 31) & ~31;
+    g->fhalf = (((C + 1) / 2) * CP_TY * d + 31) & ~31;           // the tiles arrive as two boxes of ceil(C/2) channels
+    g->fix_f = 2 * g->fhalf;
     g->smem_cons = ((size_t)CP_NST * CP_TR * g->pitch + (size_t)2 * CP_TR * d) * sizeof(float);
+    g->smem_cons_tdp = (size_t)CP_NST_TDP * CP_TR * g->pitch * sizeof(float);
     return true;
 }
-size_t pipe_smem(const PipeGeom& g, int C, int NW) {
-    const size_t prod = ((size_t)g.fix_f + (size_t)C * (CP_TY + NW - 1) * g.mz) * sizeof(float);
-    return (prod > g.smem_cons ? prod : g.smem_cons) + 128;
+size_t pipe_smem(const PipeGeom& g, int C, int NW, bool tdp) {
+    const size_t mhalf = (size_t)((((C + 1) / 2) * (CP_TY + NW - 1) * g.mz + 31) & ~31);
+    const size_t prod = ((size_t)g.fix_f + 2 * mhalf) * sizeof(float);
+    const size_t cons = tdp ? g.smem_cons_tdp : g.smem_cons;
+    return (prod > cons ? prod : cons) + 128;
 }
 
 template <int HW>
@@ -594,11 +654,13 @@ int launch_pipe(const float* fix, const float* mov, int C, int h, int w, int d, 
     constexpr int S = 2 * HW + 1;
     PipeGeom pg;
     if (!pipe_geom(C, w, d, HW, &pg)) return CA_ERR_UNSUPPORTED;
-    auto k = k_corr_pipe<HW>;
+    // T_D inside the producers (warp shuffles) when a row of the volume is exactly one warp of quads; CA_PIPE_TDP=0: A/B switch
+    const bool tdp = pg.nq == 32 && env_int("CA_PIPE_TDP", 1) != 0;
+    auto k = tdp ? k_corr_pipe<HW, true> : k_corr_pipe<HW, false>;
     // kW values per chunk: the moving tile of a producer holds CP_TY + NW - 1 rows
-    int NW = ca_min(ca_min(ca_max(env_int("CA_PIPE_NW", 4), 1), 4), S);
-    while (NW > 1 && pipe_smem(pg, C, NW) > 75 * 1024) --NW;            // three CTAs per SM
-    const size_t smem = pipe_smem(pg, C, NW);
+    int NW = ca_min(ca_min(ca_max(env_int("CA_PIPE_NW", 3), 1), 4), S);
+    while (NW > 1 && pipe_smem(pg, C, NW, tdp) > 75 * 1024) --NW;            // three CTAs per SM
+    const size_t smem = pipe_smem(pg, C, NW, tdp);
     if (smem > 110 * 1024) return CA_ERR_UNSUPPORTED;
     CorrPipeArgs a;
     a.ssd = ssd; a.C = C; a.h = h; a.w = w; a.d = d;
@@ -607,11 +669,13 @@ int launch_pipe(const float* fix, const float* mov, int C, int h, int w, int d, 
     a.nq = pg.nq; a.ncomp = pg.ncomp; a.ldr = pg.ldr;
     a.ntP = pg.ntP; a.ntC = pg.ntC; a.pitch = pg.pitch; a.ringRows = pg.ringRows; a.labelPlane = pg.labelPlane;
     a.fix_f = pg.fix_f; a.mz = pg.mz; a.mrows = CP_TY + NW - 1;
+    a.fhalf = pg.fhalf; a.mhalf = (((C + 1) / 2) * a.mrows * pg.mz + 31) & ~31;
     a.stage_f = CP_TR * pg.pitch;
     a.slotFloats = (long long)NW * S * pg.labelPlane;
     // Ring depth R and block length PB.  A producer of plane p waits for the consumers of the blocks that read plane p-R; their
     // tickets are smaller than its own only if R >= PB + 4 (a block reads PB + 4 planes): that is what rules out deadlock.
-    // Default: two blocks with their halo planes, so that the producers of block b+1 seldom wait for the consumers of block b.
+    // Default: two blocks with their halo planes, so that the producers of block b+1 seldom wait for the consumers of block b
+    // (measured at config 2: NW 3, PB 12, R 28 = a 50 MB ring is the fastest setting).
     const size_t slot_bytes = (size_t)a.slotFloats * sizeof(float);
     a.PB = ca_min(ca_max(env_int("CA_PIPE_PB", 12), 4), 60);
     a.ng = (S + NW - 1) / NW;
@@ -619,7 +683,7 @@ int launch_pipe(const float* fix, const float* mov, int C, int h, int w, int d, 
     a.nseq = nchunks * a.nx;
     const size_t ctr_bytes = cp_align256((size_t)(2 + (size_t)a.nseq + (size_t)nchunks * (size_t)(xe - xb)) * sizeof(unsigned));
     if (ws_bytes < ctr_bytes + 12 * slot_bytes) return CA_ERR_UNSUPPORTED;
-    const int r_cap = ca_min(ca_max(env_int("CA_PIPE_R", 2 * a.PB + 8), 12), CP_RMAX);
+    const int r_cap = ca_min(ca_max(env_int("CA_PIPE_R", 2 * a.PB + 4), 12), CP_RMAX);
     a.R = (int)ca_min((int64_t)r_cap, (int64_t)((ws_bytes - ctr_bytes) / slot_bytes));
     if (a.PB > a.R - 4) a.PB = a.R - 4;
     a.nb = (xe - xb + a.PB - 1) / a.PB;
@@ -643,9 +707,9 @@ int launch_pipe(const float* fix, const float* mov, int C, int h, int w, int d, 
     a.spin_limit = 1u << 23;     // x (64 ns sleep + an L2 round trip) = a few seconds
 #endif
     CaTensorMap tmF, tmM;
-    int rc = ca_tmap_make(&tmF, fix, d, w, h, C, d, d, CP_TY, C);
+    int rc = ca_tmap_make(&tmF, fix, d, w, h, C, d, d, CP_TY, (C + 1) / 2);
     if (rc != CA_OK) return rc;
-    rc = ca_tmap_make(&tmM, mov, d, w, h, C, d, a.mz, a.mrows, C);
+    rc = ca_tmap_make(&tmM, mov, d, w, h, C, d, a.mz, a.mrows, (C + 1) / 2);
     if (rc != CA_OK) return rc;
     void* tmg = ca_timing_begin(CA_T_PIPE, st);
     // counters to zero; ring to zero (its halo rows and pad columns are never written by the kernel)

@@ -74,7 +74,8 @@ def test_certified_pipe_kernel(lib, monkeypatch):
     fn.restype, fn.argtypes = ctypes.c_int, [ctypes.c_int]
     monkeypatch.setenv("CA_CORR_PIPE", "1")
     fn(1)
-    kc.check_certified(lib, DEV, cases=((12, 4, 5, 8, 2), (7, 3, 14, 36, 2), (5, 9, 35, 20, 3), (3, 21, 7, 8, 2), (3, 30, 20, 16, 1)))
+    kc.check_certified(lib, DEV, cases=((12, 4, 5, 8, 2), (7, 3, 14, 36, 2), (5, 9, 35, 20, 3), (3, 21, 7, 8, 2), (3, 30, 20, 16, 1),
+                                        (3, 12, 20, 128, 1)))     # the last: rows of one warp of quads, T_D inside the producers
     for knobs in ({"CA_PIPE_PB": "4", "CA_PIPE_R": "12"}, {"CA_PIPE_PB": "9", "CA_PIPE_R": "13", "CA_PIPE_NW": "1"},
                   {"CA_PIPE_PB": "60", "CA_PIPE_NW": "3"}):
         for k, v in knobs.items():

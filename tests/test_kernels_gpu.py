@@ -126,18 +126,19 @@ def test_certified_pipe_kernel(lib, dev, pipe_correlate):
     _pipe_error_flag(lib)
     n0 = lib.launch_count()
     kc.check_certified(lib, dev, cases=((12, 10, 9, 16, 3), (16, 6, 7, 8, 1), (3, 30, 6, 12, 4), (12, 8, 6, 12, 6), (12, 40, 35, 64, 2),
-                                        (12, 9, 30, 72, 2), (5, 5, 14, 36, 5), (4, 26, 50, 20, 1)))
+                                        (12, 9, 30, 72, 2), (5, 5, 14, 36, 5), (4, 26, 50, 20, 1), (12, 30, 21, 128, 3), (5, 9, 40, 128, 6)))
     assert lib.launch_count() > n0
     assert _pipe_error_flag(lib) == 0, "a hand-off wait of the producer / consumer kernel gave up"
 
 
 @pytest.mark.parametrize("knobs", [{"CA_PIPE_PB": "4", "CA_PIPE_R": "12"}, {"CA_PIPE_PB": "9", "CA_PIPE_R": "13", "CA_PIPE_NW": "1"},
-                                   {"CA_PIPE_PB": "60", "CA_PIPE_NW": "3"}, {"CA_PIPE_PB": "8", "CA_PIPE_NW": "2", "CA_PIPE_R": "40"}])
+                                   {"CA_PIPE_PB": "60", "CA_PIPE_NW": "3"}, {"CA_PIPE_PB": "8", "CA_PIPE_NW": "2", "CA_PIPE_R": "40"},
+                                   {"CA_PIPE_TDP": "0"}])
 def test_certified_pipe_kernel_knobs(lib, dev, pipe_correlate, monkeypatch, knobs):
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)
     _pipe_error_flag(lib)
-    kc.check_certified(lib, dev, cases=((12, 40, 35, 64, 2), (6, 21, 18, 24, 3)), tie_case=False)
+    kc.check_certified(lib, dev, cases=((12, 40, 35, 64, 2), (6, 21, 18, 24, 3), (7, 20, 19, 128, 2)), tie_case=False)
     assert _pipe_error_flag(lib) == 0
 
 
