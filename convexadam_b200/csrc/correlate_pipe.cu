@@ -74,6 +74,9 @@ struct CorrPipeArgs {
     int nw[CP_MAXG], kw0[CP_MAXG];
     unsigned tstart[CP_MAXG + 1];   // first ticket of group g
     int ringRows;             // rows of one label in a ring slot: 16 ntC + 4 (every tile copies 20 whole rows)
+    float* state;             // hand-over of the march state between the H blocks of a column (nullptr: blocks recompute their halo)
+    int ncolsmax;             // columns (label x row tile) of the largest chunk
+    unsigned* colflag;        // [chunk][column]: blocks of the column completed
     unsigned spin_limit;
 };
 
@@ -90,6 +93,8 @@ static inline unsigned cp_ld_relaxed(const unsigned* p) { return __atomic_load_n
 static inline void cp_fence_acquire() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline unsigned cp_ticket(unsigned* p) { return __atomic_fetch_add(p, 1u, __ATOMIC_ACQ_REL); }
 static inline void cp_st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+static inline float4 cp_ld4_cg(const float4* p) { return *p; }
+static inline void cp_st4_cg(float4* p, const float4& v) { *p = v; }
 #else
 __device__ unsigned g_cp_err;
 static __device__ __forceinline__ unsigned cp_ld_acquire(const unsigned* p) {
@@ -112,6 +117,9 @@ static __device__ __forceinline__ unsigned cp_ld_relaxed(const unsigned* p) {
 }
 static __device__ __forceinline__ void cp_fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 static __device__ __forceinline__ unsigned cp_ticket(unsigned* p) { return atomicAdd(p, 1u); }
+// the march state handed from one H block of a column to the next: written by one CTA, read by another -> L2 (.cg), not L1
+static __device__ __forceinline__ float4 cp_ld4_cg(const float4* p) { return __ldcg(p); }
+static __device__ __forceinline__ void cp_st4_cg(float4* p, const float4& v) { __stcg(p, v); }
 // ring stores: plain write-back stores (the lines are meant to stay in L2 until the consumers have fetched them)
 static __device__ __forceinline__ void cp_st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 #endif
@@ -212,11 +220,17 @@ static __device__ __forceinline__ void cp_producer(const CaTensorMap* tmF, const
             const unsigned old = seq - (unsigned)a.R;
             const int oc = (int)(old / (unsigned)a.nx);                       // its chunk
             const int q = a.r0 + (int)(old - (unsigned)oc * (unsigned)a.nx);   // its plane
-            const int b_last = ca_min(a.nb - 1, (q - a.xb + 2) / a.PB);
             const unsigned target = (unsigned)(a.nw[oc / S] * S * a.ntC);
             const unsigned* cd = a.ctr + 2 + a.nseq + oc * a.nb;
-            if (b_last > 0) cp_poll(cd + b_last - 1, target, a.spin_limit);
-            cp_poll(cd + b_last, target, a.spin_limit);
+            if (a.state) {
+                // with the hand-over a plane is read by one block only: block b fetches the planes [ob+2, oe+2) (block 0 also the first)
+                const int b = ca_clamp((q - a.xb - 2 + a.PB) / a.PB - 1, 0, a.nb - 1);
+                cp_poll(cd + b, target, a.spin_limit);
+            } else {
+                const int b_last = ca_min(a.nb - 1, (q - a.xb + 2) / a.PB);
+                if (b_last > 0) cp_poll(cd + b_last - 1, target, a.spin_limit);
+                cp_poll(cd + b_last, target, a.spin_limit);
+            }
         }
         CPP_T(p1);
         CPP_ACC(6, p0, p1);
@@ -482,7 +496,11 @@ static __device__ __forceinline__ void cp_consumer(const CorrPipeArgs& a, float*
     const int ty0 = tile * CP_TYC;
     // the item's block of H planes
     const int ob = a.xb + blk * a.PB, oe = ca_min(ob + a.PB, a.xe);
-    const int rs = ca_max(a.r0, ob - 2), re = ca_min(a.r1, oe + 2);
+    // with the hand-over, a block other than the first starts from its predecessor's last four in-plane results (the planes
+    // ob-2 .. ob+1) and filters the planes from ob+2 on; else it filters its own 2 + 2 halo planes again
+    const bool hand = TDP && a.state != nullptr;
+    const bool from_state = hand && blk > 0;
+    const int rs = from_state ? ob + 2 : ca_max(a.r0, ob - 2), re = ca_min(a.r1, oe + 2);
     unsigned long long* full = bars;
     constexpr int NST = TDP ? CP_NST_TDP : CP_NST;
     unsigned long long* empty = bars + CP_NSTMAX;
@@ -493,7 +511,7 @@ static __device__ __forceinline__ void cp_consumer(const CorrPipeArgs& a, float*
         ca_mbarx_init(dbar, ncw);
     }
     __syncthreads();
-    const int nraw = re - rs;
+    const int nraw = ca_max(re - rs, 0);
     CPP_T(q0);
     if (tid == a.ldr) {
         // ring rows [ty0, ty0+20) of the label <-> y = ty0-2 .. ty0+17; rows 0, 1 and >= w+2 and the pad columns are zero
@@ -536,9 +554,25 @@ static __device__ __forceinline__ void cp_consumer(const CorrPipeArgs& a, float*
         for (int s = 0; s < 4; ++s)
 #pragma unroll
             for (int o = 0; o < 4; ++o) hs[s][o][0] = hs[s][o][1] = make_float2(0.f, 0.f);
+        unsigned nbar = 0;                      // barriers of the compute threads so far (TDP; the other path counts planes)
+        unsigned* flag = a.colflag + (size_t)chunk * a.ncolsmax + col;
         if (!TDP) {
             cp_phase_a(rs, a, t, full, empty);
             cp_compute_barrier(dbar, 0u, a.ncomp, t.cmask, t.elect);
+        }
+        if (from_state) {
+            // the predecessor (same column, block blk-1: a smaller ticket) has stored its state and released the flag
+            if (tid == 0) cp_poll(flag, (unsigned)blk, a.spin_limit);
+            cp_compute_barrier(dbar, nbar++ & 1u, a.ncomp, t.cmask, t.elect);
+            const float4* sp = reinterpret_cast<const float4*>(a.state) +
+                               ((size_t)((chunk & 1) * 2 + ((blk - 1) & 1)) * a.ncolsmax + col) * (size_t)(16 * a.ncomp) + tid;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const float4 v = cp_ld4_cg(sp + (k * 4 + o) * a.ncomp);
+                    hs[k][o][0] = make_float2(v.x, v.y); hs[k][o][1] = make_float2(v.z, v.w);
+                }
         }
         for (int X = rs; X <= oe + 1; X += 4) {
             cp_consumer_step<0, TDP>(X, a, t, full, empty, dbar, hs);
@@ -548,10 +582,36 @@ static __device__ __forceinline__ void cp_consumer(const CorrPipeArgs& a, float*
         }
         CPP_T(q1);
         if (tid == 0) { CPP_ACC(13, q0, q1); CPP_CNT(14); }
-        // every plane of the block has been fetched and used by every compute thread: the item is done with the ring
-        // (barrier number nraw of the compute threads: the prologue's and one per step that had a plane to prepare)
-        cp_compute_barrier(dbar, TDP ? 0u : (unsigned)nraw & 1u, a.ncomp, t.cmask, t.elect);
-        if (tid == 0) cp_signal_relaxed(a.ctr + 2 + a.nseq + chunk * a.nb + blk);
+        if (hand) {
+            if (blk < a.nb - 1) {
+                // the state buffer of (chunk parity, block parity) was last read by block blk+1 of chunk-2: that one must be done
+                if (tid == 0 && chunk >= 2 && col < a.nw[(chunk - 2) / S] * S * a.ntC)
+                    cp_poll(a.colflag + (size_t)(chunk - 2) * a.ncolsmax + col, (unsigned)ca_min(blk + 2, a.nb), a.spin_limit);
+                cp_compute_barrier(dbar, nbar++ & 1u, a.ncomp, t.cmask, t.elect);
+                float4* sp = reinterpret_cast<float4*>(a.state) +
+                             ((size_t)((chunk & 1) * 2 + (blk & 1)) * a.ncolsmax + col) * (size_t)(16 * a.ncomp) + tid;
+                // oldest first: after n = oe + 2 - rs steps the in-plane result of plane oe-2+k sits in slot (n + k) mod 4
+                const int rot = (oe + 2 - rs) & 3;
+#define CP_STORE_STATE(R)                                                                                              \
+    _Pragma("unroll") for (int k = 0; k < 4; ++k) _Pragma("unroll") for (int o = 0; o < 4; ++o)                        \
+        cp_st4_cg(sp + (k * 4 + o) * a.ncomp, make_float4(hs[(R + k) & 3][o][0].x, hs[(R + k) & 3][o][0].y,            \
+                                                          hs[(R + k) & 3][o][1].x, hs[(R + k) & 3][o][1].y))
+                if (rot == 0) { CP_STORE_STATE(0); } else if (rot == 1) { CP_STORE_STATE(1); } else if (rot == 2) { CP_STORE_STATE(2); } else { CP_STORE_STATE(3); }
+#undef CP_STORE_STATE
+            }
+            // every plane of the block has been fetched and used, the state is stored: release the column's flag (the barrier
+            // orders every thread's stores before thread 0's release) and hand the ring planes back
+            cp_compute_barrier(dbar, nbar++ & 1u, a.ncomp, t.cmask, t.elect);
+            if (tid == 0) {
+                cp_signal(flag);
+                cp_signal_relaxed(a.ctr + 2 + a.nseq + chunk * a.nb + blk);
+            }
+        } else {
+            // every plane of the block has been fetched and used by every compute thread: the item is done with the ring
+            // (barrier number nraw of the compute threads: the prologue's and one per step that had a plane to prepare)
+            cp_compute_barrier(dbar, TDP ? 0u : (unsigned)nraw & 1u, a.ncomp, t.cmask, t.elect);
+            if (tid == 0) cp_signal_relaxed(a.ctr + 2 + a.nseq + chunk * a.nb + blk);
+        }
     }
 }
 
@@ -616,6 +676,7 @@ int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 size_t cp_align256(size_t v) { return (v + 255) & ~(size_t)255; }
+int g_last_cfg[6] = {0, 0, 0, 0, 0, 0};     // NW, PB, R, T_D in the producers, state hand-over, launches: what the last launch ran with
 
 struct PipeGeom {
     int nq, ncomp, ldr, nt;
@@ -681,10 +742,18 @@ int launch_pipe(const float* fix, const float* mov, int C, int h, int w, int d, 
     a.ng = (S + NW - 1) / NW;
     const int nchunks = a.ng * S;
     a.nseq = nchunks * a.nx;
-    const size_t ctr_bytes = cp_align256((size_t)(2 + (size_t)a.nseq + (size_t)nchunks * (size_t)(xe - xb)) * sizeof(unsigned));
+    a.ncolsmax = NW * S * pg.ntC;
+    const size_t nctr = 2 + (size_t)a.nseq + (size_t)nchunks * (size_t)(xe - xb) + (size_t)nchunks * a.ncolsmax;
+    const size_t ctr_bytes = cp_align256(nctr * sizeof(unsigned));
+    // hand-over of the march state between the H blocks of a column (only with T_D inside the producers): 16 float4 per compute
+    // thread, double-buffered by block parity and by chunk parity.  Opt-in (CA_PIPE_HANDOFF=1), measured and rejected: it saves
+    // the (PB+4)/PB in-plane halo of the consumers but chains the blocks of a column -- a consumer holds its SM slot until its
+    // predecessor is done -- 6.89 instead of 6.36 ms per direction at config 2.  Default: every block filters its own halo planes.
+    size_t state_bytes = tdp && env_int("CA_PIPE_HANDOFF", 0) != 0 ? cp_align256((size_t)4 * a.ncolsmax * 16 * pg.ncomp * sizeof(float4)) : 0;
+    if (ws_bytes < ctr_bytes + state_bytes + 12 * slot_bytes) state_bytes = 0;
     if (ws_bytes < ctr_bytes + 12 * slot_bytes) return CA_ERR_UNSUPPORTED;
     const int r_cap = ca_min(ca_max(env_int("CA_PIPE_R", 2 * a.PB + 4), 12), CP_RMAX);
-    a.R = (int)ca_min((int64_t)r_cap, (int64_t)((ws_bytes - ctr_bytes) / slot_bytes));
+    a.R = (int)ca_min((int64_t)r_cap, (int64_t)((ws_bytes - ctr_bytes - state_bytes) / slot_bytes));
     if (a.PB > a.R - 4) a.PB = a.R - 4;
     a.nb = (xe - xb + a.PB - 1) / a.PB;
     if (a.nb > CP_MAXB) return CA_ERR_UNSUPPORTED;
@@ -700,7 +769,9 @@ int launch_pipe(const float* fix, const float* mov, int C, int h, int w, int d, 
     }
     a.tstart[a.ng] = tick;
     a.ctr = (unsigned*)ws;
-    a.ring = (float*)((char*)ws + ctr_bytes);
+    a.colflag = a.ctr + 2 + (size_t)a.nseq + (size_t)nchunks * (size_t)(xe - xb);
+    a.state = state_bytes ? (float*)((char*)ws + ctr_bytes) : nullptr;
+    a.ring = (float*)((char*)ws + ctr_bytes + state_bytes);
 #ifdef CA_EMU
     a.spin_limit = 1u << 20;
 #else
@@ -713,10 +784,12 @@ int launch_pipe(const float* fix, const float* mov, int C, int h, int w, int d, 
     if (rc != CA_OK) return rc;
     void* tmg = ca_timing_begin(CA_T_PIPE, st);
     // counters to zero; ring to zero (its halo rows and pad columns are never written by the kernel)
-    if (cudaMemsetAsync(ws, 0, ctr_bytes + (size_t)a.R * slot_bytes, st) != cudaSuccess) {
+    if (cudaMemsetAsync(ws, 0, ctr_bytes, st) != cudaSuccess ||
+        cudaMemsetAsync(a.ring, 0, (size_t)a.R * slot_bytes, st) != cudaSuccess) {
         ca_set_error("correlate (pipe): memset failed");
         return CA_ERR_LAUNCH;
     }
+    g_last_cfg[0] = NW; g_last_cfg[1] = a.PB; g_last_cfg[2] = a.R; g_last_cfg[3] = tdp; g_last_cfg[4] = a.state != nullptr; ++g_last_cfg[5];
     const dim3 grid(tick), block((unsigned)pg.nt);
     CA_SMEM_OPTIN(k, 110 * 1024);
     CA_LAUNCH(k, grid, block, smem, st, tmF, tmM, a);
@@ -732,7 +805,8 @@ size_t ca_corr_pipe_workspace_bytes(int C, int h, int w, int d, int disp_hw) {
     if (!pipe_geom(C, w, d, disp_hw, &pg)) return 0;
     const int S = 2 * disp_hw + 1;
     const size_t nseq = (size_t)S * S * (size_t)h;       // >= nchunks * nx and >= nchunks * nb
-    return cp_align256((2 + 2 * nseq) * sizeof(unsigned)) + (size_t)CP_RMAX * 4 * S * pg.labelPlane * sizeof(float) + 256;
+    return cp_align256((2 + 2 * nseq + (size_t)S * S * 4 * S * pg.ntC) * sizeof(unsigned)) + (size_t)CP_RMAX * 4 * S * pg.labelPlane * sizeof(float) +
+           (size_t)4 * 4 * S * pg.ntC * 16 * pg.ncomp * sizeof(float4) + 512;
 }
 
 // fix, mov: unpadded (C,h,w,d) volumes, 16-byte aligned, d % 4 == 0.  Returns CA_ERR_UNSUPPORTED (without an error message
@@ -756,6 +830,11 @@ int ca_launch_corr_pipe(const float* fix, const float* mov, int C, int h, int w,
         default: rc = CA_ERR_UNSUPPORTED; break;
     }
     return rc;
+}
+
+// test / debug aid: {NW, PB, R, T_D in the producers, state hand-over, number of launches so far} of the last launch
+extern "C" __attribute__((visibility("default"))) void ca_debug_corr_pipe_config(int* out) {
+    for (int i = 0; i < 6; ++i) out[i] = g_last_cfg[i];
 }
 
 // test / debug aid: non-zero when a hand-off wait of the last launches gave up (see cp_poll)

@@ -77,10 +77,10 @@ def test_certified_pipe_kernel(lib, monkeypatch):
     kc.check_certified(lib, DEV, cases=((12, 4, 5, 8, 2), (7, 3, 14, 36, 2), (5, 9, 35, 20, 3), (3, 21, 7, 8, 2), (3, 30, 20, 16, 1),
                                         (3, 12, 20, 128, 1)))     # the last: rows of one warp of quads, T_D inside the producers
     for knobs in ({"CA_PIPE_PB": "4", "CA_PIPE_R": "12"}, {"CA_PIPE_PB": "9", "CA_PIPE_R": "13", "CA_PIPE_NW": "1"},
-                  {"CA_PIPE_PB": "60", "CA_PIPE_NW": "3"}):
+                  {"CA_PIPE_PB": "60", "CA_PIPE_NW": "3"}, {"CA_PIPE_HANDOFF": "1", "CA_PIPE_PB": "5"}, {"CA_PIPE_TDP": "0"}):
         for k, v in knobs.items():
             monkeypatch.setenv(k, v)
-        kc.check_certified(lib, DEV, cases=((7, 3, 14, 36, 2), (3, 21, 7, 8, 2)), tie_case=False)
+        kc.check_certified(lib, DEV, cases=((7, 3, 14, 36, 2), (3, 21, 7, 8, 2), (2, 21, 7, 128, 2)), tie_case=False)
         for k in knobs:
             monkeypatch.delenv(k)
     assert fn(1) == 0, "a hand-off wait of the producer / consumer kernel gave up"

@@ -133,7 +133,7 @@ def test_certified_pipe_kernel(lib, dev, pipe_correlate):
 
 @pytest.mark.parametrize("knobs", [{"CA_PIPE_PB": "4", "CA_PIPE_R": "12"}, {"CA_PIPE_PB": "9", "CA_PIPE_R": "13", "CA_PIPE_NW": "1"},
                                    {"CA_PIPE_PB": "60", "CA_PIPE_NW": "3"}, {"CA_PIPE_PB": "8", "CA_PIPE_NW": "2", "CA_PIPE_R": "40"},
-                                   {"CA_PIPE_TDP": "0"}])
+                                   {"CA_PIPE_TDP": "0"}, {"CA_PIPE_HANDOFF": "1"}, {"CA_PIPE_HANDOFF": "1", "CA_PIPE_PB": "5", "CA_PIPE_NW": "2"}])
 def test_certified_pipe_kernel_knobs(lib, dev, pipe_correlate, monkeypatch, knobs):
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)
@@ -142,11 +142,22 @@ def test_certified_pipe_kernel_knobs(lib, dev, pipe_correlate, monkeypatch, knob
     assert _pipe_error_flag(lib) == 0
 
 
+def _pipe_config(lib):
+    import ctypes
+    cfg = (ctypes.c_int * 6)()
+    lib.dll.ca_debug_corr_pipe_config(cfg)
+    return dict(zip(("NW", "PB", "R", "tdp", "handoff", "launches"), cfg))
+
+
 def test_full_size_pipe_kernel_certified_equals_exact(lib, full_volume, pipe_correlate):
     """The producer / consumer kernel's volume at BASELINE config 2 size: inside the bound, and the same certified selections."""
     _pipe_error_flag(lib)
+    n0 = _pipe_config(lib)["launches"]
     test_full_size_certified_equals_exact(lib, full_volume)
     assert _pipe_error_flag(lib) == 0
+    cfg = _pipe_config(lib)
+    print("producer / consumer kernel ran with", cfg)
+    assert cfg["launches"] > n0 and cfg["tdp"] == 1, "the full-size volume did not go through k_corr_pipe (T_D inside the producers)"
 
 
 def test_correlate_rejects_bad_arguments(lib, dev):
