@@ -41,11 +41,13 @@ struct AdamGeom {
     float gmul[3];    // d(position)/d(u) = (size/2) / sc
     float reg[3];     // 2*lambda / count per axis (MIND.py:167-169)
     float gscale;     // 2 * 12 / (C * N)  (MIND.py:176-177: mean over channels, *12, mean over voxels)
+    int vs, gs;       // feature groups: float4 index = voxel * vs + group * gs  ((n, CG): vs = CG, gs = 1; (CG, n): vs = 1, gs = n)
+    int flip;         // 1: the CTAs walk the H planes downwards (alternate iterations: the planes touched last are still in L2)
 };
 
 // planar (C,n) -> channel-last (n, CG) float4 groups, zero padded to a multiple of 4 channels: the 8-corner gather
 // of the moving features then costs 8*CG 128-bit loads per voxel instead of 8*C scalar ones.
-__global__ void __launch_bounds__(256) k_planar_to_cl(const float* __restrict__ in, int C, int CG, int64_t n,
+__global__ void __launch_bounds__(256) k_planar_to_cl(const float* __restrict__ in, int C, int CG, int64_t n, int64_t vs, int64_t gs,
                                                       float4* __restrict__ out) {
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x)
         for (int cg = 0; cg < CG; ++cg) {
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(256) k_planar_to_cl(const float* __restrict__ 
             o.y = (4 * cg + 1 < C) ? __ldg(in + (int64_t)(4 * cg + 1) * n + v) : 0.f;
             o.z = (4 * cg + 2 < C) ? __ldg(in + (int64_t)(4 * cg + 2) * n + v) : 0.f;
             o.w = (4 * cg + 3 < C) ? __ldg(in + (int64_t)(4 * cg + 3) * n + v) : 0.f;
-            out[v * CG + cg] = o;
+            out[v * vs + cg * gs] = o;
         }
 }
 
@@ -74,7 +76,8 @@ __global__ void __launch_bounds__(128, MINB) k_adam_grad(const float* __restrict
     const int ha = g.ha, wa = g.wa, da = g.da;
     const int n = g.hl * wa * da;                   // field arrays: window-local indexing
     const int z = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    const int y = (int)(blockIdx.y * blockDim.y + threadIdx.y), xl = (int)(blockIdx.z * blockDim.z + threadIdx.z), x = xl + g.lo;
+    const int y = (int)(blockIdx.y * blockDim.y + threadIdx.y);
+    const int xr = (int)(blockIdx.z * blockDim.z + threadIdx.z), xl = g.flip ? (int)(gridDim.z * blockDim.z) - 1 - xr : xr, x = xl + g.lo;
     if (z >= da || y >= wa || xl >= g.hl) return;
     const int o = (xl * wa + y) * da + z;
     const int of = (x * wa + y) * da + z;           // feature arrays: whole-grid indexing
@@ -170,6 +173,119 @@ __global__ void __launch_bounds__(128, MINB) k_adam_grad(const float* __restrict
     gu[o] = g.gscale * giz * g.gmul[0] + greg[0];
 }
 
+// Second form of the gradient kernel (default): the same values with about a third fewer instructions -- the first form
+// executes 1 040 instructions per voxel, 45 % of them before the channel loop, at 52 % of the issue slots
+// (profiles/r2_ncu_k_adam_grad.txt).  (a) Corners outside the volume are not predicated: their coordinates are clamped, so every
+// gather is a plain load, and their WEIGHT is zero -- `smp + val * 0` is `smp`, bit for bit, which is torch skipping the corner
+// (GridSampler.h within_bounds); (b) the dot products residual . corner accumulate over the channel groups and the twelve corner
+// differences are formed once after the loop (the first form did that per group; the order of these additions is not the
+// reference's in either form -- autograd's is not restatable -- and the result stays inside the same tolerance);
+// (c) the regulariser reads its neighbours at clamped offsets instead of under predicates (`uc - uc` adds +0);
+// (d) x / 2 is x * 0.5 (exact).
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_adam_grad2(const float* __restrict__ u, const float4* __restrict__ fixcl,
+                                                    const float4* __restrict__ movcl, int CG, AdamGeom g,
+                                                    const float* __restrict__ g0x, const float* __restrict__ g0y,
+                                                    const float* __restrict__ g0z, float* __restrict__ gu) {
+    ca_grid_dep_launch();
+    ca_grid_dep_wait();
+    const int ha = g.ha, wa = g.wa, da = g.da;
+    const int n = g.hl * wa * da;
+    const int z = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int y = (int)(blockIdx.y * blockDim.y + threadIdx.y);
+    const int xr = (int)(blockIdx.z * blockDim.z + threadIdx.z), xl = g.flip ? (int)(gridDim.z * blockDim.z) - 1 - xr : xr, x = xl + g.lo;
+    if (z >= da || y >= wa || xl >= g.hl) return;
+    const int o = (xl * wa + y) * da + z;
+    const int of = (x * wa + y) * da + z;
+    const float uc[3] = {u[o], u[n + o], u[2 * n + o]};
+    float greg[3];
+    {
+        // a window edge that is not a face of the grid has no neighbour plane: that row of the window is margin the caller
+        // discards (slab.py); a missing neighbour is read as the voxel itself and contributes uc - uc = +0
+        const int dlo[3] = {xl > 0 ? -wa * da : 0, y > 0 ? -da : 0, z > 0 ? -1 : 0};
+        const int dhi[3] = {xl < g.hl - 1 ? wa * da : 0, y < wa - 1 ? da : 0, z < da - 1 ? 1 : 0};
+        float lo[3][3], hi[3][3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+                lo[ch][ax] = u[ch * n + o + dlo[ax]];
+                hi[ch][ax] = u[ch * n + o + dhi[ax]];
+            }
+        // (a face of the GRID has a one-sided difference: there the window ends too, and the missing side adds +0)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float gr = 0.f;
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) gr += g.reg[ax] * ((uc[ch] - lo[ch][ax]) + (uc[ch] - hi[ch][ax]));
+            greg[ch] = gr;
+        }
+    }
+    // grid_disp = grid0 + (u/scale).flip(1)   (MIND.py:171), then GridSampler.h:27-36, every op rounded as torch does
+    const float cx = __fadd_rn(g0x[z], ca_div(uc[2], g.sc[2]));
+    const float cy = __fadd_rn(g0y[y], ca_div(uc[1], g.sc[1]));
+    const float cz = __fadd_rn(g0z[x], ca_div(uc[0], g.sc[0]));
+    const float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(cx, 1.f), (float)da), 1.f), 0.5f);
+    const float iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(cy, 1.f), (float)wa), 1.f), 0.5f);
+    const float iz = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(cz, 1.f), (float)ha), 1.f), 0.5f);
+    const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+    const float tx = __fsub_rn(ix, fx), ty = __fsub_rn(iy, fy), tz = __fsub_rn(iz, fz);
+    const float sx = __fsub_rn(__fadd_rn(fx, 1.f), ix), sy = __fsub_rn(__fadd_rn(fy, 1.f), iy), sz = __fsub_rn(__fadd_rn(fz, 1.f), iz);
+    const int x0 = (int)fminf(fmaxf(fx, -2.f), 1.0e9f), y0 = (int)fminf(fmaxf(fy, -2.f), 1.0e9f), z0 = (int)fminf(fmaxf(fz, -2.f), 1.0e9f);
+    // per axis: is the low / high corner inside, and its clamped coordinate
+    const bool vx[2] = {x0 >= 0 && x0 < da, x0 + 1 >= 0 && x0 + 1 < da};
+    const bool vy[2] = {y0 >= 0 && y0 < wa, y0 + 1 >= 0 && y0 + 1 < wa};
+    const bool vz[2] = {z0 >= 0 && z0 < ha, z0 + 1 >= 0 && z0 + 1 < ha};
+    const int xc[2] = {ca_min(ca_max(x0, 0), da - 1) * g.vs, ca_min(ca_max(x0 + 1, 0), da - 1) * g.vs};
+    const int yc[2] = {ca_min(ca_max(y0, 0), wa - 1), ca_min(ca_max(y0 + 1, 0), wa - 1)};
+    const int zc[2] = {ca_min(ca_max(z0, 0), ha - 1), ca_min(ca_max(z0 + 1, 0), ha - 1)};
+    float wgt[8];
+    wgt[0] = __fmul_rn(__fmul_rn(sx, sy), sz); wgt[1] = __fmul_rn(__fmul_rn(tx, sy), sz);
+    wgt[2] = __fmul_rn(__fmul_rn(sx, ty), sz); wgt[3] = __fmul_rn(__fmul_rn(tx, ty), sz);
+    wgt[4] = __fmul_rn(__fmul_rn(sx, sy), tz); wgt[5] = __fmul_rn(__fmul_rn(tx, sy), tz);
+    wgt[6] = __fmul_rn(__fmul_rn(sx, ty), tz); wgt[7] = __fmul_rn(__fmul_rn(tx, ty), tz);
+    int off[8];
+    unsigned inmask = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const bool in = vx[t & 1] && vy[(t >> 1) & 1] && vz[(t >> 2) & 1];
+        if (!in) wgt[t] = 0.f;
+        inmask |= in ? 1u << t : 0u;
+        off[t] = (zc[(t >> 2) & 1] * wa + yc[(t >> 1) & 1]) * da * g.vs + xc[t & 1];
+    }
+    float dot[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) dot[t] = 0.f;
+    const float4* fp = fixcl + (int64_t)of * g.vs;
+    for (int cg = 0; cg < CG; ++cg, movcl += g.gs, fp += g.gs) {
+        float4 val[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) val[t] = __ldg(movcl + off[t]);
+        const float4 f = __ldg(fp);
+        float4 smp = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {      // torch's corner order (tnw, tne, tsw, tse, bnw, ...), products and sums rounded separately
+            smp.x = __fadd_rn(smp.x, __fmul_rn(val[t].x, wgt[t]));
+            smp.y = __fadd_rn(smp.y, __fmul_rn(val[t].y, wgt[t]));
+            smp.z = __fadd_rn(smp.z, __fmul_rn(val[t].z, wgt[t]));
+            smp.w = __fadd_rn(smp.w, __fmul_rn(val[t].w, wgt[t]));
+        }
+        const float rx = smp.x - f.x, ry = smp.y - f.y, rz = smp.z - f.z, rw = smp.w - f.w;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) dot[t] += rx * val[t].x + ry * val[t].y + rz * val[t].z + rw * val[t].w;
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+        if (!(inmask >> t & 1u)) dot[t] = 0.f;          // a corner outside the volume carries no gradient
+    // d(w_t)/d(ix) = +-(Y_t Z_t) etc.: sum_t val_t dw_t = sum over corner pairs of (val_hi - val_lo) * (product of the other two)
+    const float gix = (sy * sz) * (dot[1] - dot[0]) + (ty * sz) * (dot[3] - dot[2]) + (sy * tz) * (dot[5] - dot[4]) + (ty * tz) * (dot[7] - dot[6]);
+    const float giy = (sx * sz) * (dot[2] - dot[0]) + (tx * sz) * (dot[3] - dot[1]) + (sx * tz) * (dot[6] - dot[4]) + (tx * tz) * (dot[7] - dot[5]);
+    const float giz = (sx * sy) * (dot[4] - dot[0]) + (tx * sy) * (dot[5] - dot[1]) + (sx * ty) * (dot[6] - dot[2]) + (tx * ty) * (dot[7] - dot[3]);
+    gu[2 * n + o] = g.gscale * gix * g.gmul[2] + greg[2];
+    gu[n + o] = g.gscale * giy * g.gmul[1] + greg[1];
+    gu[o] = g.gscale * giz * g.gmul[0] + greg[0];
+}
+
 #ifndef CA_GRAD_MINB
 #define CA_GRAD_MINB 5
 #endif
@@ -207,6 +323,7 @@ struct Box3Args {
     int Ty, ntiles, Ly;           // k_box3_p: output rows per CTA, row tiles per plane, rows per thread
     float *p, *m, *v;
     AdamScalars s;
+    int flip;                     // 1: segments / planes and channels are walked in descending order (see AdamGeom::flip)
 };
 
 static __device__ __forceinline__ float4 f4add3(const float4& a, const float4& b, const float4& c) {
@@ -221,10 +338,11 @@ __global__ void __launch_bounds__(128) k_box3_h(Box3Args a) {
     ca_grid_dep_wait();
     const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (t >= a.w * a.nq) return;
-    const int xs = (int)blockIdx.y * LX, xe = ca_min(a.h, xs + LX);
+    const int by = a.flip ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y, bz = a.flip ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+    const int xs = by * LX, xe = ca_min(a.h, xs + LX);
     const int64_t plane = (int64_t)a.w * a.d;
-    const float* ip = a.in + (int64_t)blockIdx.z * a.h * plane + (int64_t)t * 4;
-    float* op = a.out + (int64_t)blockIdx.z * a.h * plane + (int64_t)t * 4;
+    const float* ip = a.in + (int64_t)bz * a.h * plane + (int64_t)t * 4;
+    float* op = a.out + (int64_t)bz * a.h * plane + (int64_t)t * 4;
     float4 v[LX + 6];
 #pragma unroll
     for (int i = 0; i < LX + 6; ++i) {           // all loads of the segment go out together
@@ -259,7 +377,8 @@ __global__ void __launch_bounds__(256) k_box3_p(Box3Args a) {
     const int nq = a.nq, d = a.d;
     float* A = sm;
     float* B = sm + (size_t)(a.Ty + 6) * d;
-    const int64_t plane_off = ((int64_t)blockIdx.z * a.h + blockIdx.y) * a.w * d;
+    const int by = a.flip ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y, bz = a.flip ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+    const int64_t plane_off = ((int64_t)bz * a.h + by) * a.w * d;
     for (int i = tid; i < nrows * nq; i += nthr) {
         const int r = i / nq, q = i - r * nq, y = ty0 - 3 + r;
         *reinterpret_cast<float4*>(A + r * d + 4 * q) =
@@ -343,28 +462,55 @@ static inline unsigned adam_grid(int64_t n, int block) {
     return (unsigned)(b < 1 ? 1 : b);
 }
 
-#define CA_BOX3_LX 12
+#define CA_BOX3_LX 6
 #define CA_BOX3_SMEM (96 * 1024)
+
+// tuning knobs, read once per process (defaults = the measured best)
+static int adam_env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+struct AdamKnobs { int grad, flip, bx, by, bz, ty, lx, layout, minb; };
+static const AdamKnobs& adam_knobs() {
+    static const AdamKnobs k = {
+        adam_env("CA_ADAM_GRAD", 2),     // 1: first form of the gradient kernel, 2: k_adam_grad2
+        adam_env("CA_ADAM_FLIP", 1),     // bit 0: gradient kernel, bit 1: box kernels walk the planes downwards on odd iterations
+        adam_env("CA_ADAM_BX", 32), adam_env("CA_ADAM_BY", 4), adam_env("CA_ADAM_BZ", 1),    // voxels per CTA of the gradient kernel (product 128)
+        adam_env("CA_BOX3_TY", 0),       // rows per CTA of k_box3_p (0: as many as fit 96 KB of shared memory)
+        adam_env("CA_BOX3_LX", CA_BOX3_LX),   // planes per thread of k_box3_h: 6, 8, 12 or 16
+        adam_env("CA_ADAM_LAYOUT", 1),   // feature groups 0: (n, CG) voxel-major, 1: (CG, n) group-planar (k_adam_grad2 only)
+        adam_env("CA_ADAM_MINB", CA_GRAD_MINB),   // resident CTAs per SM the gradient kernel is compiled for: 4, 5, 6 or 8
+    };
+    return k;
+}
 
 // rows per CTA of k_box3_p such that both shared-memory buffers fit; 0: the plane rows are too long
 static int box3_rows_per_tile(int wa, int da) {
-    const int maxrows = (int)(CA_BOX3_SMEM / ((size_t)2 * da * 4)) - 6;
+    int maxrows = (int)(CA_BOX3_SMEM / ((size_t)2 * da * 4)) - 6;
     if (maxrows < 1) return 0;
+    if (adam_knobs().ty > 0 && adam_knobs().ty < maxrows) maxrows = adam_knobs().ty;
     const int nt = (wa + maxrows - 1) / maxrows;
     return (wa + nt - 1) / nt;
 }
 
 // out = B^3 in on a (3, h, w, d) field, through the scratch field tmp; with `upd` the result drives the Adam step
 // (and is stored only if out != null)
-static int box3_cubed(const float* in, float* tmp, float* out, int ha, int wa, int da, const Box3Args* upd, cudaStream_t st) {
+static int box3_cubed(const float* in, float* tmp, float* out, int ha, int wa, int da, const Box3Args* upd, int flip, cudaStream_t st) {
     Box3Args a;
     if (upd) a = *upd;
+    a.flip = flip;
     a.h = ha; a.w = wa; a.d = da; a.nq = da / 4;
     a.in = in; a.out = tmp;
     {
-        const dim3 grid((unsigned)ca_divup((int64_t)wa * a.nq, 128), (unsigned)ca_divup(ha, CA_BOX3_LX), 3u);
-        auto k = k_box3_h<CA_BOX3_LX>;
-        CA_LAUNCH_PDL(k, grid, dim3(128), 0, st, a);
+        const int lx = adam_knobs().lx;
+        const dim3 grid((unsigned)ca_divup((int64_t)wa * a.nq, 128), (unsigned)ca_divup(ha, lx), 3u);
+        switch (lx) {
+            case 6: CA_LAUNCH_PDL(k_box3_h<6>, grid, dim3(128), 0, st, a); break;
+            case 8: CA_LAUNCH_PDL(k_box3_h<8>, grid, dim3(128), 0, st, a); break;
+            case 12: CA_LAUNCH_PDL(k_box3_h<12>, grid, dim3(128), 0, st, a); break;
+            case 16: CA_LAUNCH_PDL(k_box3_h<16>, grid, dim3(128), 0, st, a); break;
+            default: ca_set_error("adam_run: CA_BOX3_LX must be 6, 8, 12 or 16"); return CA_ERR_BAD_ARGUMENT;
+        }
         CA_CHECK_LAUNCH("box3_h");
     }
     a.in = tmp; a.out = out;
@@ -418,13 +564,18 @@ extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int
                       (((uintptr_t)p | (uintptr_t)m | (uintptr_t)v | (uintptr_t)u_out | (uintptr_t)g_out) & 15) == 0;
     (void)zero_row;
     auto box = [&](const float* in, float* out) -> int { return ca_launch_avgpool3d(in, 3, hl, wa, da, 3, 1, 1, out, st); };
+    const AdamKnobs& kn = adam_knobs();
+    CA_CHECK_ARG(kn.bx > 0 && kn.by > 0 && kn.bz > 0 && kn.bx * kn.by * kn.bz == 128, "adam_run: CA_ADAM_BX * BY * BZ must be 128");
+    const bool planar_groups = kn.layout == 1 && kn.grad != 1;
+    const int fvs = planar_groups ? 1 : CG, fgs = planar_groups ? (int)n : 1;
     if (niter > 0 && !features_ready) {
         const unsigned gb = adam_grid(n, 256);
-        CA_LAUNCH(k_planar_to_cl, dim3(gb), dim3(256), 0, st, fix, C, CG, n, fixcl);
-        CA_LAUNCH(k_planar_to_cl, dim3(gb), dim3(256), 0, st, mov, C, CG, n, movcl);
+        CA_LAUNCH(k_planar_to_cl, dim3(gb), dim3(256), 0, st, fix, C, CG, n, (int64_t)fvs, (int64_t)fgs, fixcl);
+        CA_LAUNCH(k_planar_to_cl, dim3(gb), dim3(256), 0, st, mov, C, CG, n, (int64_t)fvs, (int64_t)fgs, movcl);
         CA_CHECK_LAUNCH("adam/planar_to_cl");
     }
     AdamGeom g;
+    g.flip = 0; g.vs = fvs; g.gs = fgs;
     g.ha = ha; g.wa = wa; g.da = da; g.C = C; g.lo = lo; g.hl = hl;
     const int dims[3] = {ha, wa, da};
     const double cnt[3] = {3.0 * (ha - 1) * wa * da, 3.0 * ha * (wa - 1) * da, 3.0 * ha * wa * (da - 1)};
@@ -438,19 +589,32 @@ extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int
     for (int it = 0; it < niter; ++it) {
         const int step = first_step + it;
         int rc;
+        // odd steps walk the grid downwards: what the previous iteration touched last is what this one touches first, so the
+        // part of the features + fields (165 MB at config 2) that the 126 MB L2 still holds is hit instead of cycled out
+        const int flip_box = (kn.flip & 2) ? (step & 1) : 0;
+        g.flip = (kn.flip & 1) ? (step & 1) : 0;
         if (fast) {
-            if ((rc = box3_cubed(p, t0, u_out, hl, wa, da, nullptr, st)) != CA_OK) return rc;
+            if ((rc = box3_cubed(p, t0, u_out, hl, wa, da, nullptr, flip_box, st)) != CA_OK) return rc;
         } else {
             if ((rc = box(p, t0)) != CA_OK) return rc;
             if ((rc = box(t0, t1)) != CA_OK) return rc;
             if ((rc = box(t1, u_out)) != CA_OK) return rc;
         }
-        const int bx = 32, by = 4, bz = 1;      // 32 x 4 voxels per CTA: neighbouring rows share corner gathers in L1
+        const int bx = kn.bx, by = kn.by, bz = kn.bz;      // 32 x 4 voxels per CTA: neighbouring rows share corner gathers in L1
         void* tmg = ca_timing_begin(CA_T_ADAM_GRAD, st);
         const dim3 ggrid((unsigned)((da + bx - 1) / bx), (unsigned)((wa + by - 1) / by), (unsigned)((hl + bz - 1) / bz)), gblock(bx, by, bz);
         // (compile-time group counts with the loop unrolled -- all 24 gathers of a voxel in flight -- were measured slower: 9.5-10.6
         // against 8.9 ms per 100 iterations; the kernel wants resident warps more than loads per warp)
-        CA_LAUNCH_PDL((k_adam_grad<0, CA_GRAD_MINB>), ggrid, gblock, 0, st, (const float*)u_out, (const float4*)fixcl, (const float4*)movcl, CG, g, g0x, g0y, g0z, gu);
+        if (kn.grad == 1)
+            CA_LAUNCH_PDL((k_adam_grad<0, CA_GRAD_MINB>), ggrid, gblock, 0, st, (const float*)u_out, (const float4*)fixcl, (const float4*)movcl, CG, g, g0x, g0y, g0z, gu);
+        else if (kn.minb == 4)
+            CA_LAUNCH_PDL((k_adam_grad2<4>), ggrid, gblock, 0, st, (const float*)u_out, (const float4*)fixcl, (const float4*)movcl, CG, g, g0x, g0y, g0z, gu);
+        else if (kn.minb == 6)
+            CA_LAUNCH_PDL((k_adam_grad2<6>), ggrid, gblock, 0, st, (const float*)u_out, (const float4*)fixcl, (const float4*)movcl, CG, g, g0x, g0y, g0z, gu);
+        else if (kn.minb == 8)
+            CA_LAUNCH_PDL((k_adam_grad2<8>), ggrid, gblock, 0, st, (const float*)u_out, (const float4*)fixcl, (const float4*)movcl, CG, g, g0x, g0y, g0z, gu);
+        else
+            CA_LAUNCH_PDL((k_adam_grad2<CA_GRAD_MINB>), ggrid, gblock, 0, st, (const float*)u_out, (const float4*)fixcl, (const float4*)movcl, CG, g, g0x, g0y, g0z, gu);
         ca_timing_end(tmg, st);
         CA_CHECK_LAUNCH("adam_grad");
         if (!fast) {
@@ -468,7 +632,7 @@ extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int
         upd.s.neg_step_size = (float)(-(lr / bc1));
         if (fast) {
             // B^3 g_u fused with the Adam step; dL/dp is stored only when the caller asks for it
-            if ((rc = box3_cubed(gu, t0, g_out, hl, wa, da, &upd, st)) != CA_OK) return rc;
+            if ((rc = box3_cubed(gu, t0, g_out, hl, wa, da, &upd, flip_box, st)) != CA_OK) return rc;
         } else {
             float* gp = g_out ? g_out : t0;
             if ((rc = box(t1, gp)) != CA_OK) return rc;

@@ -297,6 +297,14 @@ def check_onehot(lib, device):
     assert_bits_equal(got, want, "onehot_pooled")
 
 
+def first_step_p_bound(g_a, g_b, eps=1e-8):
+    """Per-element bound on |p1_a - p1_b| after the FIRST Adam step (m = v = 0, lr = 1: p1 = p0 - g / (|g| + eps)) given the two
+    gradients: |dg| * sup over [g_a, g_b] of eps / (|g| + eps)^2 (the interval contains 0 when the signs differ), + 2e-6."""
+    ga, gb = np.asarray(g_a, np.float64), np.asarray(g_b, np.float64)
+    glow = np.where(np.sign(ga) == np.sign(gb), np.minimum(np.abs(ga), np.abs(gb)), 0.0)
+    return 1.5 * np.abs(ga - gb) * eps / (glow + eps) ** 2 + 2e-6
+
+
 def check_adam(lib, device, C=12, shape=(10, 12, 14), lam=1.25, steps=(1, 2, 7)):
     r = rng(60)
     fix = r.rand(C, *shape).astype(np.float32)
@@ -318,8 +326,17 @@ def check_adam(lib, device, C=12, shape=(10, 12, 14), lam=1.25, steps=(1, 2, 7))
         print(f"[adam vs oracle] step {k + 1}: u rel {np.abs(N(u) - u_o).max() / max(1.0, np.abs(u_o).max()):.2e}, grad rel "
               f"{np.abs(N(g) - g_o).max() / gmax:.2e}, p abs {np.abs(N(p) - st.p).max():.2e}, m rel "
               f"{np.abs(N(m) - st.m).max() / max(1.0, np.abs(st.m).max()):.2e}")
-        # |dp| <= |dg| / eps (eps = 1e-8, lr = 1): the first step (v = 0) amplifies fp32 gradient noise
-        assert np.abs(N(p) - st.p).max() <= (2e-4 if k == 0 else 5e-6), f"adam p step {k + 1}: {np.abs(N(p) - st.p).max():.2e}"
+        if k == 0:
+            # first step (m = v = 0): p1 = p0 - g / (|g| + eps), eps = 1e-8, so dp = dg * eps / (|g| + eps)^2 -- up to dg / eps
+            # where the gradient vanishes.  The bound is therefore stated per element, conditioned on the gradient both sides
+            # computed (mean value theorem over [g, g_o]; the interval contains 0 when the signs differ), instead of as one
+            # number for the worst-conditioned voxel of the seed (achieved there: 1.3e-4 / 2.6e-4 with the two forms of the
+            # gradient kernel, whose gradients are equally close to the oracle's).
+            bad = np.abs(N(p).astype(np.float64) - st.p) > first_step_p_bound(N(g), g_o)
+            assert not bad.any(), f"adam p step 1: {int(bad.sum())} elements outside the conditioned bound, worst {np.abs(N(p) - st.p)[bad].max():.2e}"
+            assert np.abs(N(p) - st.p).max() <= 1e-3
+        else:
+            assert np.abs(N(p) - st.p).max() <= 5e-6, f"adam p step {k + 1}: {np.abs(N(p) - st.p).max():.2e}"
         assert np.abs(N(m) - st.m).max() <= 1e-9 * max(1.0, np.abs(st.m).max())
     # several iterations in one call == the same iterations one call at a time
     p0 = (r.randn(3, *shape) * 1.5).astype(np.float32)

@@ -11,10 +11,11 @@ KW_B = dict(mind_r=1, mind_d=2, lambda_weight=1.25, grid_sp=6, disp_hw=4, select
 
 # Teacher-forced Adam step against the reference's own snapshots.  Bounds = 2x what the CUDA path
 # achieves on the B200 (printed by the test; profiles/r2_parity_achieved.txt): the analytic fused gradient sums the 8 corner
-# contributions in a different order from autograd's, and the first step (v = 0: |dp| = |dg| / (|g| + eps) with
-# |g| ~ 1e-7) amplifies that difference.
+# contributions in a different order from autograd's.  The first step (m = v = 0: p1 = p0 - g / (|g| + eps), so
+# dp = dg * eps / (|g| + eps)^2, up to dg / eps where the gradient vanishes) amplifies that difference at a handful of voxels:
+# there the bound is stated per element, conditioned on the two gradients (kernel_checks.first_step_p_bound), next to a cap.
 TF_GRAD_REL = 6e-7      # achieved 3.0e-7
-TF_P_FIRST = 2e-4       # achieved 1.28e-4 (first step, v = 0)
+TF_P_FIRST = 1e-3       # cap; achieved 1.3e-4 / 2.6e-4 with the two forms of the gradient kernel (first step, v = 0)
 TF_P_LATER = 2e-6       # achieved 4.8e-7 / 9.5e-7
 
 
@@ -57,6 +58,10 @@ def test_golden_adam_teacher_forced(golden):
         print(f"[cuda] teacher-forced Adam step {k + 1} vs reference snapshot: grad rel {eg:.2e}, p_next abs {ep:.2e}")
         assert eg <= TF_GRAD_REL
         assert ep <= (TF_P_FIRST if k == 0 else TF_P_LATER)
+        if k == 0:
+            from tests.kernel_checks import first_step_p_bound
+            bad = np.abs(p.cpu().numpy().astype(np.float64) - g["adam0_p_next"]) > first_step_p_bound(gr.cpu().numpy(), gref)
+            assert not bad.any(), int(bad.sum())
 
 
 def test_fp16_output_rounding_and_types(golden):
