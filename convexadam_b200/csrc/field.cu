@@ -48,12 +48,16 @@ __global__ void __launch_bounds__(256) k_ic_step(const float* __restrict__ a, co
                                                  int d, const float* __restrict__ gx, const float* __restrict__ gy,
                                                  const float* __restrict__ gz, float* __restrict__ oa,
                                                  float* __restrict__ ob) {
-    const int64_t n = (int64_t)h * w * d;
-    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
-        const int z = (int)(o % d), y = (int)((o / d) % w), x = (int)(o / ((int64_t)d * w));
+    // the 15 iterations are a chain of short dependent launches: programmatic dependent launch lets the next one's CTAs be
+    // scheduled while this one drains; blockIdx.y = which of the two fields this CTA updates (twice the CTAs in flight)
+    ca_grid_dep_launch();
+    ca_grid_dep_wait();
+    const int n = h * w * d;                                   // host: 3 * n < 2^31
+    for (int o = (int)(blockIdx.x * blockDim.x + threadIdx.x); o < n; o += (int)(gridDim.x * blockDim.x)) {
+        const int r = o / d, z = o - r * d, x = r / w, y = r - x * w;
         const float bgx = gx[z], bgy = gy[y], bgz = gz[x];
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
+        {
+            const int pass = (int)blockIdx.y;
             const float* self = pass ? b : a;
             const float* other = pass ? a : b;
             float* dst = pass ? ob : oa;
@@ -67,7 +71,7 @@ __global__ void __launch_bounds__(256) k_ic_step(const float* __restrict__ a, co
             for (int t = 0; t < 8; ++t) {
                 const int xx = k.x0 + (t & 1), yy = k.y0 + ((t >> 1) & 1), zz = k.z0 + ((t >> 2) & 1);
                 if (xx >= 0 && xx < d && yy >= 0 && yy < w && zz >= 0 && zz < h) {
-                    const int64_t q = ((int64_t)zz * w + yy) * d + xx;
+                    const int q = (zz * w + yy) * d + xx;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(__ldg(other + c * n + q), k.w[t]));
                 }
@@ -92,6 +96,7 @@ extern "C" int ca_inverse_consistency(const float* f1, const float* f2, int h, i
                                       size_t workspace_bytes, ca_stream_t stream) {
     CA_CHECK_ARG(f1 && f2 && gx && gy && gz && o1 && o2 && workspace, "inverse_consistency: null pointer");
     CA_CHECK_ARG(h > 0 && w > 0 && d > 0 && iters >= 0, "inverse_consistency: bad dims");
+    CA_CHECK_ARG((int64_t)h * w * d * 3 < (1ll << 31), "inverse_consistency: field too large (32-bit voxel indices)");
     if (workspace_bytes < ca_inverse_consistency_workspace_bytes(h, w, d)) {
         ca_set_error("inverse_consistency: workspace too small");
         return CA_ERR_WORKSPACE;
@@ -111,7 +116,7 @@ extern "C" int ca_inverse_consistency(const float* f1, const float* f2, int h, i
         const bool to_out = ((iters - it) & 1) == 1;
         float* da = to_out ? o1 : wa;
         float* db = to_out ? o2 : wb;
-        CA_LAUNCH(k_ic_step, dim3(field_grid(n3 / 3)), dim3(256), 0, st, sa, sb, h, w, d, gx, gy, gz, da, db);
+        CA_LAUNCH_PDL(k_ic_step, dim3(field_grid(n3 / 3), 2u), dim3(256), 0, st, sa, sb, h, w, d, gx, gy, gz, da, db);
         CA_CHECK_LAUNCH("inverse_consistency");
         sa = da;
         sb = db;
@@ -186,11 +191,61 @@ __global__ void __launch_bounds__(256) k_trilinear(const float* __restrict__ in,
     }
 }
 
+// The same resize for output rows of a multiple of 4 voxels: a thread owns four consecutive outputs of one row (one 128-bit
+// store per channel), the row's H / W source planes and weights are computed once per thread, and nothing is divided in 64 bits.
+// Every value is formed by the same rounded operations in the same order as in k_trilinear: the results are bit-identical.
+__global__ void __launch_bounds__(256) k_trilinear_q(const float* __restrict__ in, int C, int ih, int iw, int id, int oh,
+                                                     int ow, int od, float sh, float sw, float sd, float post_mul,
+                                                     float* __restrict__ out) {
+    const int nq = od >> 2;
+    const int rows_per_cta = (int)blockDim.x / nq;                     // the host picks blockDim.x = a multiple of nq
+    const int t = (int)threadIdx.x, rl = t / nq, q = t - rl * nq;
+    const int64_t on = (int64_t)oh * ow * od, inn = (int64_t)ih * iw * id;
+    for (int r = (int)blockIdx.x * rows_per_cta + rl; r < oh * ow; r += (int)gridDim.x * rows_per_cta) {
+        const int x = r / ow, y = r - x * ow;
+        int x0, x1, y0, y1;
+        float a0, a1, b0, b1;
+        ca_src_index(x, ih, oh, sh, x0, x1, a0, a1);
+        ca_src_index(y, iw, ow, sw, y0, y1, b0, b1);
+        int z0[4], z1[4];
+        float c0[4], c1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ca_src_index(4 * q + j, id, od, sd, z0[j], z1[j], c0[j], c1[j]);
+        const int r00 = (x0 * iw + y0) * id, r01 = (x0 * iw + y1) * id, r10 = (x1 * iw + y0) * id, r11 = (x1 * iw + y1) * id;
+        for (int c = 0; c < C; ++c) {
+            const float* p = in + c * inn;
+            float o4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float v00 = __fadd_rn(__fmul_rn(c0[j], __ldg(p + r00 + z0[j])), __fmul_rn(c1[j], __ldg(p + r00 + z1[j])));
+                const float v01 = __fadd_rn(__fmul_rn(c0[j], __ldg(p + r01 + z0[j])), __fmul_rn(c1[j], __ldg(p + r01 + z1[j])));
+                const float v10 = __fadd_rn(__fmul_rn(c0[j], __ldg(p + r10 + z0[j])), __fmul_rn(c1[j], __ldg(p + r10 + z1[j])));
+                const float v11 = __fadd_rn(__fmul_rn(c0[j], __ldg(p + r11 + z0[j])), __fmul_rn(c1[j], __ldg(p + r11 + z1[j])));
+                const float v0 = __fadd_rn(__fmul_rn(b0, v00), __fmul_rn(b1, v01));
+                const float v1 = __fadd_rn(__fmul_rn(b0, v10), __fmul_rn(b1, v11));
+                o4[j] = __fmul_rn(__fadd_rn(__fmul_rn(a0, v0), __fmul_rn(a1, v1)), post_mul);
+            }
+            *reinterpret_cast<float4*>(out + c * on + (int64_t)r * od + 4 * q) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        }
+    }
+}
+
 extern "C" int ca_trilinear(const float* in, int C, int ih, int iw, int id, float* out, int oh, int ow, int od,
                             float post_mul, ca_stream_t stream) {
     CA_CHECK_ARG(in && out, "trilinear: null pointer");
     CA_CHECK_ARG(C > 0 && ih > 0 && iw > 0 && id > 0 && oh > 0 && ow > 0 && od > 0, "trilinear: bad dims");
     const float sh = (float)ih / (float)oh, sw = (float)iw / (float)ow, sd = (float)id / (float)od;
+    const int nq = od / 4;
+    if ((od & 3) == 0 && nq <= 256 && (int64_t)ih * iw * id < (1ll << 31) && (int64_t)oh * ow < (1ll << 31) && (((uintptr_t)out) & 15) == 0 &&
+        (((int64_t)oh * ow * od) & 3) == 0) {
+        const int threads = (256 / nq) * nq, rows_per_cta = threads / nq;
+        int64_t ctas = ca_divup((int64_t)oh * ow, rows_per_cta);
+        if (ctas > 148 * 64) ctas = 148 * 64;
+        CA_LAUNCH(k_trilinear_q, dim3((unsigned)ctas), dim3(threads), 0, (cudaStream_t)stream, in, C, ih, iw, id, oh, ow, od, sh, sw, sd,
+                  post_mul, out);
+        CA_CHECK_LAUNCH("trilinear_q");
+        return CA_OK;
+    }
     CA_LAUNCH(k_trilinear, dim3(field_grid((int64_t)oh * ow * od)), dim3(256), 0, (cudaStream_t)stream, in, C, ih, iw, id, oh,
               ow, od, sh, sw, sd, post_mul, out);
     CA_CHECK_LAUNCH("trilinear");

@@ -264,8 +264,11 @@ def check_inverse_consistency(lib, device, shape=(8, 10, 12)):
 def check_trilinear_affine_pack(lib, device):
     r = rng(40)
     x = r.randn(3, 8, 7, 9).astype(np.float32)
-    for size in [(16, 14, 18), (17, 15, 19), (4, 3, 4), (8, 7, 9)]:
+    # (.., .., 4k) sizes take the four-outputs-per-thread kernel, the others the one-output kernel
+    for size in [(16, 14, 18), (17, 15, 19), (4, 3, 4), (8, 7, 9), (16, 14, 20), (5, 9, 36), (8, 7, 8), (3, 2, 1028)]:
         assert_bits_equal(N(lib.trilinear(T(x, device), size)), orc.trilinear(x, size), f"trilinear {size}")
+    got = N(lib.trilinear(T(x, device), (16, 14, 20), post_mul=2.0))
+    assert_bits_equal(got, orc.trilinear(x, (16, 14, 20)) * np.float32(2.0), "trilinear (quad kernel) post_mul")
     got = N(lib.trilinear(T(x, device), (16, 14, 18), post_mul=2.0))
     assert_bits_equal(got, orc.trilinear(x, (16, 14, 18)) * np.float32(2.0), "trilinear post_mul")
     scale = np.array([3.5, 3.0, 4.0], np.float32)
@@ -305,6 +308,19 @@ def first_step_p_bound(g_a, g_b, eps=1e-8):
     return 1.5 * np.abs(ga - gb) * eps / (glow + eps) ** 2 + 2e-6
 
 
+def later_step_p_bound(g_a, g_b, m0, v0, step, eps=1e-8, b1=0.9, b2=0.999):
+    """The same for a later step from the common state (m0, v0): p' = p - s m' / D, m' = m0 + (1-b1)(g - m0),
+    D = sqrt(b2 v0 + (1-b2) g^2) / c + eps, s = 1 / (1 - b1^step), c = sqrt(1 - b2^step), hence
+    |dp/dg| <= s ((1-b1) / D + |m'| sqrt(1-b2) / (c D^2))  (|g| / sqrt(v') <= 1 / sqrt(1-b2)); D at the smallest |g| of the interval."""
+    ga, gb = np.asarray(g_a, np.float64), np.asarray(g_b, np.float64)
+    m0, v0 = np.asarray(m0, np.float64), np.asarray(v0, np.float64)
+    s, c = 1.0 / (1.0 - b1 ** step), np.sqrt(1.0 - b2 ** step)
+    glow = np.where(np.sign(ga) == np.sign(gb), np.minimum(np.abs(ga), np.abs(gb)), 0.0)
+    D = np.sqrt(b2 * v0 + (1 - b2) * glow ** 2) / c + eps
+    mmax = np.maximum(np.abs(m0 + (1 - b1) * (ga - m0)), np.abs(m0 + (1 - b1) * (gb - m0)))
+    return 1.5 * np.abs(ga - gb) * s * ((1 - b1) / D + mmax * np.sqrt(1 - b2) / (c * D ** 2)) + 2e-6
+
+
 def check_adam(lib, device, C=12, shape=(10, 12, 14), lam=1.25, steps=(1, 2, 7)):
     r = rng(60)
     fix = r.rand(C, *shape).astype(np.float32)
@@ -336,7 +352,12 @@ def check_adam(lib, device, C=12, shape=(10, 12, 14), lam=1.25, steps=(1, 2, 7))
             assert not bad.any(), f"adam p step 1: {int(bad.sum())} elements outside the conditioned bound, worst {np.abs(N(p) - st.p)[bad].max():.2e}"
             assert np.abs(N(p) - st.p).max() <= 1e-3
         else:
-            assert np.abs(N(p) - st.p).max() <= 5e-6, f"adam p step {k + 1}: {np.abs(N(p) - st.p).max():.2e}"
+            # early steps are ill-conditioned the same way wherever the accumulated v is still tiny: per-element bound again,
+            # next to a cap (achieved on the B200: 1.1e-5 at step 2, 1.5e-6 at step 4 and later)
+            tol = later_step_p_bound(N(g), g_o, m0, v0, k + 1)
+            bad = np.abs(N(p).astype(np.float64) - st.p) > tol
+            assert not bad.any(), f"adam p step {k + 1}: {int(bad.sum())} elements outside the conditioned bound, worst {np.abs(N(p) - st.p)[bad].max():.2e}"
+            assert np.abs(N(p) - st.p).max() <= (5e-5 if k < 3 else 5e-6), f"adam p step {k + 1}: {np.abs(N(p) - st.p).max():.2e}"
         assert np.abs(N(m) - st.m).max() <= 1e-9 * max(1.0, np.abs(st.m).max())
     # several iterations in one call == the same iterations one call at a time
     p0 = (r.randn(3, *shape) * 1.5).astype(np.float32)
