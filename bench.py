@@ -261,7 +261,10 @@ def main():
     fixed, moving = make_pair(shape, seed=rank)
     fixed_pin, moving_pin = fixed.pin_memory(), moving.pin_memory()
     fixed_dev, moving_dev = fixed_pin.to(dev), moving_pin.to(dev)
-    P = pipeline.Params(selected_niter=args.niter, **prm)
+    # `value` and the stage / kernel timings: the two directions of the convex stage one after the other on one stream
+    # (overlap="0"); the library's default issues them on two streams (Params.overlap), which is what `e2e` and
+    # `value_two_stream_directions` measure -- per-kernel timings of concurrently running kernels mean nothing
+    P = pipeline.Params(selected_niter=args.niter, overlap="0", **prm)
     ab = algorithmic_bytes(shape, prm)
     ssd_buf = torch.empty((ab["L"],) + tuple(s // prm["grid_sp"] for s in shape), dtype=torch.float32, device=dev)
 
@@ -317,8 +320,7 @@ def main():
     value_h2d = {"value": world * steps / (max_over_ranks(e0.elapsed_time(e1)) / 1e3), "unit": "pairs/s",
                  "h2d_bytes_per_step": int(2 * fixed.numel() * 4)}
 
-    # ---- optional mode: the two directions of the convex stage on two CUDA streams (CONVEXADAM_B200_OVERLAP=1; needs a second
-    # cost volume; off by default because per-kernel timings of concurrently running kernels stop meaning anything) ----
+    # ---- the library's default mode: the two directions of the convex stage on two CUDA streams (a second cost volume) ----
     value_overlap = None
     if not args.no_extras:
         P2 = pipeline.Params(selected_niter=args.niter, overlap="1", **prm)
@@ -331,8 +333,8 @@ def main():
         e1.record()
         barrier()
         value_overlap = {"value": world * steps / (max_over_ranks(e0.elapsed_time(e1)) / 1e3), "unit": "pairs/s",
-                         "note": "forward and backward direction of the convex stage issued on two streams (opt-in)"}
-        pipeline._VOL2.clear()
+                         "note": "forward and backward direction of the convex stage issued on two streams (the library's default, "
+                                 "what convex_adam_pt and hence `e2e` run); `value` is the one-stream mode the stage timings need"}
         torch.cuda.empty_cache()
 
     # ---- end to end through the public API (host buffers in, host array out) ----
@@ -441,6 +443,9 @@ def main():
                    "pairs_per_step_per_gpu": 1, "parallelism": f"pair-parallel x{world} (no collective on the data path)",
                    "value_region": "inputs resident in HBM when the timed region starts (bench contract); `value_t0_t1` adds the "
                                    "host-to-device copy of both images, i.e. the reference's own t0..t1 (MIND.py:102-193)",
+                   "streams": "`value`, `stages_ms`, `roofline`: the two directions of the convex stage one after the other on one stream, "
+                              "so that every stage and kernel is timed alone; the library's default (what `e2e` runs) issues them on "
+                              "two streams: `value_two_stream_directions`",
                    "l2": "the 8.6 GB cost volume (>> 126 MB L2) is rewritten and re-read every step; no explicit flush"},
         "stages_ms": stages,
         "value_t0_t1": value_h2d,

@@ -85,7 +85,8 @@ def iter_register_pipelined(pairs: Sequence, depth: int = 2, device=None, dtype=
     unknown = set(kw) - set(names)
     if unknown:
         raise TypeError(f"unexpected arguments {sorted(unknown)}")
-    prm = pipeline.Params(**{k: kw[k] for k in names if k in kw})
+    # the pairs in flight already share the GPU: each runs its two directions one after the other (depth x 1 cost volumes)
+    prm = pipeline.Params(overlap="0" if depth > 1 else "", **{k: kw[k] for k in names if k in kw})
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream(dev)
         streams = _pipeline_streams(dev, depth)

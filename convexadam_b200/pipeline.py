@@ -36,14 +36,24 @@ class Params:
     # (ca_coupled_convex_certified); "exact": the bit-exact cost volume (ca_correlate + ca_coupled_convex).  Both
     # give bit-identical argmin / selections / disp_soft; CONVEXADAM_B200_MODE overrides the default.
     mode: str = ""
-    # "1": run the forward and the backward direction of the convex stage on two CUDA streams (needs a second cost
-    # volume).  Measured at config 2: 24.1 instead of 25.9 ms for the stage (+4 % pairs/s); off by default because the
-    # kernels of the two directions then time-share the SMs and per-kernel timings stop being meaningful.
-    # "" = CONVEXADAM_B200_OVERLAP, default off
+    # The forward and the backward direction of the convex stage are independent until inverse consistency.  "1": issue them
+    # on two CUDA streams (a second cost volume, 8.6 GB at config 2): the latency-bound kernels of one direction share the SMs
+    # with the bandwidth-bound ones of the other, 24.1 instead of 25.9 ms for the stage (+5 % pairs/s), same bits.  "0": one
+    # after the other on the caller's stream (what bench.py times stage by stage -- per-kernel timings of concurrently running
+    # kernels mean nothing).  "" = CONVEXADAM_B200_OVERLAP if set, else automatic: two streams whenever the second volume can
+    # be allocated.
     overlap: str = ""
 
     def resolved_overlap(self):
-        return (self.overlap or os.environ.get("CONVEXADAM_B200_OVERLAP", "0")) in ("1", "on", "true", "True")
+        """True / False / None (automatic)."""
+        s = self.overlap or os.environ.get("CONVEXADAM_B200_OVERLAP", "")
+        if s in ("1", "on", "true", "True"):
+            return True
+        if s in ("0", "off", "false", "False"):
+            return False
+        if s in ("", "auto"):
+            return None
+        raise ValueError(f"unknown overlap setting {s!r} (0 | 1 | auto)")
 
     def resolved_mode(self):
         m = self.mode or os.environ.get("CONVEXADAM_B200_MODE", "certified")
@@ -77,17 +87,24 @@ def convex_stage(lib: Lib, fix_s, mov_s, shape, prm: Params, ssd_buf=None):
 
     if not prm.ic:
         return one_direction(fix_s, mov_s, ssd_buf)
-    if not (prm.resolved_overlap() and lib.is_cuda):
+    want = prm.resolved_overlap()
+    ssd_buf2 = None
+    if lib.is_cuda and want is not False:
+        try:
+            # per call, not cached: concurrent callers (pipelined batches, host threads) must not share it; torch's caching
+            # allocator makes the second and later allocations free
+            ssd_buf2 = torch.empty_like(ssd_buf)
+        except torch.cuda.OutOfMemoryError:
+            if want:
+                raise
+    if ssd_buf2 is None:
         soft = one_direction(fix_s, mov_s, ssd_buf)
         soft_ = one_direction(mov_s, fix_s, ssd_buf)
         return ic_and_upsample(lib, soft, soft_, shape, prm)
-    # The two directions are independent until inverse consistency: issue them on two streams so that the latency-bound
-    # kernels of one (selection passes, exact re-decisions, box filters) share the SMs with the issue-bound raw SSD
-    # kernel of the other.  Each direction owns a cost volume; both streams start after, and are joined by, the
-    # caller's stream.
+    # Each direction owns a cost volume; both streams start after, and are joined by, the caller's stream.  (The side streams
+    # are shared by concurrent callers on a device: that only serialises them, every dependency is an event.)
     main = torch.cuda.current_stream(dev)
     side = _side_streams(dev)
-    ssd_buf2 = _second_volume(ssd_buf)
     start = torch.cuda.Event()
     start.record(main)
     outs = []
@@ -98,15 +115,16 @@ def convex_stage(lib: Lib, fix_s, mov_s, shape, prm: Params, ssd_buf=None):
         done = torch.cuda.Event()
         done.record(st)
         main.wait_event(done)
-    for t in (fix_s, mov_s, ssd_buf, ssd_buf2) + tuple(outs):
+    for t in (fix_s, mov_s, ssd_buf, ssd_buf2):
         for st in side:
             t.record_stream(st)
+    for t in outs:                 # allocated on a side stream, consumed on the caller's
+        t.record_stream(main)
     _mark("correlate+coupled_convex (two directions on two streams)")
     return ic_and_upsample(lib, outs[0], outs[1], shape, prm)
 
 
 _SIDE = {}
-_VOL2 = {}
 
 
 def _side_streams(dev):
@@ -114,15 +132,6 @@ def _side_streams(dev):
     if key not in _SIDE:
         _SIDE[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
     return _SIDE[key]
-
-
-def _second_volume(buf):
-    """The backward direction's cost volume (cached per device and shape: 8.6 GB at config 2)."""
-    key = (str(buf.device), tuple(buf.shape))
-    if key not in _VOL2:
-        _VOL2.clear()
-        _VOL2[key] = torch.empty_like(buf)
-    return _VOL2[key]
 
 
 def ic_and_upsample(lib: Lib, soft, soft_, shape, prm: Params):

@@ -138,13 +138,14 @@ def test_full_size_certified_mode_equals_exact_mode():
     dev = torch.device("cuda:0")
     fixed, moving = make_pair((192, 160, 256), seed=3)
     kw = dict(mind_r=1, mind_d=2, lambda_weight=1.25, grid_sp=2, disp_hw=6, selected_niter=1, selected_smooth=0, grid_sp_adam=2, ic=True)
-    a = pipeline.register_mind(fixed.to(dev), moving.to(dev), pipeline.Params(mode="exact", **kw))
-    b = pipeline.register_mind(fixed.to(dev), moving.to(dev), pipeline.Params(mode="certified", **kw))
+    a = pipeline.register_mind(fixed.to(dev), moving.to(dev), pipeline.Params(mode="exact", overlap="0", **kw))
+    b = pipeline.register_mind(fixed.to(dev), moving.to(dev), pipeline.Params(mode="certified", overlap="0", **kw))
     assert bool((a.view(torch.int32) == b.view(torch.int32)).all())
-    # ... and with the two directions issued on two streams
-    c = pipeline.register_mind(fixed.to(dev), moving.to(dev), pipeline.Params(mode="certified", overlap="1", **kw))
-    torch.cuda.synchronize()
-    assert bool((a.view(torch.int32) == c.view(torch.int32)).all())
+    # ... and with the two directions issued on two streams (explicitly, and as the library's default decides)
+    for ov in ("1", ""):
+        c = pipeline.register_mind(fixed.to(dev), moving.to(dev), pipeline.Params(mode="certified", overlap=ov, **kw))
+        torch.cuda.synchronize()
+        assert bool((a.view(torch.int32) == c.view(torch.int32)).all()), ov
 
 
 def test_settings_sweep_equals_individual_calls():
