@@ -401,8 +401,8 @@ def main():
     t_corr = stages.get("correlate", 0.0) / ndir
     ach_corr = ab["correlate_per_direction"] / (t_corr * 1e-3) / 1e9 if t_corr > 0 else 0.0
     fused = "corr_fused" in ktimes
-    piped = "corr_pipe" in ktimes
-    corr_kernels = "k_corr_fused (one fused launch)" if fused else "k_corr_pipe (one launch of producer / consumer CTAs)" if piped else \
+    pipe_kernel = "corr_pipe" in ktimes
+    corr_kernels = "k_corr_fused (one fused launch)" if fused else "k_corr_pipe (one launch of producer / consumer CTAs)" if pipe_kernel else \
         ("k_raw_ssd_tmap + k_box12_fast" if mode == "certified" else "k_raw_ssd_staged + k_box12") + ", %d launches" % int(
             round((ktimes.get("raw_ssd", (0, 0))[1] + ktimes.get("box_filters", (0, 0))[1]) / steps / ndir))
     roof = {"kernel": "correlate stage of one direction (%s): features in, (L,h,w,d) cost volume out" % corr_kernels,
@@ -412,7 +412,7 @@ def main():
             "share_of_step": ndir * t_corr / step_ms,
             "note": "algorithmic bytes = SURVEY 8(d) bytes_corr per direction: both coarse feature volumes read once, the cost volume "
                     "written once (+ int64 argmin); 'launch' = one direction of the stage",
-            "traffic": committed_traffic("pipe" if piped else mode, fused, shape)}
+            "traffic": committed_traffic("pipe" if pipe_kernel else mode, fused, shape)}
     # per-kernel extras, each against the SURVEY 8(d) bytes it is responsible for (the raw-SSD planes between the two kernels
     # of the stage are NOT algorithmic bytes: they are the traffic the fused kernel removes)
     others = [kernel_line("corr_fused", "k_corr_fused (raw SSD + both box filters + H march, tensor-map TMA)",
