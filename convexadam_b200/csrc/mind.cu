@@ -12,6 +12,8 @@
 // libdevice, <= 2 ulp) and the global mean (double here, float cascade there).
 #include "ca_platform.h"
 
+#include <cstdlib>
+
 // The 6-neighbourhood (units of the dilation, (H,W,D)) and, per OUTPUT channel c (after the permutation at utils.py:66),
 // the two neighbours whose difference is squared: utils.py:30-47 selects the pairs (x>y) & (dist==2) in row-major
 // order.  Hard-wired so that every index is a compile-time constant (registers, no local memory);
@@ -132,6 +134,97 @@ __global__ void __launch_bounds__(128) k_mind_phase_a(const float* __restrict__ 
     if (threadIdx.x == 0) partial[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = red[0];
 }
 
+// The same phase for NR consecutive rows per thread (grid (ceil(D/128), ceil(W/NR), H)): the squared differences at a tap
+// location are the same for every voxel whose patch contains it, so a thread that owns the voxels (x, y0 .. y0+NR-1, z) forms
+// them once per location row and adds them to the (up to 2R+1) voxels of its column they belong to -- 6 loads and 24 flops per
+// location instead of per (voxel, tap): 2 400 -> 810 instructions per voxel at R = 1, NR = 4.  Every accumulator still receives
+// its (2R+1)^3 terms in torch's order (dx, dy, dz ascending: the location rows are walked upwards, which is dy ascending for
+// each voxel), and the block sums of the channel mean are formed per row exactly as k_mind_phase_a forms them, so mind, var and
+// the clamp bounds are bit-identical to that kernel's.
+template <int R, int NR, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_mind_phase_a_rows(const float* __restrict__ img, int H, int W, int D, int dil,
+                                                           float* __restrict__ mind, float* __restrict__ var,
+                                                           double* __restrict__ partial) {
+    __shared__ double red[128];
+    constexpr int IA[12] = MIND_IA, IB[12] = MIND_IB, INV[12] = MIND_INV, OFF[6][3] = MIND_OFF;
+    constexpr int K = 2 * R + 1, NL = NR + 2 * R;
+    const int64_t V = (int64_t)H * W * D;
+    const int z = (int)(blockIdx.x * blockDim.x + threadIdx.x), y0 = (int)blockIdx.y * NR, x = (int)blockIdx.z;
+    float vrow[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) vrow[i] = 0.f;
+    if (z < D) {
+        float acc[NR][12];
+#pragma unroll
+        for (int i = 0; i < NR; ++i)
+#pragma unroll
+            for (int c = 0; c < 12; ++c) acc[i][c] = 0.f;
+        int xo[K][3], zo[K][3], yo[NL][3];
+#pragma unroll
+        for (int t = 0; t < K; ++t)
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+                xo[t][o] = ca_clamp(ca_clamp(x + t - R, 0, H - 1) + (o - 1) * dil, 0, H - 1) * W * D;
+                zo[t][o] = ca_clamp(ca_clamp(z + t - R, 0, D - 1) + (o - 1) * dil, 0, D - 1);
+            }
+#pragma unroll
+        for (int j = 0; j < NL; ++j)
+#pragma unroll
+            for (int o = 0; o < 3; ++o) yo[j][o] = ca_clamp(ca_clamp(y0 + j - R, 0, W - 1) + (o - 1) * dil, 0, W - 1) * D;
+#pragma unroll
+        for (int dx = 0; dx < K; ++dx)
+#pragma unroll
+            for (int j = 0; j < NL; ++j)          // location row y0 + j - R: tap dy = j - i of the voxel in row y0 + i
+#pragma unroll
+                for (int dz = 0; dz < K; ++dz) {
+                    float nb[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) nb[k] = __ldg(img + xo[dx][OFF[k][0] + 1] + yo[j][OFF[k][1] + 1] + zo[dz][OFF[k][2] + 1]);
+#pragma unroll
+                    for (int c = 0; c < 12; ++c) {
+                        const float df = __fsub_rn(nb[IA[c]], nb[IB[c]]);
+                        const float d2 = __fmul_rn(df, df);
+#pragma unroll
+                        for (int i = 0; i < NR; ++i)
+                            if (j - i >= 0 && j - i < K) acc[i][c] = __fadd_rn(acc[i][c], d2);
+                    }
+                }
+        const float k3 = (float)(K * K * K);
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            if (y0 + i >= W) break;
+            float mn = 0.f;
+#pragma unroll
+            for (int c = 0; c < 12; ++c) {
+                acc[i][c] = ca_div(acc[i][c], k3);
+                mn = (c == 0 || acc[i][c] < mn) ? acc[i][c] : mn;
+            }
+#pragma unroll
+            for (int c = 0; c < 12; ++c) acc[i][c] = __fsub_rn(acc[i][c], mn);
+            float s = 0.f;
+#pragma unroll
+            for (int oc = 0; oc < 12; ++oc) s = __fadd_rn(s, acc[i][INV[oc]]);   // torch.mean(mind, 1): un-permuted order
+            vrow[i] = ca_div(s, 12.f);
+            const int64_t o = ((int64_t)x * W + (y0 + i)) * D + z;
+#pragma unroll
+            for (int c = 0; c < 12; ++c) mind[c * V + o] = acc[i][c];
+            var[o] = vrow[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        if (y0 + i >= W) break;                                     // uniform over the CTA
+        red[threadIdx.x] = (z < D) ? (double)vrow[i] : 0.0;
+        __syncthreads();
+        for (int s = 64; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) partial[((int64_t)x * W + (y0 + i)) * gridDim.x + blockIdx.x] = red[0];
+        __syncthreads();
+    }
+}
+
 // stats[0] = lo, stats[1] = hi  (utils.py:61: clamp(mind_var, mean*0.001, mean*1000), mean via .item() -> double)
 __global__ void __launch_bounds__(1024) k_mind_stats(const double* __restrict__ partial, int npartial, int64_t V,
                                                      float* __restrict__ stats) {
@@ -233,7 +326,16 @@ extern "C" int ca_mindssc_pooled(const float* img, int H, int W, int D, int radi
     // element offsets are 32-bit in the specialised kernels
     const bool small = V < (1ll << 31);
     const dim3 agrid((unsigned)nzb, (unsigned)W, (unsigned)H);
-    if (radius == 1 && small) { auto k = k_mind_phase_a<1>; CA_LAUNCH(k, agrid, dim3(128), 0, st, img, H, W, D, radius, dilation, mind, var, partial); }
+    // CA_MIND_ROWS=1: one voxel per thread (k_mind_phase_a); default: 4 rows per thread.  Read per call (the parity test compares both).
+    const char* rows_e = getenv("CA_MIND_ROWS");
+    const int rows_env = rows_e && *rows_e ? atoi(rows_e) : 4;
+#define CA_MIND_ROWS_LAUNCH(RR, NRR, MB) { auto k = k_mind_phase_a_rows<RR, NRR, MB>; const dim3 rgrid((unsigned)nzb, (unsigned)ca_divup(W, NRR), (unsigned)H); \
+        CA_LAUNCH(k, rgrid, dim3(128), 0, st, img, H, W, D, dilation, mind, var, partial); }
+    // measured per image at config 2 (phase A + stats + phase B): one voxel per thread 0.833 ms; 4 rows per thread compiled for
+    // 4 / 5 / 6 resident CTAs 0.80 / 0.72 / 0.73 ms (unconstrained: 106 registers, 0.78 ms); 2 / 3 / 8 rows 0.775 / 0.80 / 1.20 ms
+    if (radius == 1 && small && rows_env == 4) CA_MIND_ROWS_LAUNCH(1, 4, 5)
+    else if (radius == 2 && small && rows_env == 4) CA_MIND_ROWS_LAUNCH(2, 4, 2)
+    else if (radius == 1 && small) { auto k = k_mind_phase_a<1>; CA_LAUNCH(k, agrid, dim3(128), 0, st, img, H, W, D, radius, dilation, mind, var, partial); }
     else if (radius == 2 && small) { auto k = k_mind_phase_a<2>; CA_LAUNCH(k, agrid, dim3(128), 0, st, img, H, W, D, radius, dilation, mind, var, partial); }
     else { auto k = k_mind_phase_a<0>; CA_LAUNCH(k, agrid, dim3(128), 0, st, img, H, W, D, radius, dilation, mind, var, partial); }
     CA_CHECK_LAUNCH("mind_phase_a");

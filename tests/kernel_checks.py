@@ -52,6 +52,24 @@ def check_mind(lib, device, shape=(22, 18, 26)):
     assert np.abs(N(b) - orc.avgpool3d(ref, 2, 2)).max() <= 3e-7
 
 
+def check_mind_rows(lib, device, shapes=((9, 7, 11), (14, 12, 18), (6, 13, 130))):
+    """The four-rows-per-thread form of MIND phase A (default) == the one-voxel-per-thread form (CA_MIND_ROWS=1), bit for bit,
+    row counts that are no multiple of 4 and rows longer than one CTA included."""
+    import os
+    for si, shape in enumerate(shapes):
+        img = (rng(70 + si).randn(*shape) * 100).astype(np.float32)
+        for (r, dl) in [(1, 2), (2, 2), (1, 1)]:
+            got = {}
+            for rows in ("1", "4"):
+                os.environ["CA_MIND_ROWS"] = rows
+                try:
+                    got[rows] = [N(t) for t in lib.mindssc_pooled(T(img, device), r, dl, 1, 2)]
+                finally:
+                    del os.environ["CA_MIND_ROWS"]
+            for a, b in zip(got["1"], got["4"]):
+                assert_bits_equal(b, a, f"mind rows form {shape} r{r} d{dl}")
+
+
 def check_correlate(lib, device, cases=((12, 6, 5, 7, 2), (16, 4, 6, 8, 1), (3, 5, 4, 9, 3), (12, 7, 6, 12, 2))):
     lib.poison_workspaces = True        # scratch starts as NaN patterns: nothing may depend on its previous content
     try:

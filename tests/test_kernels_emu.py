@@ -23,6 +23,7 @@ def test_product_binding_rejects_emulation_build(lib):
 
 def test_avgpool(lib): kc.check_avgpool(lib, DEV)
 def test_mind(lib): kc.check_mind(lib, DEV, shape=(14, 12, 18))
+def test_mind_rows(lib): kc.check_mind_rows(lib, DEV, shapes=((9, 7, 11), (6, 13, 130)))
 def test_correlate(lib): kc.check_correlate(lib, DEV, cases=((12, 4, 5, 7, 2), (16, 3, 4, 8, 1), (3, 4, 4, 5, 3)))
 def test_coupled(lib): kc.check_coupled(lib, DEV, h=4, w=5, d=8)
 def test_certified(lib): kc.check_certified(lib, DEV, cases=((12, 4, 5, 8, 2), (3, 4, 5, 7, 1)))

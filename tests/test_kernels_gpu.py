@@ -23,6 +23,7 @@ def dev():
 
 def test_avgpool(lib, dev): kc.check_avgpool(lib, dev)
 def test_mind(lib, dev): kc.check_mind(lib, dev, shape=(40, 34, 46))
+def test_mind_rows(lib, dev): kc.check_mind_rows(lib, dev, shapes=((9, 7, 11), (40, 34, 46), (6, 13, 130), (20, 18, 300)))
 def test_mesh_and_axes(lib, dev): kc.check_mesh_and_axes(lib, dev)
 def test_inverse_consistency(lib, dev): kc.check_inverse_consistency(lib, dev, shape=(20, 18, 22))
 def test_trilinear_affine_pack(lib, dev): kc.check_trilinear_affine_pack(lib, dev)
