@@ -111,6 +111,15 @@ static __device__ __forceinline__ float4 ca_ld_stream4(const float4* p) {
     return *p;
 #endif
 }
+static __device__ __forceinline__ float2 ca_ld_stream2(const float2* p) {
+#if defined(__CUDA_ARCH__)
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+#else
+    return *p;
+#endif
+}
 static __device__ __forceinline__ float ca_ld_stream1(const float* p) {
 #if defined(__CUDA_ARCH__)
     float r;

@@ -539,10 +539,24 @@ __global__ void __launch_bounds__(128, 5) k_cost_argmin_pruned(const float* __re
 // only on kH, kW, kD, so the squared distances split into per-axis terms that are computed once per slab (kD), once per
 // block (kW) and once per label (kH) -- in the reference's rounded operations, so every cost and every bound is the
 // value the generic kernel computes, bit for bit, at less than half the instructions.
-template <int VEC, int S, bool CERT>
-__global__ void __launch_bounds__(128, 5) k_cost_argmin_sep(const float* __restrict__ ssd, const float* __restrict__ bmin,
+// VEC consecutive floats as one streaming load
+template <int VEC>
+static __device__ __forceinline__ void cc_ld_vec(const float* p, float (&o)[VEC]) {
+    if (VEC == 4) {
+        const float4 t = ca_ld_stream4(reinterpret_cast<const float4*>(p));
+        o[0] = t.x; o[1 % VEC] = t.y; o[2 % VEC] = t.z; o[3 % VEC] = t.w;
+    } else if (VEC == 2) {
+        const float2 t = ca_ld_stream2(reinterpret_cast<const float2*>(p));
+        o[0] = t.x; o[1 % VEC] = t.y;
+    } else {
+        o[0] = ca_ld_stream1(p);
+    }
+}
+
+template <int VEC, int S, bool CERT, int BG = 4>
+__global__ void __launch_bounds__(128, VEC == 4 ? 5 : 8) k_cost_argmin_sep(const float* __restrict__ ssd, const float* __restrict__ bmin,
                                                             const float* __restrict__ smin, int64_t n, const float4* __restrict__ boxes,
-                                                            const float* __restrict__ soft, float coeff, int row_len,
+                                                            const float* __restrict__ soft, float coeff, int row_len, int rpw,
                                                             const unsigned long long* __restrict__ prev,
                                                             unsigned long long* __restrict__ keys, int* __restrict__ flagged,
                                                             int* __restrict__ nflagged) {
@@ -553,12 +567,12 @@ __global__ void __launch_bounds__(128, 5) k_cost_argmin_sep(const float* __restr
     for (int i = threadIdx.x; i < S + 2; i += blockDim.x) sax[i] = tab[i];
     __syncthreads();
     int64_t v0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-    if (VEC == 4 && row_len > 0) {
+    if (row_len > 0) {      // a warp = rpw rows x (32 / rpw) lanes of VEC voxels: a compact tile prunes alike
         const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         const int64_t warp = gt >> 5;
         const int lane = (int)(gt & 31);
-        const int tpr = row_len / 32;
-        v0 = ((warp / tpr) * 4 + (lane >> 3)) * row_len + (warp % tpr) * 32 + (lane & 7) * 4;
+        const int lpr = 32 / rpw, tpr = row_len / (lpr * VEC);
+        v0 = ((warp / tpr) * rpw + (lane / lpr)) * row_len + (warp % tpr) * (lpr * VEC) + (lane % lpr) * VEC;
     }
     if (v0 >= n) return;
     float s0[VEC], s1[VEC], s2[VEC], best[VEC], U[VEC], second[VEC], r01[VEC];
@@ -602,12 +616,7 @@ __global__ void __launch_bounds__(128, 5) k_cost_argmin_sep(const float* __restr
 #pragma unroll
     for (int sl = 0; sl < S; ++sl) {
         float sm[VEC];
-        if (VEC == 4) {
-            const float4 b4 = ca_ld_stream4(reinterpret_cast<const float4*>(smin + (int64_t)sl * n + v0));
-            sm[0] = b4.x; sm[1 % VEC] = b4.y; sm[2 % VEC] = b4.z; sm[3 % VEC] = b4.w;
-        } else {
-            sm[0] = ca_ld_stream1(smin + (int64_t)sl * n + v0);
-        }
+        cc_ld_vec<VEC>(smin + (int64_t)sl * n + v0, sm);
         const float a2 = sax[sl].z;
         bool need = false;
 #pragma unroll
@@ -629,20 +638,15 @@ __global__ void __launch_bounds__(128, 5) k_cost_argmin_sep(const float* __restr
             e0q[i] = __fmul_rn(e0, e0);
         }
         // level 2: the blocks of this slab
-        for (int bb = 0; bb < S; bb += 4) {
-            float bmv[4][VEC];
+        for (int bb = 0; bb < S; bb += BG) {          // BG block minima in flight together
+            float bmv[BG][VEC];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < BG; ++u) {
                 const int b = sl * S + ca_min(bb + u, S - 1);
-                if (VEC == 4) {
-                    const float4 b4 = ca_ld_stream4(reinterpret_cast<const float4*>(bmin + (int64_t)b * n + v0));
-                    bmv[u][0] = b4.x; bmv[u][1 % VEC] = b4.y; bmv[u][2 % VEC] = b4.z; bmv[u][3 % VEC] = b4.w;
-                } else {
-                    bmv[u][0] = ca_ld_stream1(bmin + (int64_t)b * n + v0);
-                }
+                cc_ld_vec<VEC>(bmin + (int64_t)b * n + v0, bmv[u]);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < BG; ++u) {
                 if (bb + u >= S) break;
                 const int b = sl * S + bb + u;
                 const float a1 = sax[bb + u].y;
@@ -659,12 +663,7 @@ __global__ void __launch_bounds__(128, 5) k_cost_argmin_sep(const float* __restr
 #pragma unroll
                 for (int k = 0; k < S; ++k) {
                     const int l = b * S + k;
-                    if (VEC == 4) {
-                        const float4 c4 = ca_ld_stream4(reinterpret_cast<const float4*>(sp + (int64_t)l * n));
-                        cv[k][0] = c4.x; cv[k][1 % VEC] = c4.y; cv[k][2 % VEC] = c4.z; cv[k][3 % VEC] = c4.w;
-                    } else {
-                        cv[k][0] = ca_ld_stream1(sp + (int64_t)l * n);
-                    }
+                    cc_ld_vec<VEC>(sp + (int64_t)l * n, cv[k]);
                 }
 #pragma unroll
                 for (int k = 0; k < S; ++k) {
@@ -793,11 +792,33 @@ int ca_launch_cost_argmin_pruned(const float* ssd, const float* bmin, int64_t n,
     }
 #undef CA_PRUNED
 #undef CA_PRUNED_K
-#define CA_SEP_K(SS, VV, CC) { auto k = k_cost_argmin_sep<VV, SS, CC>; CA_LAUNCH(k, dim3(gx), dim3(128), 0, st, ssd, bmin, smin, n, boxes, soft, coeff, row_len, keys, keys, flagged, nflagged); }
+    // Voxels per thread of the separable kernel.  The pass is latency-bound (dependent loads slab -> block -> labels) and a warp
+    // evaluates every block ANY of its voxels needs: fewer voxels per thread = more warps in flight and fewer voxels sharing a
+    // pruning decision.  Measured per direction at config 2 (coupled_certified, six passes + block minima): 4 voxels 3.43 ms,
+    // 2 voxels 3.11 ms, 1 voxel 2.87 ms (warp = 32 voxels of a row) / 2.77 ms (warp = 2 rows x 16 voxels, the default);
+    // CA_CC_VEC = 1 | 2 | 4, CA_CC_RPW = rows of the 1-voxel form's warp tile.
+    static int sep_vec_env = -1;
+    if (sep_vec_env < 0) { const char* e = getenv("CA_CC_VEC"); sep_vec_env = e && *e ? atoi(e) : 1; }
+    const int svec = (vec == 4 && (sep_vec_env == 2 || sep_vec_env == 1)) ? sep_vec_env : vec;
+    const unsigned gxs = (unsigned)ca_divup(ca_divup(n, svec), 128);
+    // rows of a warp's tile: 4 for the 4- and 2-voxel forms (as before), CA_CC_RPW for the 1-voxel form (default 2 rows x 16 voxels)
+    static int sep_rpw_env = -1;
+    if (sep_rpw_env < 0) { const char* e = getenv("CA_CC_RPW"); sep_rpw_env = e && *e ? atoi(e) : 2; }
+    int rpw = svec == 1 ? sep_rpw_env : 4;
+    if (rpw != 1 && rpw != 2 && rpw != 4 && rpw != 8) rpw = 1;
+    // whole tiles only: rows of a multiple of (32 / rpw) * svec voxels, a multiple of rpw rows
+    const int srow = (row_len > 0 && row_len % ((32 / rpw) * svec) == 0 && (n / row_len) % rpw == 0) ? row_len : 0;
+    static int sep_bg_env = -1;
+    if (sep_bg_env < 0) { const char* e = getenv("CA_CC_BG"); sep_bg_env = e && *e ? atoi(e) : 0; }
+#define CA_SEP_KB(SS, VV, CC) { auto k = k_cost_argmin_sep<VV, SS, CC, SS>; CA_LAUNCH(k, dim3(gxs), dim3(128), 0, st, ssd, bmin, smin, n, boxes, soft, coeff, srow, rpw, keys, keys, flagged, nflagged); }
+#define CA_SEP_K(SS, VV, CC) { auto k = k_cost_argmin_sep<VV, SS, CC>; CA_LAUNCH(k, dim3(gxs), dim3(128), 0, st, ssd, bmin, smin, n, boxes, soft, coeff, srow, rpw, keys, keys, flagged, nflagged); }
 #define CA_SEP(SS)                                              \
     case SS:                                                    \
-        if (vec == 4 && cert) CA_SEP_K(SS, 4, true)             \
-        else if (vec == 4) CA_SEP_K(SS, 4, false)               \
+        if (svec == 2 && cert && sep_bg_env == 1) CA_SEP_KB(SS, 2, true)  \
+        else if (svec == 2 && cert) CA_SEP_K(SS, 2, true)       \
+        else if (svec == 2) CA_SEP_K(SS, 2, false)              \
+        else if (svec == 4 && cert) CA_SEP_K(SS, 4, true)       \
+        else if (svec == 4) CA_SEP_K(SS, 4, false)              \
         else if (cert) CA_SEP_K(SS, 1, true)                    \
         else CA_SEP_K(SS, 1, false)                             \
         break;
@@ -807,6 +828,7 @@ int ca_launch_cost_argmin_pruned(const float* ssd, const float* bmin, int64_t n,
     }
 #undef CA_SEP
 #undef CA_SEP_K
+#undef CA_SEP_KB
     ca_timing_end(tm, st);
     CA_CHECK_LAUNCH("cost_argmin_pruned");
     return CA_OK;
