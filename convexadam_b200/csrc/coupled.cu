@@ -83,17 +83,25 @@ __global__ void __launch_bounds__(128) k_soft_from_keys(const unsigned long long
     if (z >= d) return;
     const int64_t n = (int64_t)h * w * d;
     const unsigned* lab = reinterpret_cast<const unsigned*>(keys);       // little endian: label = low 32 bits of the key
+    // all 27 label loads go out together (clamped coordinates), then the 81 mesh values; a tap outside the volume adds +0,
+    // which leaves the ascending (dH,dW,dD) sum of the in-volume taps unchanged bit for bit
+    int lbl[27];
+    bool in[27];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+        const int xx = x + t / 9 - 1, yy = y + (t / 3) % 3 - 1, zz = z + t % 3 - 1;
+        in[t] = xx >= 0 && xx < h && yy >= 0 && yy < w && zz >= 0 && zz < d;
+        const int64_t q = ((int64_t)ca_min(ca_max(xx, 0), h - 1) * w + ca_min(ca_max(yy, 0), w - 1)) * d + ca_min(ca_max(zz, 0), d - 1);
+        lbl[t] = (int)__ldg(lab + 2 * q);
+    }
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    for (int xx = ca_max(x - 1, 0); xx < ca_min(x + 2, h); ++xx)
-        for (int yy = ca_max(y - 1, 0); yy < ca_min(y + 2, w); ++yy) {
-            const int64_t row = ((int64_t)xx * w + yy) * d;
-            for (int zz = ca_max(z - 1, 0); zz < ca_min(z + 2, d); ++zz) {
-                const int l = (int)__ldg(lab + 2 * (row + zz));
-                a0 = __fadd_rn(a0, __ldg(mesh + l));
-                a1 = __fadd_rn(a1, __ldg(mesh + L + l));
-                a2 = __fadd_rn(a2, __ldg(mesh + 2 * L + l));
-            }
-        }
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+        const float m0 = __ldg(mesh + lbl[t]), m1 = __ldg(mesh + L + lbl[t]), m2 = __ldg(mesh + 2 * L + lbl[t]);
+        a0 = __fadd_rn(a0, in[t] ? m0 : 0.f);
+        a1 = __fadd_rn(a1, in[t] ? m1 : 0.f);
+        a2 = __fadd_rn(a2, in[t] ? m2 : 0.f);
+    }
     const int64_t o = ((int64_t)x * w + y) * d + z;
     soft[o] = ca_div(a0, 27.f);
     soft[n + o] = ca_div(a1, 27.f);

@@ -20,7 +20,7 @@ struct Corner8 {
 
 static __device__ __forceinline__ float ca_unnormalize(float c, int size) {
     // GridSampler.h:27-36: ((coord + 1) * size - 1) / 2, every op rounded
-    return ca_div(__fsub_rn(__fmul_rn(__fadd_rn(c, 1.f), (float)size), 1.f), 2.f);
+    return __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(c, 1.f), (float)size), 1.f), 0.5f);      // x / 2 == x * 0.5, exactly
 }
 
 static __device__ __forceinline__ void ca_corners(float ix, float iy, float iz, Corner8& k) {
@@ -66,16 +66,22 @@ __global__ void __launch_bounds__(256) k_ic_step(const float* __restrict__ a, co
                         iz = ca_unnormalize(__fadd_rn(bgz, sz), h);
             Corner8 k;
             ca_corners(ix, iy, iz, k);
+            // every corner is loaded (clamped coordinates, all 24 loads in flight); a corner outside the volume gets the
+            // weight 0, and acc + v * 0 is acc bit for bit: torch skips it (GridSampler.h within_bounds)
             float acc[3] = {0.f, 0.f, 0.f};
+            float val[8][3];
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
                 const int xx = k.x0 + (t & 1), yy = k.y0 + ((t >> 1) & 1), zz = k.z0 + ((t >> 2) & 1);
-                if (xx >= 0 && xx < d && yy >= 0 && yy < w && zz >= 0 && zz < h) {
-                    const int q = (zz * w + yy) * d + xx;
+                if (!(xx >= 0 && xx < d && yy >= 0 && yy < w && zz >= 0 && zz < h)) k.w[t] = 0.f;
+                const int q = (ca_min(ca_max(zz, 0), h - 1) * w + ca_min(ca_max(yy, 0), w - 1)) * d + ca_min(ca_max(xx, 0), d - 1);
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(__ldg(other + c * n + q), k.w[t]));
-                }
+                for (int c = 0; c < 3; ++c) val[t][c] = __ldg(other + c * n + q);
             }
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(val[t][c], k.w[t]));
             dst[o] = __fmul_rn(0.5f, __fsub_rn(sx, acc[0]));
             dst[n + o] = __fmul_rn(0.5f, __fsub_rn(sy, acc[1]));
             dst[2 * n + o] = __fmul_rn(0.5f, __fsub_rn(sz, acc[2]));
