@@ -6,6 +6,7 @@ no host synchronisation (the reference syncs at utils.py:61 and round-trips the 
 MIND.py:156).  The cost volume (L,h,w,d) is allocated once and reused for the backward direction.
 """
 import os
+import threading
 from dataclasses import dataclass
 
 import torch
@@ -89,11 +90,10 @@ def convex_stage(lib: Lib, fix_s, mov_s, shape, prm: Params, ssd_buf=None):
         return one_direction(fix_s, mov_s, ssd_buf)
     want = prm.resolved_overlap()
     ssd_buf2 = None
+    main = torch.cuda.current_stream(dev) if lib.is_cuda else None
     if lib.is_cuda and want is not False:
         try:
-            # per call, not cached: concurrent callers (pipelined batches, host threads) must not share it; torch's caching
-            # allocator makes the second and later allocations free
-            ssd_buf2 = torch.empty_like(ssd_buf)
+            ssd_buf2 = _second_volume(ssd_buf, main)
         except torch.cuda.OutOfMemoryError:
             if want:
                 raise
@@ -101,21 +101,22 @@ def convex_stage(lib: Lib, fix_s, mov_s, shape, prm: Params, ssd_buf=None):
         soft = one_direction(fix_s, mov_s, ssd_buf)
         soft_ = one_direction(mov_s, fix_s, ssd_buf)
         return ic_and_upsample(lib, soft, soft_, shape, prm)
-    # Each direction owns a cost volume; both streams start after, and are joined by, the caller's stream.  (The side streams
-    # are shared by concurrent callers on a device: that only serialises them, every dependency is an event.)
-    main = torch.cuda.current_stream(dev)
+    # Each direction owns a cost volume; both streams start after, and are joined by, the caller's stream.  The second volume
+    # and the side streams belong to (device, caller's stream): calls on one stream reuse them in stream order; the lock makes
+    # the enqueue of one call's fork .. join atomic, so that two host threads on the same stream cannot interleave them.
     side = _side_streams(dev)
-    start = torch.cuda.Event()
-    start.record(main)
     outs = []
-    for st, (a, b, buf) in zip(side, ((fix_s, mov_s, ssd_buf), (mov_s, fix_s, ssd_buf2))):
-        st.wait_event(start)
-        with torch.cuda.stream(st):
-            outs.append(one_direction(a, b, buf, mark=False))
-        done = torch.cuda.Event()
-        done.record(st)
-        main.wait_event(done)
-    for t in (fix_s, mov_s, ssd_buf, ssd_buf2):
+    with _FORK_LOCK:
+        start = torch.cuda.Event()
+        start.record(main)
+        for st, (a, b, buf) in zip(side, ((fix_s, mov_s, ssd_buf), (mov_s, fix_s, ssd_buf2))):
+            st.wait_event(start)
+            with torch.cuda.stream(st):
+                outs.append(one_direction(a, b, buf, mark=False))
+            done = torch.cuda.Event()
+            done.record(st)
+            main.wait_event(done)
+    for t in (fix_s, mov_s, ssd_buf):
         for st in side:
             t.record_stream(st)
     for t in outs:                 # allocated on a side stream, consumed on the caller's
@@ -125,6 +126,27 @@ def convex_stage(lib: Lib, fix_s, mov_s, shape, prm: Params, ssd_buf=None):
 
 
 _SIDE = {}
+_VOL2 = {}                          # (device, shape, caller's stream) -> the backward direction's cost volume
+_FORK_LOCK = threading.Lock()
+
+
+def _second_volume(buf, main):
+    """The backward direction's cost volume, kept per (device, shape, caller's stream) -- 8.6 GB at config 2.  Allocating it per
+    call would be free for a caller that synchronises between calls, but a caller that enqueues registrations ahead of the GPU
+    would hold one volume per call in flight.  At most two are kept."""
+    key = (str(buf.device), tuple(buf.shape), int(main.cuda_stream))
+    vol = _VOL2.pop(key, None)
+    if vol is None:
+        while len(_VOL2) >= 2:
+            _VOL2.pop(next(iter(_VOL2)))
+        vol = torch.empty_like(buf)
+    _VOL2[key] = vol                # most recently used last
+    return vol
+
+
+def release_buffers():
+    """Drops the cached second cost volumes (they are re-allocated on the next call)."""
+    _VOL2.clear()
 
 
 def _side_streams(dev):
