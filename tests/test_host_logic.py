@@ -163,3 +163,18 @@ def test_translation_helpers_match_reference_formula():
     assert field_to_translation((2.5, -0.5, 1.49), (1.0, 1.0, 1.0)) == (1.0, -0.0, 2.0)        # half to even, reversed
     got = index_translation_to_world_translation((1, 2, 3), (0, 1, 0, -1, 0, 0, 0, 0, 1))
     assert np.allclose(got, [2.0, -1.0, 3.0])
+
+
+def test_overlap_setting_parses(monkeypatch):
+    """Params.overlap / CONVEXADAM_B200_OVERLAP: 0 | 1 | auto (default), anything else is an error; the explicit field wins."""
+    from convexadam_b200.pipeline import Params
+    monkeypatch.delenv("CONVEXADAM_B200_OVERLAP", raising=False)
+    assert Params().resolved_overlap() is None
+    assert Params(overlap="1").resolved_overlap() is True and Params(overlap="0").resolved_overlap() is False
+    monkeypatch.setenv("CONVEXADAM_B200_OVERLAP", "0")
+    assert Params().resolved_overlap() is False and Params(overlap="1").resolved_overlap() is True
+    monkeypatch.setenv("CONVEXADAM_B200_OVERLAP", "auto")
+    assert Params().resolved_overlap() is None
+    monkeypatch.setenv("CONVEXADAM_B200_OVERLAP", "sometimes")
+    with pytest.raises(ValueError):
+        Params().resolved_overlap()

@@ -12,19 +12,15 @@ sys.path.insert(0, ROOT)
 
 SWEEP = [
     {"CA_ADAM_GRAD": "1"},
-    {"CA_ADAM_LAYOUT": "0"},
     {},
-    {"CA_ADAM_FLIP": "1"},
-    {"CA_ADAM_FLIP": "3"},
-    {"CA_ADAM_MINB": "4"},
-    {"CA_ADAM_MINB": "6"},
-    {"CA_ADAM_MINB": "8"},
-    {"CA_ADAM_MINB": "6", "CA_ADAM_FLIP": "1"},
+    {"CA_ADAM_BX": "8", "CA_ADAM_BY": "4", "CA_ADAM_BZ": "4"},
+    {"CA_ADAM_BX": "16", "CA_ADAM_BY": "4", "CA_ADAM_BZ": "2"},
+    {"CA_ADAM_BX": "16", "CA_ADAM_BY": "2", "CA_ADAM_BZ": "4"},
+    {"CA_ADAM_BX": "8", "CA_ADAM_BY": "8", "CA_ADAM_BZ": "2"},
+    {"CA_ADAM_BX": "8", "CA_ADAM_BY": "2", "CA_ADAM_BZ": "8"},
+    {"CA_ADAM_BX": "4", "CA_ADAM_BY": "8", "CA_ADAM_BZ": "4"},
     {"CA_ADAM_BX": "32", "CA_ADAM_BY": "2", "CA_ADAM_BZ": "2"},
-    {"CA_ADAM_BX": "64", "CA_ADAM_BY": "2", "CA_ADAM_BZ": "1"},
-    {"CA_ADAM_BX": "128", "CA_ADAM_BY": "1", "CA_ADAM_BZ": "1"},
-    {"CA_ADAM_BX": "16", "CA_ADAM_BY": "8", "CA_ADAM_BZ": "1"},
-    {"CA_BOX3_LX": "6"},
+    {"CA_ADAM_BX": "32", "CA_ADAM_BY": "1", "CA_ADAM_BZ": "4"},
 ]
 
 
