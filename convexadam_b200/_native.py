@@ -53,6 +53,7 @@ _SIGS = {
     "ca_trilinear": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _f, _vp]),
     "ca_adam_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "ca_adam_run": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ca_adam_run_pools": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "ca_pack_field": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "ca_apply_convex": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "ca_field_mean_workspace_bytes": (_sz, []),
@@ -413,7 +414,9 @@ class Lib:
         self._chk(self.dll.ca_nearest_inside(self._p(inside), h, w, d, self._p(idx), self._p(ws), nb, self._stream(inside)))
         return idx
 
-    def adam_run(self, fix, mov, lambda_weight, p, m, v, first_step, niter, want_grad=False):
+    def adam_run(self, fix, mov, lambda_weight, p, m, v, first_step, niter, want_grad=False, pools=None):
+        """pools: None = the reference's B^3 (three 3-wide average pools); a sequence of odd widths = the pool-sequence smoother of
+        the self-configuring search (kovesi_spline, convexAdam_hyper_util.py:475-488)."""
         fix = self._t(fix)
         mov = self._t(mov)
         for s in (p, m, v):
@@ -426,6 +429,13 @@ class Lib:
         g = torch.empty_like(p) if want_grad else None
         nb = self.dll.ca_adam_workspace_bytes(Cn, ha, wa, da)
         ws = self._ws(nb, fix)
+        if pools is not None:
+            widths = (C.c_int * len(pools))(*[int(w) for w in pools])
+            self._chk(self.dll.ca_adam_run_pools(self._p(fix), self._p(mov), Cn, ha, wa, da, lambda_weight, self._p(p), self._p(m),
+                                                self._p(v), first_step, niter, self._p(gx), self._p(gy), self._p(gz),
+                                                C.cast(widths, C.c_void_p), len(pools), self._p(u), self._p(g),
+                                                self._p(ws), nb, self._stream(fix)))
+            return (u, g) if want_grad else u
         self._chk(self.dll.ca_adam_run(self._p(fix), self._p(mov), Cn, ha, wa, da, lambda_weight, self._p(p), self._p(m),
                                       self._p(v), first_step, niter, self._p(gx), self._p(gy), self._p(gz), self._p(u),
                                       self._p(g), self._p(ws), nb, self._stream(fix)))

@@ -534,10 +534,14 @@ extern "C" size_t ca_adam_window_workspace_bytes(int C, int ha, int wa, int da, 
 }
 extern "C" size_t ca_adam_workspace_bytes(int C, int ha, int wa, int da) { return ca_adam_window_workspace_bytes(C, ha, wa, da, 0, ha); }
 
-extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int ha, int wa, int da, int lo, int hi,
+// widths / nwidths: nullptr / 0 = the reference's three 3-wide pools (B^3, MIND.py:166); otherwise the smoother is the sequence
+// AvgPool3d(w_i, stride 1, padding (w_i - 1) / 2) of the self-configuring search (kovesi_spline, convexAdam_hyper_util.py:475-488;
+// used at adam_run_withconfig_shiftSpline.py:217).  Each pool is symmetric (zero padding, divisor w^3 everywhere), so the
+// backward of the sequence is the same pools in reverse order.
+static int adam_run_impl(const float* fix, const float* mov, int C, int ha, int wa, int da, int lo, int hi,
                                   float lambda_weight, float* p, float* m, float* v, int first_step, int niter, const float* g0x,
                                   const float* g0y, const float* g0z, float* u_out, float* g_out, void* workspace,
-                                  size_t workspace_bytes, int features_ready, ca_stream_t stream) {
+                                  size_t workspace_bytes, int features_ready, const int* widths, int nwidths, ca_stream_t stream) {
     CA_CHECK_ARG(fix && mov && p && m && v && g0x && g0y && g0z && u_out && workspace, "adam_run: null pointer");
     CA_CHECK_ARG(C > 0 && C <= 128 && ha > 1 && wa > 1 && da > 1, "adam_run: bad dims (1..128 channels, each Adam-grid axis >= 2)");
     CA_CHECK_ARG(lo >= 0 && hi <= ha && lo < hi, "adam_run: bad window [%d, %d) of %d planes", lo, hi, ha);
@@ -560,10 +564,22 @@ extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int
     float4* movcl = fixcl + n * CG;
     float* zero_row = (float*)(((uintptr_t)(movcl + n * CG) + 255) & ~(uintptr_t)255);   // da + 16 zeros for k_field_box
     // the fused B^3 kernels need float4 rows that fit shared memory; any other shape takes three generic avg_pool3d passes
-    const bool fast = (da & 3) == 0 && box3_rows_per_tile(wa, da) > 0 &&
+    const bool fast = nwidths == 0 && (da & 3) == 0 && box3_rows_per_tile(wa, da) > 0 &&
                       (((uintptr_t)p | (uintptr_t)m | (uintptr_t)v | (uintptr_t)u_out | (uintptr_t)g_out) & 15) == 0;
     (void)zero_row;
     auto box = [&](const float* in, float* out) -> int { return ca_launch_avgpool3d(in, 3, hl, wa, da, 3, 1, 1, out, st); };
+    // the pool sequence src -> dst through the two scratch fields (forward: ascending, backward: descending order)
+    auto pools = [&](const float* src, float* dst, bool reverse) -> int {
+        const float* cur = src;
+        for (int i = 0; i < nwidths; ++i) {
+            const int w = widths[reverse ? nwidths - 1 - i : i];
+            float* out = (i == nwidths - 1) ? dst : (cur == t0 ? t1 : t0);
+            const int rc = ca_launch_avgpool3d(cur, 3, hl, wa, da, w, 1, (w - 1) / 2, out, st);
+            if (rc != CA_OK) return rc;
+            cur = out;
+        }
+        return CA_OK;
+    };
     const AdamKnobs& kn = adam_knobs();
     CA_CHECK_ARG(kn.bx > 0 && kn.by > 0 && kn.bz > 0 && kn.bx * kn.by * kn.bz == 128, "adam_run: CA_ADAM_BX * BY * BZ must be 128");
     const bool planar_groups = kn.layout == 1 && kn.grad != 1;
@@ -595,6 +611,8 @@ extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int
         g.flip = (kn.flip & 1) ? (step & 1) : 0;
         if (fast) {
             if ((rc = box3_cubed(p, t0, u_out, hl, wa, da, nullptr, flip_box, st)) != CA_OK) return rc;
+        } else if (nwidths > 0) {
+            if ((rc = pools(p, u_out, false)) != CA_OK) return rc;
         } else {
             if ((rc = box(p, t0)) != CA_OK) return rc;
             if ((rc = box(t0, t1)) != CA_OK) return rc;
@@ -617,7 +635,7 @@ extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int
             CA_LAUNCH_PDL((k_adam_grad2<CA_GRAD_MINB>), ggrid, gblock, 0, st, (const float*)u_out, (const float4*)fixcl, (const float4*)movcl, CG, g, g0x, g0y, g0z, gu);
         ca_timing_end(tmg, st);
         CA_CHECK_LAUNCH("adam_grad");
-        if (!fast) {
+        if (!fast && nwidths == 0) {
             if ((rc = box(gu, t0)) != CA_OK) return rc;
             if ((rc = box(t0, t1)) != CA_OK) return rc;
         }
@@ -634,13 +652,33 @@ extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int
             // B^3 g_u fused with the Adam step; dL/dp is stored only when the caller asks for it
             if ((rc = box3_cubed(gu, t0, g_out, hl, wa, da, &upd, flip_box, st)) != CA_OK) return rc;
         } else {
-            float* gp = g_out ? g_out : t0;
-            if ((rc = box(t1, gp)) != CA_OK) return rc;
+            // (with a pool list dL/dp may overwrite g_u itself: the first pool has read it by then -- unless it is the only one)
+            float* gp = g_out ? g_out : (nwidths > 1 ? gu : t0);
+            if (nwidths > 0) { if ((rc = pools(gu, gp, true)) != CA_OK) return rc; }
+            else if ((rc = box(t1, gp)) != CA_OK) return rc;
             CA_LAUNCH(k_adam_update, dim3(adam_grid(3 * nw, 256)), dim3(256), 0, st, p, m, v, gp, 3 * nw, upd.s);
             CA_CHECK_LAUNCH("adam_update");
         }
     }
     return CA_OK;
+}
+
+extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int ha, int wa, int da, int lo, int hi,
+                                  float lambda_weight, float* p, float* m, float* v, int first_step, int niter, const float* g0x,
+                                  const float* g0y, const float* g0z, float* u_out, float* g_out, void* workspace,
+                                  size_t workspace_bytes, int features_ready, ca_stream_t stream) {
+    return adam_run_impl(fix, mov, C, ha, wa, da, lo, hi, lambda_weight, p, m, v, first_step, niter, g0x, g0y, g0z, u_out, g_out,
+                         workspace, workspace_bytes, features_ready, nullptr, 0, stream);
+}
+
+extern "C" int ca_adam_run_pools(const float* fix, const float* mov, int C, int ha, int wa, int da, float lambda_weight, float* p,
+                                 float* m, float* v, int first_step, int niter, const float* g0x, const float* g0y,
+                                 const float* g0z, const int* widths, int nwidths, float* u_out, float* g_out, void* workspace,
+                                 size_t workspace_bytes, ca_stream_t stream) {
+    CA_CHECK_ARG(widths && nwidths >= 1 && nwidths <= 16, "adam_run_pools: 1..16 pool widths (host array)");
+    for (int i = 0; i < nwidths; ++i) CA_CHECK_ARG(widths[i] >= 1 && (widths[i] & 1) == 1 && widths[i] <= 31, "adam_run_pools: pool widths must be odd, 1..31");
+    return adam_run_impl(fix, mov, C, ha, wa, da, 0, ha, lambda_weight, p, m, v, first_step, niter, g0x, g0y, g0z, u_out, g_out,
+                         workspace, workspace_bytes, 0, widths, nwidths, stream);
 }
 
 extern "C" int ca_adam_run(const float* fix, const float* mov, int C, int ha, int wa, int da, float lambda_weight, float* p,

@@ -48,8 +48,19 @@ def convex_fields(img_fixed, img_moving, settings, mind_r=1, mind_d=2, ic=True, 
     return out
 
 
+def kovesi_widths(sigma, n=4):
+    """Widths of the n average pools whose sequence approximates a Gaussian of standard deviation sigma (Kovesi's "fast almost
+    Gaussian filtering"): m pools of the lower odd width w_l (none when w_l = 1), then n - m of the upper width w_u --
+    the list `kovesi_spline(sigma, n)` builds at convexAdam_hyper_util.py:475-488."""
+    w_ideal = np.sqrt(12 * sigma ** 2 / n + 1)
+    w_u = int(np.ceil((w_ideal - 1) / 2) * 2 + 1)
+    w_l = max(w_u - 2, 1)
+    m = int(np.round((12 * sigma ** 2 - n * w_l ** 2 - 4 * n * w_l - 3 * n) / (-4 * w_l - 4)))
+    return ([w_l] * m if w_l > 1 else []) + [w_u] * (n - m)
+
+
 def adam_fields(img_fixed, img_moving, adam_settings, snapshots=(80,), grid_sp=6, disp_hw=4, selected_smooth=0, mind_r=1, mind_d=2,
-                ic=True, device=None, to_host=True):
+                ic=True, device=None, to_host=True, smoother=None):
     """The Adam stage for a list of settings on top of ONE convex stage (second half).
 
     The reference's Adam search (self_configuring/adam_run_withconfig_shiftSpline.py:159-264) restarts from the stored
@@ -60,14 +71,21 @@ def adam_fields(img_fixed, img_moving, adam_settings, snapshots=(80,), grid_sp=6
 
     adam_settings: iterable of (grid_sp_adam, lambda_weight); snapshots: increasing iteration counts.
     Returns {(grid_sp_adam, lambda_weight, niter): field}; every field is bit-identical to
-    `convex_adam_pt(..., grid_sp_adam=gsa, lambda_weight=lam, selected_niter=niter)`.  (The search's spline / Gaussian
-    regularisers, convexAdam_hyper_util.py:454-488, are not built: the regulariser is the reference's B^3, MIND.py:166.)"""
+    `convex_adam_pt(..., grid_sp_adam=gsa, lambda_weight=lam, selected_niter=niter)`.
+    smoother: None = the reference's B^3 (MIND.py:166); ("kovesi", sigma[, n]) or a sequence of odd pool widths = the
+    pool-sequence smoother of the search (`avgs[avg_n]`, adam_run_withconfig_shiftSpline.py:140-141,217; `kovesi_widths`).
+    The search's two GaussianSmoothing entries (replicate-padded 1-D convolutions, hyper_util.py:454-473) are not built."""
     lib = get_lib()
     dev = torch.device(device if device is not None else "cuda")
     fixed = torch.as_tensor(img_fixed).float()
     moving = torch.as_tensor(img_moving).float()
     if fixed.dim() != 3 or fixed.shape != moving.shape:
         raise ValueError("img_fixed and img_moving must be 3-D volumes of the same shape")
+    pools = None
+    if smoother is not None:
+        pools = kovesi_widths(*smoother[1:]) if (len(smoother) >= 2 and smoother[0] == "kovesi") else [int(w) for w in smoother]
+        if not pools or any(w < 1 or w % 2 == 0 for w in pools):
+            raise ValueError("adam_fields: the smoother must be a non-empty sequence of odd pool widths")
     snapshots = [int(n) for n in snapshots]
     if not snapshots or snapshots != sorted(set(snapshots)) or snapshots[0] < 1:
         raise ValueError("snapshots must be increasing iteration counts >= 1")
@@ -96,7 +114,7 @@ def adam_fields(img_fixed, img_moving, adam_settings, snapshots=(80,), grid_sp=6
             m, v = torch.zeros_like(p), torch.zeros_like(p)
             done = 0
             for n in snapshots:
-                u = lib.adam_run(fa, ma, lam, p, m, v, done + 1, n - done)
+                u = lib.adam_run(fa, ma, lam, p, m, v, done + 1, n - done, pools=pools)
                 done = n
                 disp = pipeline.adam_finish(lib, u, (H, W, D), prm)
                 out[(gsa, lam, n)] = lib.pack_field(disp).cpu().numpy() if to_host else disp

@@ -14,6 +14,7 @@
  *   ca_field_affine        (x/scale).flip(1), x*scale*gs     convex_adam_MIND.py:134,139,141
  *   ca_trilinear           F.interpolate(mode='trilinear')   convex_adam_MIND.py:141,153,182
  *   ca_adam_run            the Adam instance-optimisation    convex_adam_MIND.py:147-181
+ *   ca_adam_run_pools      ... with the search's pool-sequence smoother   self_configuring/adam_run_withconfig_shiftSpline.py:159-264
  *   ca_pack_field          dtype rounding + np.stack(...,3)  convex_adam_MIND.py:198-202
  *   ca_apply_convex        map_coordinates warp              apply_convex.py:13-24
  *   ca_field_mean          np.mean(field[mask], axis=0)      convex_adam_translation.py:88-96
@@ -202,6 +203,16 @@ CA_API size_t ca_adam_workspace_bytes(int C, int ha, int wa, int da);
 CA_API int ca_adam_run(const float* fix, const float* mov, int C, int ha, int wa, int da, float lambda_weight, float* p,
                 float* m, float* v, int first_step, int niter, const float* g0x, const float* g0y, const float* g0z,
                 float* u_out, float* g_out, void* workspace, size_t workspace_bytes, ca_stream_t stream);
+
+/* The same loop with the smoother of the self-configuring search in place of B^3 (self_configuring/
+ * adam_run_withconfig_shiftSpline.py:217, `avgs[avg_n](net[0].weight)` with avgs = kovesi_spline(sigma, 4),
+ * convexAdam_hyper_util.py:475-488): the sequence AvgPool3d(widths[i], stride 1, padding (widths[i]-1)/2), i = 0..nwidths-1
+ * (zero padding, divisor w^3; widths odd; `widths` is a HOST array).  Forward u = P_n ... P_1 p, backward the same pools in
+ * reverse order.  Everything else as ca_adam_run. */
+CA_API int ca_adam_run_pools(const float* fix, const float* mov, int C, int ha, int wa, int da, float lambda_weight, float* p,
+                      float* m, float* v, int first_step, int niter, const float* g0x, const float* g0y, const float* g0z,
+                      const int* widths, int nwidths, float* u_out, float* g_out, void* workspace, size_t workspace_bytes,
+                      ca_stream_t stream);
 
 /* The same on a window of the Adam grid: p, m, v, u_out, g_out hold the H planes [lo, hi) only, (3, hi-lo, wa, da);
  * fix, mov and the grid axes stay whole-grid.  Window edges that are not faces of the grid are treated like faces, so

@@ -318,6 +318,50 @@ def check_onehot(lib, device):
     assert_bits_equal(got, want, "onehot_pooled")
 
 
+def check_adam_pools(lib, device, shape=(10, 9, 12), lam=1.25):
+    """ca_adam_run_pools (the pool-sequence smoother of the self-configuring search) against a plain torch-CPU autograd
+    restatement of the reference's loop body (self_configuring/adam_run_withconfig_shiftSpline.py:213-229) with
+    avgs[avg_n] = kovesi_spline(sigma, 4) (convexAdam_hyper_util.py:475-488): u of the forward, dL/dp, and -- through the
+    conditioned bound -- p after the step; [3, 3, 3] must reproduce the B^3 path bit for bit."""
+    import torch.nn.functional as F
+    r = rng(80)
+    h, w, d = shape
+    fix = r.rand(12, *shape).astype(np.float32)
+    mov = r.rand(12, *shape).astype(np.float32)
+    p0 = (r.randn(3, *shape) * 1.5).astype(np.float32)
+    for widths in ([3, 3, 5, 5], [5], [5, 5, 5, 5], [3, 5, 5, 5]):
+        pt = torch.tensor(p0, requires_grad=True)
+        x = pt[None]
+        for wd in widths:
+            x = F.avg_pool3d(x, wd, stride=1, padding=(wd - 1) // 2)
+        ds = x.permute(0, 2, 3, 4, 1)
+        reg = lam * ((ds[0, :, 1:, :] - ds[0, :, :-1, :]) ** 2).mean() + lam * ((ds[0, 1:, :, :] - ds[0, :-1, :, :]) ** 2).mean() + \
+            lam * ((ds[0, :, :, 1:] - ds[0, :, :, :-1]) ** 2).mean()
+        scale = torch.tensor([(h - 1) / 2, (w - 1) / 2, (d - 1) / 2]).unsqueeze(0)
+        grid0 = F.affine_grid(torch.eye(3, 4).unsqueeze(0), (1, 1, h, w, d), align_corners=False)
+        grid_disp = grid0.view(-1, 3).float() + (ds.reshape(-1, 3) / scale).flip(1).float()
+        smp = F.grid_sample(torch.from_numpy(mov)[None], grid_disp.view(1, h, w, d, 3), align_corners=False, mode="bilinear")
+        loss = ((smp - torch.from_numpy(fix)[None]).pow(2).mean(1) * 12).mean()
+        (loss + reg).backward()
+        u_ref, g_ref = x.detach()[0].numpy(), pt.grad.numpy()
+        p, m, v = T(p0, device), T(np.zeros_like(p0), device), T(np.zeros_like(p0), device)
+        u, g = lib.adam_run(T(fix, device), T(mov, device), lam, p, m, v, 1, 1, want_grad=True, pools=widths)
+        eu = np.abs(N(u) - u_ref).max() / max(1.0, np.abs(u_ref).max())
+        eg = np.abs(N(g) - g_ref).max() / np.abs(g_ref).max()
+        print(f"[adam pools {widths} vs torch autograd] u rel {eu:.2e}, grad rel {eg:.2e}")
+        assert eu <= 1e-6 and eg <= 2e-6, (widths, eu, eg)      # achieved: u bit-equal, gradient <= 5.5e-7
+        p_ref = p0 - g_ref / (np.abs(g_ref) + 1e-8)              # first Adam step, lr = 1
+        bad = np.abs(N(p).astype(np.float64) - p_ref) > first_step_p_bound(N(g), g_ref) + 2e-6
+        assert not bad.any(), (widths, int(bad.sum()))
+    # three 3-wide pools are B^3: the generic pool path and the fused B^3 kernels agree to the rounding of their different
+    # summation orders (the fused kernels are separable), and two iterations through either stay together
+    pa, ma, va = T(p0, device), T(np.zeros_like(p0), device), T(np.zeros_like(p0), device)
+    pb, mb, vb = T(p0, device), T(np.zeros_like(p0), device), T(np.zeros_like(p0), device)
+    ua = lib.adam_run(T(fix, device), T(mov, device), lam, pa, ma, va, 1, 2, pools=[3, 3, 3])
+    ub = lib.adam_run(T(fix, device), T(mov, device), lam, pb, mb, vb, 1, 2)
+    assert np.abs(N(ua) - N(ub)).max() <= 1e-3 and np.median(np.abs(N(ua) - N(ub))) <= 1e-6
+
+
 def first_step_p_bound(g_a, g_b, eps=1e-8):
     """Per-element bound on |p1_a - p1_b| after the FIRST Adam step (m = v = 0, lr = 1: p1 = p0 - g / (|g| + eps)) given the two
     gradients: |dg| * sup over [g_a, g_b] of eps / (|g| + eps)^2 (the interval contains 0 when the signs differ), + 2e-6."""

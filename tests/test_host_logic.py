@@ -178,3 +178,14 @@ def test_overlap_setting_parses(monkeypatch):
     monkeypatch.setenv("CONVEXADAM_B200_OVERLAP", "sometimes")
     with pytest.raises(ValueError):
         Params().resolved_overlap()
+
+
+def test_kovesi_widths_match_reference():
+    """search.kovesi_widths against the pool widths the reference's own kovesi_spline(sigma, 4) builds (values produced in this
+    container by executing that function from /root/reference/self_configuring/convexAdam_hyper_util.py:475-488), for every sigma
+    of the search's `avgs` list (adam_run_withconfig_shiftSpline.py:140-141) and two more."""
+    from convexadam_b200.search import kovesi_widths
+    table = {0.7: [3], 1.0: [3, 3], 1.3: [3, 3, 3], 1.6: [3, 3, 3, 3], 1.9: [3, 3, 3, 5], 2.2: [3, 3, 5, 5], 2.5: [3, 5, 5, 5],
+             2.8: [5, 5, 5, 5], 3.5: [5, 5, 7, 7]}
+    for sigma, want in table.items():
+        assert kovesi_widths(sigma, 4) == want, (sigma, kovesi_widths(sigma, 4))

@@ -35,6 +35,7 @@ def test_adam(lib): kc.check_adam(lib, DEV, shape=(6, 7, 8), steps=(1, 3))
 def test_correlate_slab(lib): kc.check_correlate_slab(lib, DEV)
 def test_cc_pieces(lib): kc.check_cc_pieces(lib, DEV)
 def test_adam_window(lib): kc.check_adam_window(lib, DEV)
+def test_adam_pools(lib): kc.check_adam_pools(lib, DEV, shape=(7, 6, 8))
 def test_apply_convex(lib): kc.check_apply_convex(lib, DEV)
 
 

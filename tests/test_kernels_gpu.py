@@ -44,6 +44,7 @@ def test_correlate_slab(lib, dev):
 
 def test_cc_pieces(lib, dev): kc.check_cc_pieces(lib, dev, C=12, h=11, w=9, d=12, hw=3, cut=5)
 def test_adam_window(lib, dev): kc.check_adam_window(lib, dev, C=12, shape=(44, 10, 16))
+def test_adam_pools(lib, dev): kc.check_adam_pools(lib, dev)
 
 
 def test_coupled(lib, dev):

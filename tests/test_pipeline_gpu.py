@@ -279,3 +279,22 @@ def test_use_mask_path_vs_oracle(tmp_path):
     assert err <= 1e-4
     plain = api()(fixed, moving, dtype=torch.float32, **kw)
     assert np.abs(got - plain).max() > 1e-3          # the masks do change the result
+
+
+def test_adam_sweep_with_pool_smoother():
+    """search.adam_fields with the search's pool-sequence smoother (kovesi_spline): three 3-wide pools are the reference's B^3, so
+    that setting must land on the default path's field (the generic pools and the fused separable kernels round differently);
+    a wider spline gives a different, finite field."""
+    from convexadam_b200.search import adam_fields
+    from convexadam_b200.synth import make_pair
+    fixed, moving = make_pair((48, 42, 54), seed=5, disp_scale=0.1)
+    kw = dict(snapshots=(3, 6), grid_sp=3, disp_hw=2)
+    base = adam_fields(fixed, moving, [(2, 1.25)], **kw)
+    same = adam_fields(fixed, moving, [(2, 1.25)], smoother=("kovesi", 1.3), **kw)       # -> [3, 3, 3]
+    wide = adam_fields(fixed, moving, [(2, 1.25)], smoother=("kovesi", 2.2), **kw)       # -> [3, 3, 5, 5]
+    for key in base:
+        assert same[key].shape == base[key].shape == (48, 42, 54, 3)
+        assert np.abs(same[key] - base[key]).max() <= 1e-3, np.abs(same[key] - base[key]).max()
+        assert np.isfinite(wide[key]).all() and np.abs(wide[key] - base[key]).max() > 1e-3
+    with pytest.raises(ValueError):
+        adam_fields(fixed, moving, [(2, 1.25)], smoother=[3, 4], **kw)
