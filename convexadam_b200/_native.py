@@ -53,6 +53,7 @@ _SIGS = {
     "ca_trilinear": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _f, _vp]),
     "ca_adam_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "ca_adam_run": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ca_adam_run_gauss": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "ca_adam_run_pools": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "ca_pack_field": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "ca_apply_convex": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
@@ -414,9 +415,10 @@ class Lib:
         self._chk(self.dll.ca_nearest_inside(self._p(inside), h, w, d, self._p(idx), self._p(ws), nb, self._stream(inside)))
         return idx
 
-    def adam_run(self, fix, mov, lambda_weight, p, m, v, first_step, niter, want_grad=False, pools=None):
+    def adam_run(self, fix, mov, lambda_weight, p, m, v, first_step, niter, want_grad=False, pools=None, gauss=None):
         """pools: None = the reference's B^3 (three 3-wide average pools); a sequence of odd widths = the pool-sequence smoother of
-        the self-configuring search (kovesi_spline, convexAdam_hyper_util.py:475-488)."""
+        the self-configuring search (kovesi_spline, convexAdam_hyper_util.py:475-488).  gauss: a sequence of an odd number of
+        filter weights = its GaussianSmoothing (hyper_util.py:454-473; `search.gaussian_weights`)."""
         fix = self._t(fix)
         mov = self._t(mov)
         for s in (p, m, v):
@@ -429,6 +431,15 @@ class Lib:
         g = torch.empty_like(p) if want_grad else None
         nb = self.dll.ca_adam_workspace_bytes(Cn, ha, wa, da)
         ws = self._ws(nb, fix)
+        if gauss is not None:
+            if pools is not None:
+                raise ValueError("adam_run: pools and gauss exclude each other")
+            wts = (C.c_float * len(gauss))(*[float(w) for w in gauss])
+            self._chk(self.dll.ca_adam_run_gauss(self._p(fix), self._p(mov), Cn, ha, wa, da, lambda_weight, self._p(p), self._p(m),
+                                                self._p(v), first_step, niter, self._p(gx), self._p(gy), self._p(gz),
+                                                C.cast(wts, C.c_void_p), len(gauss), self._p(u), self._p(g),
+                                                self._p(ws), nb, self._stream(fix)))
+            return (u, g) if want_grad else u
         if pools is not None:
             widths = (C.c_int * len(pools))(*[int(w) for w in pools])
             self._chk(self.dll.ca_adam_run_pools(self._p(fix), self._p(mov), Cn, ha, wa, da, lambda_weight, self._p(p), self._p(m),

@@ -456,6 +456,36 @@ __global__ void __launch_bounds__(256) k_box3_p(Box3Args a) {
     }
 }
 
+// ---- the search's GaussianSmoothing (convexAdam_hyper_util.py:425-473): per axis, replicate padding by N/2 and a valid
+// cross-correlation with N normalised Gaussian weights, out[i] = sum_t w[t] in[clamp(i + t - N/2)].  adjoint != 0 applies the
+// transpose of that matrix (the backward of the padded convolution: what the clamped taps read is added back onto the border
+// voxel).  One thread per output element, taps in ascending order.
+struct Conv1dArgs { float w[32]; int N; };
+__global__ void __launch_bounds__(256) k_conv1d_rep(const float* __restrict__ in, float* __restrict__ out, int nc, int h, int w, int d,
+                                                    int axis, Conv1dArgs a, int adjoint) {
+    const int n = h * w * d, total = nc * n;
+    const int len = axis == 0 ? h : (axis == 1 ? w : d), stride = axis == 0 ? w * d : (axis == 1 ? d : 1), r = a.N / 2;
+    for (int o = (int)(blockIdx.x * blockDim.x + threadIdx.x); o < total; o += (int)(gridDim.x * blockDim.x)) {
+        const int v = o % n;
+        const int j = axis == 0 ? v / (w * d) : (axis == 1 ? (v / d) % w : v % d);
+        const float* line = in + (o - j * stride);
+        float acc = 0.f;
+        if (!adjoint) {
+            for (int t = 0; t < a.N; ++t) acc += a.w[t] * line[ca_min(ca_max(j + t - r, 0), len - 1) * stride];
+        } else {
+            // every (i, t) with clamp(i + t - r) == j, i ascending then t ascending
+            for (int i = ca_max(j - r, 0); i <= ca_min(j + r, len - 1); ++i) {
+                const float g = line[i * stride];
+                for (int t = 0; t < a.N; ++t) {
+                    const int q = i + t - r;
+                    if ((q == j) || (j == 0 && q < 0) || (j == len - 1 && q > len - 1)) acc += a.w[t] * g;
+                }
+            }
+        }
+        out[o] = acc;
+    }
+}
+
 static inline unsigned adam_grid(int64_t n, int block) {
     int64_t b = ca_divup(n, block);
     if (b > 148 * 32) b = 148 * 32;
@@ -541,7 +571,7 @@ extern "C" size_t ca_adam_workspace_bytes(int C, int ha, int wa, int da) { retur
 static int adam_run_impl(const float* fix, const float* mov, int C, int ha, int wa, int da, int lo, int hi,
                                   float lambda_weight, float* p, float* m, float* v, int first_step, int niter, const float* g0x,
                                   const float* g0y, const float* g0z, float* u_out, float* g_out, void* workspace,
-                                  size_t workspace_bytes, int features_ready, const int* widths, int nwidths, ca_stream_t stream) {
+                                  size_t workspace_bytes, int features_ready, const int* widths, int nwidths, const float* gauss, int ngauss, ca_stream_t stream) {
     CA_CHECK_ARG(fix && mov && p && m && v && g0x && g0y && g0z && u_out && workspace, "adam_run: null pointer");
     CA_CHECK_ARG(C > 0 && C <= 128 && ha > 1 && wa > 1 && da > 1, "adam_run: bad dims (1..128 channels, each Adam-grid axis >= 2)");
     CA_CHECK_ARG(lo >= 0 && hi <= ha && lo < hi, "adam_run: bad window [%d, %d) of %d planes", lo, hi, ha);
@@ -564,10 +594,23 @@ static int adam_run_impl(const float* fix, const float* mov, int C, int ha, int 
     float4* movcl = fixcl + n * CG;
     float* zero_row = (float*)(((uintptr_t)(movcl + n * CG) + 255) & ~(uintptr_t)255);   // da + 16 zeros for k_field_box
     // the fused B^3 kernels need float4 rows that fit shared memory; any other shape takes three generic avg_pool3d passes
-    const bool fast = nwidths == 0 && (da & 3) == 0 && box3_rows_per_tile(wa, da) > 0 &&
+    const bool fast = nwidths == 0 && ngauss == 0 && (da & 3) == 0 && box3_rows_per_tile(wa, da) > 0 &&
                       (((uintptr_t)p | (uintptr_t)m | (uintptr_t)v | (uintptr_t)u_out | (uintptr_t)g_out) & 15) == 0;
     (void)zero_row;
     auto box = [&](const float* in, float* out) -> int { return ca_launch_avgpool3d(in, 3, hl, wa, da, 3, 1, 1, out, st); };
+    // the Gaussian smoother (forward: axes 0, 1, 2; backward: the transposed filters along 2, 1, 0), src -> dst through t0, t1
+    Conv1dArgs cw;
+    cw.N = ngauss;
+    for (int i = 0; i < 32; ++i) cw.w[i] = (gauss && i < ngauss) ? gauss[i] : 0.f;
+    auto gaussian = [&](const float* src, float* dst, bool adjoint) -> int {
+        const unsigned gb = adam_grid(3 * nw, 256);
+        const int ax[3] = {adjoint ? 2 : 0, 1, adjoint ? 0 : 2};
+        CA_LAUNCH(k_conv1d_rep, dim3(gb), dim3(256), 0, st, src, t0, 3, hl, wa, da, ax[0], cw, (int)adjoint);
+        CA_LAUNCH(k_conv1d_rep, dim3(gb), dim3(256), 0, st, (const float*)t0, t1, 3, hl, wa, da, ax[1], cw, (int)adjoint);
+        CA_LAUNCH(k_conv1d_rep, dim3(gb), dim3(256), 0, st, (const float*)t1, dst, 3, hl, wa, da, ax[2], cw, (int)adjoint);
+        CA_CHECK_LAUNCH("adam/gaussian");
+        return CA_OK;
+    };
     // the pool sequence src -> dst through the two scratch fields (forward: ascending, backward: descending order)
     auto pools = [&](const float* src, float* dst, bool reverse) -> int {
         const float* cur = src;
@@ -613,6 +656,8 @@ static int adam_run_impl(const float* fix, const float* mov, int C, int ha, int 
             if ((rc = box3_cubed(p, t0, u_out, hl, wa, da, nullptr, flip_box, st)) != CA_OK) return rc;
         } else if (nwidths > 0) {
             if ((rc = pools(p, u_out, false)) != CA_OK) return rc;
+        } else if (ngauss > 0) {
+            if ((rc = gaussian(p, u_out, false)) != CA_OK) return rc;
         } else {
             if ((rc = box(p, t0)) != CA_OK) return rc;
             if ((rc = box(t0, t1)) != CA_OK) return rc;
@@ -635,7 +680,7 @@ static int adam_run_impl(const float* fix, const float* mov, int C, int ha, int 
             CA_LAUNCH_PDL((k_adam_grad2<CA_GRAD_MINB>), ggrid, gblock, 0, st, (const float*)u_out, (const float4*)fixcl, (const float4*)movcl, CG, g, g0x, g0y, g0z, gu);
         ca_timing_end(tmg, st);
         CA_CHECK_LAUNCH("adam_grad");
-        if (!fast && nwidths == 0) {
+        if (!fast && nwidths == 0 && ngauss == 0) {
             if ((rc = box(gu, t0)) != CA_OK) return rc;
             if ((rc = box(t0, t1)) != CA_OK) return rc;
         }
@@ -653,8 +698,9 @@ static int adam_run_impl(const float* fix, const float* mov, int C, int ha, int 
             if ((rc = box3_cubed(gu, t0, g_out, hl, wa, da, &upd, flip_box, st)) != CA_OK) return rc;
         } else {
             // (with a pool list dL/dp may overwrite g_u itself: the first pool has read it by then -- unless it is the only one)
-            float* gp = g_out ? g_out : (nwidths > 1 ? gu : t0);
+            float* gp = g_out ? g_out : ((nwidths > 1 || ngauss > 0) ? gu : t0);
             if (nwidths > 0) { if ((rc = pools(gu, gp, true)) != CA_OK) return rc; }
+            else if (ngauss > 0) { if ((rc = gaussian(gu, gp, true)) != CA_OK) return rc; }
             else if ((rc = box(t1, gp)) != CA_OK) return rc;
             CA_LAUNCH(k_adam_update, dim3(adam_grid(3 * nw, 256)), dim3(256), 0, st, p, m, v, gp, 3 * nw, upd.s);
             CA_CHECK_LAUNCH("adam_update");
@@ -668,7 +714,7 @@ extern "C" int ca_adam_run_window(const float* fix, const float* mov, int C, int
                                   const float* g0y, const float* g0z, float* u_out, float* g_out, void* workspace,
                                   size_t workspace_bytes, int features_ready, ca_stream_t stream) {
     return adam_run_impl(fix, mov, C, ha, wa, da, lo, hi, lambda_weight, p, m, v, first_step, niter, g0x, g0y, g0z, u_out, g_out,
-                         workspace, workspace_bytes, features_ready, nullptr, 0, stream);
+                         workspace, workspace_bytes, features_ready, nullptr, 0, nullptr, 0, stream);
 }
 
 extern "C" int ca_adam_run_pools(const float* fix, const float* mov, int C, int ha, int wa, int da, float lambda_weight, float* p,
@@ -678,7 +724,16 @@ extern "C" int ca_adam_run_pools(const float* fix, const float* mov, int C, int 
     CA_CHECK_ARG(widths && nwidths >= 1 && nwidths <= 16, "adam_run_pools: 1..16 pool widths (host array)");
     for (int i = 0; i < nwidths; ++i) CA_CHECK_ARG(widths[i] >= 1 && (widths[i] & 1) == 1 && widths[i] <= 31, "adam_run_pools: pool widths must be odd, 1..31");
     return adam_run_impl(fix, mov, C, ha, wa, da, 0, ha, lambda_weight, p, m, v, first_step, niter, g0x, g0y, g0z, u_out, g_out,
-                         workspace, workspace_bytes, 0, widths, nwidths, stream);
+                         workspace, workspace_bytes, 0, widths, nwidths, nullptr, 0, stream);
+}
+
+extern "C" int ca_adam_run_gauss(const float* fix, const float* mov, int C, int ha, int wa, int da, float lambda_weight, float* p,
+                                 float* m, float* v, int first_step, int niter, const float* g0x, const float* g0y,
+                                 const float* g0z, const float* weights, int nweights, float* u_out, float* g_out, void* workspace,
+                                 size_t workspace_bytes, ca_stream_t stream) {
+    CA_CHECK_ARG(weights && nweights >= 1 && nweights <= 31 && (nweights & 1) == 1, "adam_run_gauss: an odd number (1..31) of filter weights (host array)");
+    return adam_run_impl(fix, mov, C, ha, wa, da, 0, ha, lambda_weight, p, m, v, first_step, niter, g0x, g0y, g0z, u_out, g_out,
+                         workspace, workspace_bytes, 0, nullptr, 0, weights, nweights, stream);
 }
 
 extern "C" int ca_adam_run(const float* fix, const float* mov, int C, int ha, int wa, int da, float lambda_weight, float* p,

@@ -59,6 +59,16 @@ def kovesi_widths(sigma, n=4):
     return ([w_l] * m if w_l > 1 else []) + [w_u] * (n - m)
 
 
+def gaussian_weights(sigma):
+    """The normalised filter weights of the reference's GaussianSmoothing(sigma), computed with the same float32 torch operations
+    (convexAdam_hyper_util.py:458-464): N = 2 ceil(1.5 sigma) + 1 taps."""
+    sg = torch.tensor([float(sigma)])
+    N = int(torch.ceil(sg * 3.0 / 2.0).long().item()) * 2 + 1
+    weight = torch.exp(-torch.pow(torch.linspace(-(N // 2), N // 2, N), 2) / (2 * torch.pow(sg, 2)))
+    weight /= weight.sum()
+    return [float(x) for x in weight]
+
+
 def adam_fields(img_fixed, img_moving, adam_settings, snapshots=(80,), grid_sp=6, disp_hw=4, selected_smooth=0, mind_r=1, mind_d=2,
                 ic=True, device=None, to_host=True, smoother=None):
     """The Adam stage for a list of settings on top of ONE convex stage (second half).
@@ -73,16 +83,18 @@ def adam_fields(img_fixed, img_moving, adam_settings, snapshots=(80,), grid_sp=6
     Returns {(grid_sp_adam, lambda_weight, niter): field}; every field is bit-identical to
     `convex_adam_pt(..., grid_sp_adam=gsa, lambda_weight=lam, selected_niter=niter)`.
     smoother: None = the reference's B^3 (MIND.py:166); ("kovesi", sigma[, n]) or a sequence of odd pool widths = the
-    pool-sequence smoother of the search (`avgs[avg_n]`, adam_run_withconfig_shiftSpline.py:140-141,217; `kovesi_widths`).
-    The search's two GaussianSmoothing entries (replicate-padded 1-D convolutions, hyper_util.py:454-473) are not built."""
+    pool-sequence smoother of the search (`avgs[avg_n]`, adam_run_withconfig_shiftSpline.py:140-141,217; `kovesi_widths`);
+    ("gauss", sigma) = its GaussianSmoothing(sigma) (replicate-padded separable filter, hyper_util.py:454-473)."""
     lib = get_lib()
     dev = torch.device(device if device is not None else "cuda")
     fixed = torch.as_tensor(img_fixed).float()
     moving = torch.as_tensor(img_moving).float()
     if fixed.dim() != 3 or fixed.shape != moving.shape:
         raise ValueError("img_fixed and img_moving must be 3-D volumes of the same shape")
-    pools = None
-    if smoother is not None:
+    pools = gauss = None
+    if smoother is not None and len(smoother) == 2 and smoother[0] == "gauss":
+        gauss = gaussian_weights(smoother[1])
+    elif smoother is not None:
         pools = kovesi_widths(*smoother[1:]) if (len(smoother) >= 2 and smoother[0] == "kovesi") else [int(w) for w in smoother]
         if not pools or any(w < 1 or w % 2 == 0 for w in pools):
             raise ValueError("adam_fields: the smoother must be a non-empty sequence of odd pool widths")
@@ -114,7 +126,7 @@ def adam_fields(img_fixed, img_moving, adam_settings, snapshots=(80,), grid_sp=6
             m, v = torch.zeros_like(p), torch.zeros_like(p)
             done = 0
             for n in snapshots:
-                u = lib.adam_run(fa, ma, lam, p, m, v, done + 1, n - done, pools=pools)
+                u = lib.adam_run(fa, ma, lam, p, m, v, done + 1, n - done, pools=pools, gauss=gauss)
                 done = n
                 disp = pipeline.adam_finish(lib, u, (H, W, D), prm)
                 out[(gsa, lam, n)] = lib.pack_field(disp).cpu().numpy() if to_host else disp

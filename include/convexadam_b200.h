@@ -14,7 +14,7 @@
  *   ca_field_affine        (x/scale).flip(1), x*scale*gs     convex_adam_MIND.py:134,139,141
  *   ca_trilinear           F.interpolate(mode='trilinear')   convex_adam_MIND.py:141,153,182
  *   ca_adam_run            the Adam instance-optimisation    convex_adam_MIND.py:147-181
- *   ca_adam_run_pools      ... with the search's pool-sequence smoother   self_configuring/adam_run_withconfig_shiftSpline.py:159-264
+ *   ca_adam_run_pools, ca_adam_run_gauss   ... with the search's smoothers   self_configuring/adam_run_withconfig_shiftSpline.py:140-141,217
  *   ca_pack_field          dtype rounding + np.stack(...,3)  convex_adam_MIND.py:198-202
  *   ca_apply_convex        map_coordinates warp              apply_convex.py:13-24
  *   ca_field_mean          np.mean(field[mask], axis=0)      convex_adam_translation.py:88-96
@@ -212,6 +212,14 @@ CA_API int ca_adam_run(const float* fix, const float* mov, int C, int ha, int wa
 CA_API int ca_adam_run_pools(const float* fix, const float* mov, int C, int ha, int wa, int da, float lambda_weight, float* p,
                       float* m, float* v, int first_step, int niter, const float* g0x, const float* g0y, const float* g0z,
                       const int* widths, int nwidths, float* u_out, float* g_out, void* workspace, size_t workspace_bytes,
+                      ca_stream_t stream);
+
+/* ... and with the search's GaussianSmoothing(sigma) (convexAdam_hyper_util.py:454-473 over filter1D, :425-437): along each axis in
+ * turn, replicate padding by nweights/2 and a valid cross-correlation with the nweights normalised weights (a HOST array,
+ * computed by the caller as the reference computes them); backward = the transposed filters in reverse axis order. */
+CA_API int ca_adam_run_gauss(const float* fix, const float* mov, int C, int ha, int wa, int da, float lambda_weight, float* p,
+                      float* m, float* v, int first_step, int niter, const float* g0x, const float* g0y, const float* g0z,
+                      const float* weights, int nweights, float* u_out, float* g_out, void* workspace, size_t workspace_bytes,
                       ca_stream_t stream);
 
 /* The same on a window of the Adam grid: p, m, v, u_out, g_out hold the H planes [lo, hi) only, (3, hi-lo, wa, da);

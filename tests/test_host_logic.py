@@ -189,3 +189,15 @@ def test_kovesi_widths_match_reference():
              2.8: [5, 5, 5, 5], 3.5: [5, 5, 7, 7]}
     for sigma, want in table.items():
         assert kovesi_widths(sigma, 4) == want, (sigma, kovesi_widths(sigma, 4))
+
+
+def test_gaussian_weights_match_reference():
+    """search.gaussian_weights against the weights the reference's own GaussianSmoothing(sigma) holds (bit patterns produced in this
+    container by executing that class from /root/reference/self_configuring/convexAdam_hyper_util.py:454-464)."""
+    from convexadam_b200.search import gaussian_weights
+    table = {0.7: ['0x1.3b3ae40000000p-7', '0x1.a4b52e0000000p-3', '0x1.23cb920000000p-1', '0x1.a4b52e0000000p-3', '0x1.3b3ae40000000p-7'],
+             1.0: ['0x1.be5f100000000p-5', '0x1.f41fd80000000p-3', '0x1.9c48680000000p-2', '0x1.f41fd80000000p-3', '0x1.be5f100000000p-5'],
+             2.0: ['0x1.1f5f620000000p-4', '0x1.0c70fc0000000p-3', '0x1.8694700000000p-3', '0x1.ba95be0000000p-3', '0x1.8694700000000p-3',
+                   '0x1.0c70fc0000000p-3', '0x1.1f5f620000000p-4']}
+    for sigma, want in table.items():
+        assert [float.hex(x) for x in gaussian_weights(sigma)] == want, sigma

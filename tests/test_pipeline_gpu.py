@@ -296,5 +296,8 @@ def test_adam_sweep_with_pool_smoother():
         assert same[key].shape == base[key].shape == (48, 42, 54, 3)
         assert np.abs(same[key] - base[key]).max() <= 1e-3, np.abs(same[key] - base[key]).max()
         assert np.isfinite(wide[key]).all() and np.abs(wide[key] - base[key]).max() > 1e-3
+    gauss = adam_fields(fixed, moving, [(2, 1.25)], smoother=("gauss", 0.7), **kw)      # the search's GaussianSmoothing(.7)
+    for key in base:
+        assert np.isfinite(gauss[key]).all() and np.abs(gauss[key] - base[key]).max() > 1e-3
     with pytest.raises(ValueError):
         adam_fields(fixed, moving, [(2, 1.25)], smoother=[3, 4], **kw)
