@@ -357,10 +357,12 @@ def main():
         t0 = time.perf_counter()
         # N > 1: the ranks are independent workers, not a lockstep job.  Started together they would all copy their 189 MB
         # result to the host at the same instants and queue on the host's memory path; each rank therefore starts rank/N of
-        # a step late -- INSIDE the timed region, so the delay is paid for in the number reported.
+        # a step late (at most one copy time per rank) -- INSIDE the timed region, so the delay is paid for in the number reported.
         stagger = 0.0
         if world > 1 and os.environ.get("BENCH_E2E_STAGGER", "1") == "1":
-            stagger = rank * (ms / steps / 1e3) / world
+            # spacing = one rank's copy time at full PCIe rate (enough to take the copies apart), at most 1/N of a step
+            copy_s = (2 * fixed.numel() * 4 + 3 * fixed.numel() * 8) / 50e9
+            stagger = rank * min((ms / steps / 1e3) / world, copy_s)
             time.sleep(stagger)
         for _ in range(steps):
             out = convex_adam_pt(fixed_pin, moving_pin, **kw)
