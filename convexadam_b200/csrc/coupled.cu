@@ -547,6 +547,9 @@ __global__ void __launch_bounds__(128, 5) k_cost_argmin_pruned(const float* __re
 // only on kH, kW, kD, so the squared distances split into per-axis terms that are computed once per slab (kD), once per
 // block (kW) and once per label (kH) -- in the reference's rounded operations, so every cost and every bound is the
 // value the generic kernel computes, bit for bit, at less than half the instructions.
+#ifndef CA_SEP1_MINB
+#define CA_SEP1_MINB 8      // resident CTAs the one-voxel form of the selection pass is compiled for (55 registers); 10 / 12 (48 / 40 registers, no spills) measured slower: 2.94 / 2.92 against 2.77 ms per direction
+#endif
 // VEC consecutive floats as one streaming load
 template <int VEC>
 static __device__ __forceinline__ void cc_ld_vec(const float* p, float (&o)[VEC]) {
@@ -562,7 +565,7 @@ static __device__ __forceinline__ void cc_ld_vec(const float* p, float (&o)[VEC]
 }
 
 template <int VEC, int S, bool CERT, int BG = 4>
-__global__ void __launch_bounds__(128, VEC == 4 ? 5 : 8) k_cost_argmin_sep(const float* __restrict__ ssd, const float* __restrict__ bmin,
+__global__ void __launch_bounds__(128, VEC == 4 ? 5 : (VEC == 1 ? CA_SEP1_MINB : 8)) k_cost_argmin_sep(const float* __restrict__ ssd, const float* __restrict__ bmin,
                                                             const float* __restrict__ smin, int64_t n, const float4* __restrict__ boxes,
                                                             const float* __restrict__ soft, float coeff, int row_len, int rpw,
                                                             const unsigned long long* __restrict__ prev,
